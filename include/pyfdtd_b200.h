@@ -1,0 +1,188 @@
+/*
+ * pyfdtd_b200.h -- C-ABI of libpyfdtd_b200.so, the sm_100a implementation of the Py-FDTD_PIC
+ * time-stepping hot path.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross this boundary.
+ *   - Every `double*` / `int*` inside PfGrid and the PIC structs is a DEVICE pointer (the Python
+ *     host layer takes them from torch.Tensor.data_ptr(); torch is only the buffer carrier).
+ *     PfGrid structs themselves and the `const int* T_total`-style arrays are HOST memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls enqueue
+ *     work and return; pf_sync() or the caller's own stream sync waits for it.
+ *   - Return value: 0 = ok, <0 = PF_E_* (pf_last_error() gives text).  The reference reports
+ *     errors by print+sys.exit (Environment_Setup.py:59-155, BaseFDTD11.py:36-66); the Python
+ *     layer turns these codes into exceptions.
+ *   - The library never allocates caller-visible memory; scratch is provided by the caller and
+ *     sized by the pf_*_scratch_bytes() queries.
+ *
+ * All arrays of one grid have length L = Nz+1 (MasterController.py:149-159), indices are the
+ * reference's own cell indices.
+ */
+#ifndef PYFDTD_B200_H
+#define PYFDTD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+
+enum { PF_OK = 0, PF_E_ARG = -1, PF_E_CUDA = -2, PF_E_UNSUPPORTED = -3, PF_E_SCRATCH = -4 };
+
+/* integrator selector: which Solver_Engine.Integrator*1D loop body is run */
+enum {
+    PF_FREE = 0,    /* Solver_Engine.py:167-183  IntegratorFreeSpace1D */
+    PF_LORENTZ = 1, /* Solver_Engine.py:294-316  IntegratorLinLor1D    */
+    PF_NL = 2       /* Solver_Engine.py:236-261  IntegratorNL1D        */
+};
+
+/* engine selector for pf_run_pass / pf_run_batch */
+enum {
+    PF_ENGINE_OPS = 0, /* one kernel per reference leaf op, general per-cell coefficient arrays   */
+    PF_ENGINE_TILE = 1 /* fused, register/shared-memory resident, k-step temporally blocked tiles;
+                          requires PfGrid.canonical (see below)                                   */
+};
+
+/* flags for PfGrid.flags */
+enum {
+    PF_F_TFSF = 1,      /* P.TFSF                                              */
+    PF_F_CPML_M = 2,    /* P.CPMLXm                                            */
+    PF_F_CPML_P = 4,    /* P.CPMLXp                                            */
+    PF_F_CANONICAL = 8, /* coefficient arrays have the piecewise form the tile engine assumes:
+                           denE = denH = UpHySelf = 1, bmY == beX, Jx absent/0,
+                           UpExMat/UpHyMat constant outside [mf,mr) and constant inside,
+                           Cb[nz] == UpExMat[nz] and C2[nz] == c2_pml on the CPML correction
+                           ranges and 0 at nz = L-pw (BaseFDTD11.py:306-330).  Set by the host
+                           layer after checking the arrays bit for bit.                          */
+    PF_F_FMA = 16       /* allow fused multiply-add contraction (faster, not bit-identical to the
+                           reference's un-contracted fp64 arithmetic; <= 1e-10 relative)         */
+};
+
+/* One 1-D grid: a single simulation, one sweep member, or one rank's slab of a long grid.
+ * Mirrors the arrays of the reference's Variables / CPML_Variables jitclasses
+ * (MasterController.py:145-210, 401-434) that the hot loop touches. */
+typedef struct PfGrid {
+    /* geometry (Params, MasterController.py:287-336) */
+    int32_t L;        /* Nz+1                                                                    */
+    int32_t pw;       /* pmlWidth                                                                */
+    int32_t mf, mr;   /* materialFrontEdge, materialRearEdge: slab = [mf, mr)                    */
+    int32_t nzsrc;    /* source cell; TF/SF correction is applied to Hy[nzsrc-1]                 */
+    int32_t flags;    /* PF_F_*                                                                  */
+    int32_t n_probes; /* number of probe cells                                                   */
+    int32_t probe_stride; /* row length of probe_out (= timeSteps)                               */
+    /* global-index window for domain decomposition: this grid holds cells [z0, z0+L) of a global
+     * grid of Lg cells (z0 = 0, Lg = L for an undecomposed grid).  Index-dependent rules (update
+     * ranges, CPML ranges, slab, source, probes) are evaluated on global indices.               */
+    int64_t z0, Lg;
+    /* scalars */
+    double dt_over_dz;          /* P.delT/P.dz                         BaseFDTD11.py:753         */
+    double eps0;                /* P.permit_0                                                    */
+    double polA, polB, polC;    /* Lorentz ADE                         BaseFDTD11.py:620-626     */
+    double cub_a, cub_b, cub_c; /* cubic coefficients cub, qua, one    BaseFDTD11.py:808-810     */
+    double nl_den0, nl_den1;    /* eps0*sqrt(1.2), eps0*chi3Stat       BaseFDTD11.py:864-869     */
+    /* canonical-form scalars (used by the tile engine only) */
+    double cE0, cE1;            /* UpExMat outside / inside [mf,mr)                              */
+    double cH0, cH1;            /* UpHyMat outside / inside [mf,mr)                              */
+    double c2_pml;              /* C2 on the CPML ranges (delT/mu0)                              */
+    /* state (read and written) */
+    double *Ex, *Hy, *Dx, *P, *Pprev, *psiE, *psiH, *Acubic;
+    /* coefficients (read only); Jx may be NULL (= 0, the PIC current slot, BaseFDTD11.py:667)   */
+    const double *Jx, *UpExMat, *denE, *UpHySelf, *UpHyMat, *denH;
+    const double *beX, *ceX, *Cb, *bmY, *cmY, *C2;
+    /* per-step source terms, indexed by absolute step n:
+     *   srcE[n] = Exs[n]/P.courantNo, srcH[n] = Hys[n]/P.courantNo   Solver_Engine.py:307-310   */
+    const double *srcE, *srcH;
+    /* probes: Ex[probe_idx[p]] after step n -> probe_out[p*probe_stride + n]
+     * (Solver_Engine.probeSim :16-54; windowing of x1ColBe/x1ColAf is applied by the host layer) */
+    const int32_t *probe_idx;
+    double *probe_out;
+} PfGrid;
+
+/* ---- library / device ------------------------------------------------------------------- */
+int pf_abi_version(void);
+const char *pf_last_error(void);
+/* fills sm_count, cc_major, cc_minor, free/total bytes; returns PF_E_CUDA without a device      */
+int pf_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *free_bytes, size_t *total_bytes);
+int pf_sync(void *stream);
+/* number of kernels this library has launched since load (bench.py's gpu_launches)             */
+unsigned long long pf_launch_count(void);
+
+/* ---- leaf ops: one call = one reference leaf function on one grid ---------------------- */
+int pf_ade_ex_update(const PfGrid *g, void *stream);        /* BaseFDTD11.py:663-669  ADE_ExUpdate               */
+int pf_ade_hy_update(const PfGrid *g, void *stream);        /* BaseFDTD11.py:640-656  ADE_HyUpdate               */
+int pf_cpml_psi_e_update(const PfGrid *g, void *stream);    /* BaseFDTD11.py:364-376  CPML_Psi_e_Update          */
+int pf_cpml_psi_m_update(const PfGrid *g, void *stream);    /* BaseFDTD11.py:381-393  CPML_Psi_m_Update          */
+int pf_source_inject(const PfGrid *g, int n, void *stream); /* Solver_Engine.py:307-310                          */
+int pf_ade_dx_update(const PfGrid *g, void *stream);        /* BaseFDTD11.py:750-760  ADE_DxUpdate               */
+int pf_ade_polarisation_update(const PfGrid *g, void *stream); /* BaseFDTD11.py:487-538 + 609-633 (history shift + ADE) */
+int pf_ade_ex_create(const PfGrid *g, void *stream);        /* BaseFDTD11.py:712-725  ADE_ExCreate               */
+int pf_acubic_finder(const PfGrid *g, void *stream);        /* BaseFDTD11.py:793-853  AcubicFinder + cubic solve */
+int pf_nonlin_ex_update(const PfGrid *g, void *stream);     /* BaseFDTD11.py:858-877  NonLinExUpdate             */
+int pf_probe_record(const PfGrid *g, int n, void *stream);  /* Solver_Engine.py:16-54 probeSim                   */
+/* CubicEquationSolver.solve root[0] (CubicEquationSolver.py:29-105) for n polynomials,
+ * coeffs = [n][4] (a,b,c,d) device, root0 = [n] device                                          */
+int pf_cubic_root0(const double *coeffs, double *root0, int n, void *stream);
+
+/* ---- integrator passes ------------------------------------------------------------------ */
+/* One pass of `nsteps` steps starting at absolute step n0 on ONE grid: the body of the
+ * `for counts in range(P.timeSteps)` loop of Solver_Engine.Integrator{FreeSpace,LinLor,NL}1D
+ * (Solver_Engine.py:167 / 294 / 236).  do_pol = 1 runs the polarisation update (pass i==1 of the
+ * Lorentz integrator).  snap_out (may be NULL): Ex is copied to row n/snap_interval after step
+ * n whenever n>0 and n % snap_interval == 0 and row < snap_rows (Solver_Engine.vidMake :57-68).
+ * scratch: pf_run_scratch_bytes(g,1,engine) bytes of device memory (may be NULL for ENGINE_OPS). */
+int pf_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, int engine,
+                double *snap_out, int snap_interval, int snap_rows,
+                void *scratch, size_t scratch_bytes, void *stream);
+
+/* The same pass over n_grids independent grids (the members of a LoopedSim sweep,
+ * MasterController.py:543-563), fused: every launch advances every member by k steps.
+ * Members may differ in every field of PfGrid; nsteps[m] gives each member's step count
+ * (members that finish early idle).  k_block = steps per launch (0 = library default).          */
+int pf_run_batch(const PfGrid *grids, int n_grids, int mode, int do_pol, int n0, const int *nsteps,
+                 int k_block, void *scratch, size_t scratch_bytes, void *stream);
+size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine);
+
+/* tile-engine introspection (bench / tests): tile width in cells, max k, threads per CTA       */
+int pf_tile_config(int *tile_cells, int *k_max, int *threads);
+
+/* ---- halo exchange support for 1-D domain decomposition (config 5) --------------------- */
+/* Pack / unpack the k-cell ghost zones of every state array of grid g into / from a contiguous
+ * buffer (order: Ex,Hy,Dx,P,Pprev,psiE,psiH; arrays the mode does not use are skipped).
+ * side: 0 = left edge, 1 = right edge.  `interior`=1 packs the k owned cells next to the edge
+ * (to send), 0 addresses the k ghost cells (to receive).  Returns doubles moved, <0 on error.  */
+long long pf_halo_pack(const PfGrid *g, int mode, int side, int k, double *buf, void *stream);
+long long pf_halo_unpack(const PfGrid *g, int mode, int side, int k, const double *buf, void *stream);
+
+/* ---- PIC (builder-defined spec; the reference only has the Jx slot) ------ */
+typedef struct PfPic {
+    int64_t n;            /* macro-particles                                                     */
+    int32_t L;            /* grid cells (Nz+1)                                                   */
+    int32_t _pad;
+    double dz, dt;        /* grid spacing / time step                                            */
+    double q_over_m;      /* charge/mass of the species [C/kg]                                   */
+    double c;             /* speed of light                                                      */
+    double mu0;           /* By = mu0*Hy                                                         */
+    double jx_scale;      /* Jx_slot contribution per particle = jx_scale * w * vx * shape       */
+    /* particle SoA (device): position z [m], momenta ux = gamma*vx, uz = gamma*vz [m/s], weight */
+    double *z, *ux, *uz, *w;
+    int32_t *cell;        /* cell index floor(z/dz), maintained by push                          */
+    /* fields (device, length L): Ex at integer nodes, Hy at half nodes nz+1/2                   */
+    const double *Ex, *Hy;
+    double *Jx;           /* output current slot, length L (overwritten by deposit)             */
+} PfPic;
+
+/* relativistic Boris push + linear (CIC) field gather; updates z, ux, uz, cell                  */
+int pf_pic_push(const PfPic *p, void *stream);
+/* sort particles by cell (stable; keys = cell); scratch sized by pf_pic_scratch_bytes          */
+int pf_pic_sort(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
+/* deterministic cell-sorted deposition of Jx (requires particles sorted by cell)               */
+int pf_pic_deposit(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
+size_t pf_pic_scratch_bytes(const PfPic *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYFDTD_B200_H */

@@ -1,0 +1,360 @@
+"""Field / CPML / ADE / cubic update functions and the coefficient builders of the hot path.
+
+Mirror of the reference's ``BaseFDTD11`` module (same function names, arguments and return values):
+
+* Setup functions (run once per pass, O(Nz)) stay on the host and reproduce the reference's values
+  bit for bit: functions the reference compiles with numba call libm ``exp``/``pow``, so they are
+  evaluated here with ``math.exp``/``math.pow``; functions the reference runs in plain Python call
+  the same numpy routines in the same order.
+* Per-step leaf ops (``ADE_ExUpdate`` ... ``NonLinExUpdate``) launch the matching sm_100a kernel
+  through the C-ABI (``pf_ade_ex_update`` ...).  They exist for drop-in completeness and tests; the
+  integrators in Solver_Engine never call them per step but hand the whole time loop to the library.
+
+There is no CPU fallback for the leaf ops: without the CUDA library / a GPU they raise.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import _device as dev
+from . import _native as nat
+
+LIFT_SIZE_GUARDS = False  # opt-in for the long-grid configuration (reference caps: Nz<=25000, T<=2**17)
+
+
+# ------------------------------------------------------------------------------------------------ setup
+def FieldInit(V, P):
+    """BaseFDTD11.py:36-82 -- argument guards, then zeroed field arrays."""
+    if type(P.Nz) != int:
+        raise TypeError("Grid spaces must be a positive integer value")
+    if type(P.timeSteps) != int:
+        raise TypeError("Number of timeSteps must be positive integer valued")
+    if not LIFT_SIZE_GUARDS:
+        if P.timeSteps > 2 ** 17:
+            raise ValueError("timeSteps max too large")
+        if P.Nz > 25000:
+            raise ValueError("Grid size too big")
+    if P.Nz == 0:
+        raise ValueError("Cannot have grid size 0!")
+    if P.timeSteps == 0:
+        raise ValueError("Cannot have zero timeSteps!")
+    if P.Nz < 0:
+        raise ValueError("Grid size cannot be negative")
+    if P.timeSteps < 0:
+        raise ValueError("Cannot have negative timeSteps")
+    L = P.Nz + 1
+    for name in ("Ex", "Hy", "polarisationCurr", "Dx", "tempVarPol", "tempTempVarPol", "tempVarE", "tempTempVarE"):
+        setattr(V, name, np.zeros(L))
+    return (V.tempVarPol, V.tempTempVarE, V.tempVarE, V.tempTempVarPol, V.polarisationCurr, V.Ex, V.Dx, V.Hy)
+
+
+def Gaussian(V, P):
+    """BaseFDTD11.py:86-96 -- the broadband pulse (t is the integer step index)."""
+    t = np.arange(P.timeSteps)
+    width = 200
+    delay = width * 2.2
+    arg = ((t - delay) * (t - delay)) / (width * width) * np.cos(2 * np.pi * P.freq_in * (t - delay))
+    return P.Amplitude * (np.exp(-arg) * 2) / P.courantNo
+
+
+def SmoothTurnOn(V, P, tempfreq=0):
+    """BaseFDTD11.py:104-120 -- sine that is switched off after P.Periods periods."""
+    frq = tempfreq if tempfreq != 0 else P.freq_in
+    ppw = P.c0 / (frq * P.dz)
+    n = np.arange(P.timeSteps)
+    on = n * P.delT < P.period * P.Periods
+    w = 2.0 * np.pi / ppw
+    Exs = np.where(on, np.sin(w * (P.courantNo * n)), 0.0)
+    Hys = np.where(on, np.sin(w * (P.courantNo * (n + 1))), 0.0)
+    return Exs, Hys
+
+
+def EmptySpaceCalc(V, P):
+    """BaseFDTD11.py:124-132 -- vacuum update coefficients everywhere."""
+    L = P.Nz + 1
+    V.UpHyMat = np.full(L, (1 / P.CharImp) * P.courantNo)
+    V.UpExMat = np.full(L, P.CharImp * P.courantNo)
+    return V.UpHyMat, V.UpExMat
+
+
+def Material(V, P):
+    """BaseFDTD11.py:136-161 -- dielectric slab on [materialFrontEdge, materialRearEdge)."""
+    Nz, mf, mr = P.Nz, int(P.materialFrontEdge), int(P.materialRearEdge)
+    V.epsilon = np.ones(Nz)
+    V.mu = np.ones(Nz)
+    for arr in (V.UpExHcompsCo, V.UpExSelf, V.UpHyEcompsCo, V.UpHySelf):
+        arr[:Nz] = 1
+    V.epsilon[mf:mr] = P.epsRe
+    V.mu[mf:mr] = P.muRe
+    V.UpExHcompsCo[mf:mr] = P.eHcompsCo
+    V.UpExSelf[mf:mr] = P.eSelfCo
+    V.UpHyEcompsCo[mf:mr] = P.hEcompsCo
+    V.UpHySelf[mf:mr] = P.hSelfCo
+    return V.epsilon, V.mu, V.UpExHcompsCo, V.UpExSelf, V.UpHyEcompsCo, V.UpHySelf
+
+
+def UpdateCoef(V, P):
+    """BaseFDTD11.py:168-182 -- fold epsilon/mu of the slab into the update coefficients."""
+    L = P.Nz + 1
+    mf, mr = int(P.materialFrontEdge), int(P.materialRearEdge)
+    UpHyMat = np.full(L, (1 / P.CharImp) * P.courantNo)
+    UpExMat = np.full(L, P.CharImp * P.courantNo)
+    UpExMat[mf:mr] = UpExMat[mf:mr] / V.epsilon[mf:mr]
+    UpHyMat[mf:mr] = UpHyMat[mf:mr] / V.mu[mf:mr]
+    return UpHyMat, UpExMat
+
+
+def CPML_FieldInit(V, P, C_V, C_P):
+    """BaseFDTD11.py:195-219."""
+    L = P.Nz + 1
+    C_V.kappa_Ex = np.ones(L)
+    C_V.kappa_Hy = np.ones(L)
+    for k in ("psi_Ex", "psi_Hy", "alpha_Ex", "alpha_Hy", "sigma_Ex", "sigma_Hy", "beX", "bmY", "ceX", "cmY",
+              "eLoss_CPML", "mLoss_CPML", "Ca", "Cb", "Cc", "C1", "C2", "C3"):
+        setattr(C_V, k, np.zeros(L))
+    C_V.den_Exdz = np.ones(len(V.Ex))
+    C_V.den_Hydz = np.ones(len(V.Ex))
+    return C_V
+
+
+def CPML_ScalingCalc(V, P, C_V, C_P):
+    """BaseFDTD11.py:222-272 -- polynomial grading of sigma/kappa/alpha, mirrored on the right.
+    The Hy profiles alias the Ex profiles, as in the reference."""
+    pw, L = int(P.pmlWidth), len(V.Ex)
+    kap, sig, alp = np.empty(pw), np.empty(pw), np.empty(pw)
+    for n in range(pw):
+        depth = (pw - n) / pw
+        graded = math.pow(depth, C_P.r_scale)
+        kap[n] = 1 + (C_P.kappaMax - 1) * graded
+        sig[n] = C_P.sigmaOpt * graded
+        alp[n] = C_P.alphaMax * math.pow((n + 1) / pw, C_P.r_a_scale)
+    for dst, prof in ((C_V.kappa_Ex, kap), (C_V.sigma_Ex, sig), (C_V.alpha_Ex, alp)):
+        dst[:pw] = prof
+        dst[L - pw:L] = prof[::-1]
+    C_V.kappa_Hy = C_V.kappa_Ex
+    C_V.sigma_Hy = C_V.sigma_Ex
+    C_V.alpha_Hy = C_V.alpha_Ex
+    return C_V.sigma_Ex, C_V.sigma_Hy, C_V.alpha_Ex, C_V.alpha_Hy, C_V.kappa_Ex, C_V.kappa_Hy
+
+
+def _cpml_cells(P, L):
+    pw = int(P.pmlWidth)
+    return list(range(pw)) + list(range(L - pw, L))
+
+
+def _recursive_conv_coefs(P, sigma, kappa, alpha, cells, per_dz):
+    b = np.zeros(len(sigma))
+    c = np.zeros(len(sigma))
+    for nz in cells:
+        s, k, a = sigma[nz], kappa[nz], alpha[nz]
+        bn = math.exp(-((s * P.delT / (k * P.permit_0)) + ((a * P.delT) / P.permit_0)))
+        den = s * k + a * k * k
+        if per_dz:
+            den = den * P.dz
+        b[nz] = bn
+        c[nz] = (bn - 1) * s / den
+    return b, c
+
+
+def CPML_Ex_RC_Define(V, P, C_V, C_P):
+    """BaseFDTD11.py:274-286 -- b_e, c_e of the E-side recursive convolution."""
+    b, c = _recursive_conv_coefs(P, C_V.sigma_Ex, C_V.kappa_Ex, C_V.alpha_Ex, _cpml_cells(P, len(V.Ex)), False)
+    cells = _cpml_cells(P, len(V.Ex))
+    C_V.beX[cells] = b[cells]
+    C_V.ceX[cells] = c[cells]
+    return C_V.beX, C_V.ceX
+
+
+def CPML_HY_RC_Define(V, P, C_V, C_P):
+    """BaseFDTD11.py:288-296 -- b_m, c_m (note: also uses eps0, and c_m carries 1/dz)."""
+    cells = _cpml_cells(P, len(V.Hy))
+    b, c = _recursive_conv_coefs(P, C_V.sigma_Hy, C_V.kappa_Hy, C_V.alpha_Hy, cells, True)
+    C_V.bmY[cells] = b[cells]
+    C_V.cmY[cells] = c[cells]
+    return C_V.bmY, C_V.cmY
+
+
+def _correction_cells(P, L):
+    """0..pw-1 and L-1 down to L-pw+1: the right range EXCLUDES L-pw (BaseFDTD11.py:306,312)."""
+    pw = int(P.pmlWidth)
+    return np.concatenate([np.arange(0, pw), np.arange(L - 1, L - pw, -1)]).astype(np.int64)
+
+
+def CPML_Ex_Update_Coef(V, P, C_V, C_P):
+    """BaseFDTD11.py:299-318."""
+    betaE = (0.5 * V.plasmaFreqE * V.plasmaFreqE * P.permit_0 * P.delT) / (1 + 0.5 * V.gammaE * P.delT)
+    a = ((2 * P.permit_0 - betaE * P.delT) / (2 * P.permit_0 + betaE * P.delT))
+    idx = _correction_cells(P, len(V.Hy))
+    C_V.eLoss_CPML[idx] = (C_V.sigma_Ex[idx] * P.delT) / (2 * P.permit_0)
+    C_V.Ca[idx] = a
+    C_V.Cb[idx] = V.UpExHcompsCo[idx] * V.UpExMat[idx]
+    C_V.Cc[idx] = P.delT / ((1 + C_V.eLoss_CPML[idx]) * P.permit_0)
+    return C_V.eLoss_CPML, C_V.Ca, C_V.Cb, C_V.Cc
+
+
+def CPML_Hy_Update_Coef(V, P, C_V, C_P):
+    """BaseFDTD11.py:321-330."""
+    idx = _correction_cells(P, len(V.Hy))
+    C_V.C1[idx] = 1
+    C_V.C2[idx] = P.delT / P.permea_0
+    C_V.C3[idx] = P.delT / ((1 + C_V.mLoss_CPML[idx]) * P.permea_0)
+    return C_V.mLoss_CPML, C_V.C1, C_V.C2, C_V.C3
+
+
+def denominators(V, P, C_V, C_P):
+    """BaseFDTD11.py:332-357 -- 1/kappa, with the reference's mirrored right-hand indexing."""
+    pw, L = int(P.pmlWidth), len(V.Hy)
+    for den, kap, start in ((C_V.den_Hydz, C_V.kappa_Hy, pw), (C_V.den_Exdz, C_V.kappa_Ex, pw - 1)):
+        den[:] = 1.0
+        if P.CPMLXm:
+            den[:pw + 1] = 1 / kap[:pw + 1]
+        if P.CPMLXp:
+            lo = max(L - pw, pw + 1) if P.CPMLXm else L - pw
+            j = np.arange(lo, L)
+            den[j] = 1 / kap[start - (j - lo)]
+    return C_V.den_Exdz, C_V.den_Hydz
+
+
+def AnalyticalReflectionE(V, P):
+    """BaseFDTD11.py:882-923 -- Fresnel normal-incidence reflection of the Lorentz half-space."""
+    w = 2 * np.pi * P.freq_in
+    eps = 1 + (V.plasmaFreqE * V.plasmaFreqE) / (V.omega_0E * V.omega_0E - (w * w) + 1j * V.gammaE * w)
+    n2 = np.real(np.sqrt(eps))
+    return abs((n2 - 1) / (1 + n2))
+
+
+# ------------------------------------------------------------------------------------------------ leaf ops
+def _lorentz_abc(V, P):
+    """BaseFDTD11.py:620-626."""
+    D = (1 / P.delT ** 2) + (V.gammaE / (2 * P.delT))
+    A = ((2 / P.delT ** 2) - V.omega_0E ** 2) / D
+    B = ((V.gammaE / (2 * P.delT)) - 1 / P.delT ** 2) / D
+    C = (P.permit_0 * V.plasmaFreqE ** 2) / D
+    return A, B, C
+
+
+def _cubic_abc(V, P):
+    """BaseFDTD11.py:804-810."""
+    w = 2 * np.pi * P.freq_in
+    eps = 1 + (V.plasmaFreqE * V.plasmaFreqE) / (V.omega_0E * V.omega_0E - (w * w) + 1j * V.gammaE * w)
+    cub = (V.alpha3 * V.chi3Stat) ** 2
+    qua = 2 * np.real(V.alpha3 * eps * V.chi3Stat)
+    one = np.abs(eps) ** 2
+    return float(cub), float(qua), float(one)
+
+
+def grid_scalars(V, P):
+    A, B, C = _lorentz_abc(V, P)
+    ca, cb, cc = _cubic_abc(V, P)
+    return dict(pw=int(P.pmlWidth), mf=int(P.materialFrontEdge), mr=int(P.materialRearEdge), nzsrc=int(P.nzsrc),
+                dt_over_dz=P.delT / P.dz, eps0=P.permit_0, polA=A, polB=B, polC=C, cub_a=ca, cub_b=cb, cub_c=cc,
+                nl_den0=P.permit_0 * float(np.sqrt(1.2)), nl_den1=P.permit_0 * V.chi3Stat)
+
+
+def grid_flags(P, fma=False):
+    return ((nat.PF_F_TFSF if P.TFSF else 0) | (nat.PF_F_CPML_M if P.CPMLXm else 0) |
+            (nat.PF_F_CPML_P if P.CPMLXp else 0) | (nat.PF_F_FMA if fma else 0))
+
+
+def _host_arrays(V, C_V, pprev):
+    return dict(Ex=V.Ex, Hy=V.Hy, Dx=V.Dx, P=V.polarisationCurr, Pprev=pprev, psiE=C_V.psi_Ex, psiH=C_V.psi_Hy,
+                Acubic=V.Acubic, UpExMat=V.UpExMat, denE=C_V.den_Exdz, UpHySelf=V.UpHySelf, UpHyMat=V.UpHyMat,
+                denH=C_V.den_Hydz, beX=C_V.beX, ceX=C_V.ceX, Cb=C_V.Cb, bmY=C_V.bmY, cmY=C_V.cmY, C2=C_V.C2)
+
+
+def _leaf(V, P, C_V, C_P, fn_name, fetch, pprev=None, extra=()):
+    """Upload the grid, run one leaf kernel, download the arrays it mutates."""
+    L = len(V.Ex)
+    Jx = V.Jx if np.any(V.Jx != 0.0) else None
+    g = dev.DeviceGrid(L=L, T=1, arrays=_host_arrays(V, C_V, V.tempTempVarPol if pprev is None else pprev),
+                       scalars=grid_scalars(V, P), srcE=np.zeros(1), srcH=np.zeros(1), probe_idx=[],
+                       flags=grid_flags(P), Jx=Jx)
+    fn = getattr(nat.lib(), fn_name)
+    nat.check(fn(g.ref(), *extra, nat.current_stream_ptr()), fn_name)
+    return g.fetch(fetch, probes=False)
+
+
+def ADE_ExUpdate(V, P, C_V, C_P, counts=0):
+    """BaseFDTD11.py:663-669 -> pf_ade_ex_update."""
+    V.Ex = _leaf(V, P, C_V, C_P, "pf_ade_ex_update", ["Ex"])["Ex"]
+    return V.Ex
+
+
+def ADE_HyUpdate(V, P, C_V, C_P):
+    """BaseFDTD11.py:640-656 -> pf_ade_hy_update."""
+    V.Hy = _leaf(V, P, C_V, C_P, "pf_ade_hy_update", ["Hy"])["Hy"]
+    return V.Hy
+
+
+def CPML_Psi_e_Update(V, P, C_V, C_P):
+    """BaseFDTD11.py:364-376 -> pf_cpml_psi_e_update."""
+    out = _leaf(V, P, C_V, C_P, "pf_cpml_psi_e_update", ["psiE", "Ex"])
+    C_V.psi_Ex, V.Ex = out["psiE"], out["Ex"]
+    return C_V.psi_Ex, V.Ex
+
+
+def CPML_Psi_m_Update(V, P, C_V, C_P):
+    """BaseFDTD11.py:381-393 -> pf_cpml_psi_m_update."""
+    out = _leaf(V, P, C_V, C_P, "pf_cpml_psi_m_update", ["psiH", "Hy"])
+    C_V.psi_Hy, V.Hy = out["psiH"], out["Hy"]
+    return C_V.psi_Hy, V.Hy
+
+
+def ADE_DxUpdate(V, P, C_V, C_P):
+    """BaseFDTD11.py:750-760 -> pf_ade_dx_update."""
+    V.Dx = _leaf(V, P, C_V, C_P, "pf_ade_dx_update", ["Dx"])["Dx"]
+    return V.Dx
+
+
+def ADE_TempPolCurr(V, P, C_V, C_P):
+    """BaseFDTD11.py:487-538 -- history shift (pure bookkeeping, stays on the host).  Inside the
+    integrators this shift is fused into the polarisation kernel; only the polarisation and E
+    histories are kept (the Hy/Jx/psi shadows of the reference alias live arrays and are unused)."""
+    V.tempTempVarPol = V.tempVarPol
+    V.tempVarPol = V.polarisationCurr.copy()
+    V.tempTempVarE = V.tempVarE
+    V.tempVarE = V.Ex.copy()
+    V.tempTempVarHy, V.tempVarHy = V.tempVarHy, V.Hy
+    V.tempTempVarJx, V.tempVarJx = V.tempVarJx, V.Jx
+    C_V.tempTempVarPsiEx, C_V.tempVarPsiEx = C_V.tempVarPsiEx, C_V.psi_Ex
+    C_V.tempTempVarPsiHy, C_V.tempVarPsiHy = C_V.tempVarPsiHy, C_V.psi_Hy
+    return (V.tempTempVarPol, V.tempVarPol, V.tempVarE, V.tempTempVarE, V.tempTempVarHy, V.tempVarHy,
+            V.tempTempVarJx, V.tempVarJx, C_V.tempTempVarPsiEx, C_V.tempVarPsiEx, C_V.tempTempVarPsiHy,
+            C_V.tempVarPsiHy)
+
+
+def ADE_PolarisationCurrent_Ex(V, P, C_V, C_P, counts=0):
+    """BaseFDTD11.py:609-633 -> pf_ade_polarisation_update (P^{n-1} taken from V.tempTempVarPol)."""
+    V.polarisationCurr = _leaf(V, P, C_V, C_P, "pf_ade_polarisation_update", ["P"], pprev=V.tempTempVarPol)["P"]
+    return V.polarisationCurr
+
+
+def ADE_ExCreate(V, P, C_V, C_P):
+    """BaseFDTD11.py:712-725 -> pf_ade_ex_create."""
+    V.Ex = _leaf(V, P, C_V, C_P, "pf_ade_ex_create", ["Ex"])["Ex"]
+    return V.Ex
+
+
+def AcubicFinder(V, P, C_V=None, C_P=None):
+    """BaseFDTD11.py:793-853 (Nonlin_Eqn_Setup + Nonlin_Cubic_Solver) -> pf_acubic_finder."""
+    C_V = C_V if C_V is not None else _NullCpml(len(V.Ex))
+    V.Acubic = _leaf(V, P, C_V, C_P, "pf_acubic_finder", ["Acubic"])["Acubic"]
+    return V.Acubic
+
+
+def NonLinExUpdate(V, P, C_V=None, C_P=None):
+    """BaseFDTD11.py:858-877 -> pf_nonlin_ex_update."""
+    C_V = C_V if C_V is not None else _NullCpml(len(V.Ex))
+    V.Ex = _leaf(V, P, C_V, C_P, "pf_nonlin_ex_update", ["Ex"])["Ex"]
+    return V.Ex
+
+
+class _NullCpml:
+    """CPML arrays for leaf ops the reference calls without C_V (AcubicFinder, NonLinExUpdate)."""
+
+    def __init__(self, L):
+        z = np.zeros(L)
+        self.psi_Ex = self.psi_Hy = self.beX = self.ceX = self.Cb = self.bmY = self.cmY = self.C2 = z
+        self.den_Exdz = self.den_Hydz = np.ones(L)

@@ -1,0 +1,264 @@
+"""The three time-stepping integrators, their source / boundary managers and probes.
+
+Mirror of the reference's ``Solver_Engine`` module: ``IntegratorFreeSpace1D`` (:142),
+``IntegratorNL1D`` (:220), ``IntegratorLinLor1D`` (:275), ``boundCondManager`` (:70),
+``SourceManager`` (:89), ``Sig_Mod`` (:133), ``probeSim`` (:16), ``vidMake`` (:57).  Signatures and the
+returned 8-tuple ``(Ex, Hy, Exs, Hys, psi_Ex, psi_Hy, x1ColBe, x1ColAf)`` are the reference's.
+
+The per-pass setup is host-side (BaseFDTD11 mirror).  The ``for counts in range(P.timeSteps)`` loop
+(:167 / :236 / :294) -- the hot path -- is ONE call into libpyfdtd_b200 per pass (``pf_run_pass``),
+which is also where the reference has its own (unimplemented) external-integrator hook
+``JH.Jul_Integrator_Prep`` (:164-165).
+
+Engine selection: ``ENGINE = "auto"`` uses the fused, temporally blocked tile engine whenever the
+coefficient arrays have its canonical piecewise form (always true for arrays built by this module's
+setup chain) and falls back to the general one-kernel-per-leaf-op engine otherwise (still CUDA).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import BaseFDTD11
+from . import _device as dev
+from . import _native as nat
+from . import genericStability as gStab
+
+ENGINE = "auto"      # "auto" | "tile" | "ops"
+USE_FMA = False      # True: allow FMA contraction in the kernels (PF_F_FMA; not bit-identical)
+LAST_RUN_INFO = {}   # engine used, bytes moved, kernel launches of the last pass (for tests / bench)
+
+
+# ------------------------------------------------------------------------------------------------ probes / history
+def probeSim(V, P, C_V, C_P, counts, val="null", af=False, granAttn=25, whichField="Ex", attenRead=False,
+             nonlinear=False):
+    """Solver_Engine.py:16-54 -- record one probe sample (host-side API; the integrators record
+    probes on the device every step and store whole traces)."""
+    if nonlinear:
+        if whichField == "Ex":
+            V.Port1[counts] = V.Ex[P.materialFrontEdge]
+            V.Port2[counts] = V.Ex[P.materialRearEdge]
+            return V.Port1, V.Port2
+        return V.x1ColBe
+    if attenRead:
+        for i, idx in enumerate(atten_probe_cells(V, P, granAttn)):
+            if whichField == "Ex":
+                V.x1Atten[i][counts] = V.Ex[idx]
+        return V.x1Atten
+    if af:
+        V.x1ColAf[counts] = val
+        return V.x1ColAf
+    V.x1ColBe[counts] = val
+    return V.x1ColBe
+
+
+def atten_probe_cells(V, P, granAttn=25):
+    """Attenuation probe cells: materialFrontEdge + granAttn*i (Solver_Engine.py:32)."""
+    return np.arange(P.materialFrontEdge, granAttn * V.attenAmnt + P.materialFrontEdge, granAttn)[: len(V.x1Atten)]
+
+
+def vidMake(V, P, C_V, C_P, counts, field, whichField="Ex"):
+    """Solver_Engine.py:57-68."""
+    row = int(counts / P.vidInterval)
+    if whichField == "Ex":
+        if row < len(V.Ex_History):
+            V.Ex_History[row] = field
+        return V.Ex_History
+    return "vidMake has gone to the end of the returns "
+
+
+# ------------------------------------------------------------------------------------------------ managers
+def boundCondManager(V, P, C_V, C_P):
+    """Solver_Engine.py:70-87 -- build every CPML coefficient array."""
+    if P.CPMLXp or P.CPMLXm:
+        (C_V.sigma_Ex, C_V.sigma_Hy, C_V.alpha_Ex, C_V.alpha_Hy, C_V.kappa_Ex,
+         C_V.kappa_Hy) = BaseFDTD11.CPML_ScalingCalc(V, P, C_V, C_P)
+        C_V.beX, C_V.ceX = BaseFDTD11.CPML_Ex_RC_Define(V, P, C_V, C_P)
+        C_V.bmY, C_V.cmY = BaseFDTD11.CPML_HY_RC_Define(V, P, C_V, C_P)
+        C_V.eLoss_CPML, C_V.Ca, C_V.Cb, C_V.Cc = BaseFDTD11.CPML_Ex_Update_Coef(V, P, C_V, C_P)
+        C_V.mLoss_CPML, C_V.C1, C_V.C2, C_V.C3 = BaseFDTD11.CPML_Hy_Update_Coef(V, P, C_V, C_P)
+        C_V.den_Exdz, C_V.den_Hydz = BaseFDTD11.denominators(V, P, C_V, C_P)
+    return C_V
+
+
+def SourceManager(V, P, C_V, C_P):
+    """Solver_Engine.py:89-124 -- per-step source tables Exs, Hys."""
+    if P.SineCont == True:  # noqa: E712  (kept: the reference tests identity with True)
+        Exs, Hys = BaseFDTD11.SmoothTurnOn(V, P)
+        Exp, Hyp = np.zeros(P.timeSteps), np.zeros(P.timeSteps)
+        if P.nonLinMed:
+            Exp, Hyp = BaseFDTD11.SmoothTurnOn(V, P, tempfreq=P.freq_in * 0.8)   # pump at 0.8 f
+            Exp = np.asarray(Exp) * P.courantNo
+            Hyp = np.asarray(Hyp) * P.courantNo
+            Exp = Exp * 0.1
+            Hyp = Hyp * 0.01
+        Exs = np.asarray(Exs) * P.courantNo + Exp
+        Hys = np.asarray(Hys) * P.courantNo + Hyp
+        if P.TFSF == True:  # noqa: E712
+            Hys = Hys * (1 / P.CharImp)
+        return Exs, Hys
+    if P.Gaussian == True:  # noqa: E712
+        Exs = BaseFDTD11.Gaussian(V, P)
+        Hys = BaseFDTD11.Gaussian(V, P) if P.TFSF == True else np.zeros(len(Exs))  # noqa: E712
+        return Exs, Hys
+    return [], []
+
+
+def SechArr(a):
+    """Solver_Engine.py:126-131."""
+    a = np.where(a > 50, 50, a)
+    return 1 / np.cosh(a)
+
+
+def Sig_Mod(V, P, sig, AmpCarr=1, AmpMod=1, tau=14.6e-10):
+    """Solver_Engine.py:133-140 -- sech envelope."""
+    t = np.arange(len(sig)) * (P.delT)
+    return (AmpMod + sig) * SechArr((2 * np.pi * (1 / tau)) * t)
+
+
+# ------------------------------------------------------------------------------------------------ the hot loop
+def _pick_engine(P, arrs, Jx, probe_idx):
+    if ENGINE == "ops":
+        return nat.PF_ENGINE_OPS, None
+    canon = dev.canonical_form(P, arrs, Jx)
+    slab_src_clash = P.TFSF and (P.materialFrontEdge - 1 <= P.nzsrc - 1 < P.materialRearEdge)
+    ok = canon is not None and dev.probes_ok_for_tiles(probe_idx) and not slab_src_clash
+    if ENGINE == "tile" and not ok:
+        raise ValueError("ENGINE='tile' requested but the grid is not in the tile engine's canonical form")
+    return (nat.PF_ENGINE_TILE, canon) if ok else (nat.PF_ENGINE_OPS, None)
+
+
+def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=False, n0=0, nsteps=None):
+    """The reference's per-pass time loop, executed by libpyfdtd_b200 on the current CUDA device.
+
+    Uploads V/C_V state + coefficients (one H2D), runs ``nsteps`` steps of integrator ``mode`` starting at
+    absolute step ``n0``, downloads state + probe traces (one D2H) and writes them back into V / C_V.
+    Returns the probe traces, shape [len(probe_idx), timeSteps].
+    """
+    torch = nat.require_cuda()
+    lib = nat.lib()
+    T = int(P.timeSteps)
+    nsteps = T - n0 if nsteps is None else int(nsteps)
+    L = len(V.Ex)
+    arrs = BaseFDTD11._host_arrays(V, C_V, V.tempVarPol)
+    Jx = V.Jx if np.any(V.Jx != 0.0) else None
+    engine, canon = _pick_engine(P, arrs, Jx, probe_idx)
+    scal = BaseFDTD11.grid_scalars(V, P)
+    flags = BaseFDTD11.grid_flags(P, USE_FMA)
+    if canon is not None:
+        scal.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
+        flags |= nat.PF_F_CANONICAL
+    launches0 = lib.pf_launch_count()
+    g = dev.DeviceGrid(L=L, T=T, arrays=arrs, scalars=scal, srcE=np.asarray(Exs) / P.courantNo,
+                       srcH=np.asarray(Hys) / P.courantNo, probe_idx=list(probe_idx), flags=flags, Jx=Jx)
+    stream = nat.current_stream_ptr()
+    scratch = None
+    sbytes = lib.pf_run_scratch_bytes(g.ref(), 1, engine)
+    if sbytes:
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=g.device)
+    snap_t = None
+    rows = int(P.timeSteps / P.vidInterval)
+    if snapshots and rows > 0:
+        snap_t = torch.zeros((rows, L), dtype=torch.float64, device=g.device)
+    mode_id = dev.MODE_ID[mode]
+    pprev2 = None
+
+    def call(first, count):
+        nat.check(lib.pf_run_pass(g.ref(), mode_id, int(do_pol), first, count, engine,
+                                  snap_t.data_ptr() if snap_t is not None else None,
+                                  int(P.vidInterval) if snap_t is not None else 0, rows if snap_t is not None else 0,
+                                  scratch.data_ptr() if scratch is not None else None, sbytes, stream), "pf_run_pass")
+
+    if mode == "lorentz" and do_pol and nsteps >= 1:
+        # keep P^{N-2} as well so V.tempTempVarPol / V.tempVarPol end up as the reference leaves them
+        if nsteps > 1:
+            call(n0, nsteps - 1)
+        pprev2 = g.tensor_view("Pprev").clone()
+        call(n0 + nsteps - 1, 1)
+    elif nsteps > 0:
+        call(n0, nsteps)
+    out = g.fetch(["Ex", "Hy", "Dx", "P", "Pprev", "psiE", "psiH", "Acubic"])
+    V.Ex, V.Hy, V.Dx = out["Ex"], out["Hy"], out["Dx"]
+    C_V.psi_Ex, C_V.psi_Hy = out["psiE"], out["psiH"]
+    if mode == "lorentz":
+        V.polarisationCurr = out["P"]
+        V.tempVarPol = out["Pprev"]
+        if pprev2 is not None:
+            V.tempTempVarPol = pprev2.cpu().numpy()
+    if mode == "nl":
+        V.Acubic = out["Acubic"]
+    if snap_t is not None:
+        hist = snap_t.cpu().numpy()
+        n_abs = np.arange(rows) * int(P.vidInterval)
+        done = (n_abs > 0) & (n_abs >= n0) & (n_abs < n0 + nsteps)
+        V.Ex_History[done] = hist[done]
+    LAST_RUN_INFO.update(engine="tile" if engine == nat.PF_ENGINE_TILE else "ops", h2d_bytes=g.h2d_bytes,
+                         d2h_bytes=g.d2h_bytes, launches=lib.pf_launch_count() - launches0, cells=L, steps=nsteps)
+    return out["probe_out"]
+
+
+def _linear_probes(V, P):
+    atten = list(atten_probe_cells(V, P)) if P.atten else []
+    return atten
+
+
+def _two_pass(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf, lorentz):
+    """Shared body of IntegratorFreeSpace1D / IntegratorLinLor1D: pass 0 = incident run (probe x1Loc),
+    pass 1 = run with the medium's polarisation (probe x2Loc, history, attenuation probes)."""
+    n = np.arange(P.timeSteps)
+    for i in range(2):
+        (V.tempVarPol, V.tempTempVarE, V.tempVarE, V.tempTempVarPol, V.polarisationCurr, V.Ex, V.Dx,
+         V.Hy) = BaseFDTD11.FieldInit(V, P)
+        V.UpHyMat, V.UpExMat = BaseFDTD11.EmptySpaceCalc(V, P)
+        if not lorentz:
+            (V.epsilon, V.mu, V.UpExHcompsCo, V.UpExSelf, V.UpHyEcompsCo,
+             V.UpHySelf) = BaseFDTD11.Material(V, P)
+            V.UpHyMat, V.UpExMat = BaseFDTD11.UpdateCoef(V, P)
+        C_V = BaseFDTD11.CPML_FieldInit(V, P, C_V, C_P)
+        C_V = boundCondManager(V, P, C_V, C_P)
+        if lorentz:
+            _, _, _, V.plasmaFreqE, _ = gStab.spatialStab(P.timeSteps, P.Nz, P.dz, P.freq_in, P.delT,
+                                                           V.plasmaFreqE, V.omega_0E, V.gammaE)
+        Exs, Hys = SourceManager(V, P, C_V, C_P)
+        if not lorentz:
+            tauIn = 1 / (P.freq_in / 5)
+            Exs = Sig_Mod(V, P, Exs, tau=tauIn)
+            Hys = Sig_Mod(V, P, Hys, AmpMod=1 / P.CharImp, tau=tauIn)
+        V.test = 0
+        if i == 0:
+            traces = run_time_loop(V, P, C_V, C_P, "lorentz" if lorentz else "free", False, Exs, Hys, [P.x1Loc])
+            V.x1ColBe = np.where(n <= probeReadFinishBe, traces[0], V.x1ColBe)
+        else:
+            atten = _linear_probes(V, P)
+            traces = run_time_loop(V, P, C_V, C_P, "lorentz" if lorentz else "free", lorentz, Exs, Hys,
+                                   [P.x2Loc] + atten, snapshots=True)
+            window = n >= probeReadStartAf
+            V.x1ColAf = np.where(window, traces[0], V.x1ColAf)
+            for k in range(len(atten)):
+                V.x1Atten[k] = np.where(window, traces[1 + k], V.x1Atten[k])
+    return V.Ex, V.Hy, Exs, Hys, C_V.psi_Ex, C_V.psi_Hy, V.x1ColBe, V.x1ColAf
+
+
+def IntegratorFreeSpace1D(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf):
+    """Solver_Engine.py:142-215 -- vacuum / dielectric slab + CPML, two passes."""
+    return _two_pass(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf, lorentz=False)
+
+
+def IntegratorLinLor1D(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf):
+    """Solver_Engine.py:275-371 -- Lorentz ADE medium + CPML, two passes."""
+    return _two_pass(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf, lorentz=True)
+
+
+def IntegratorNL1D(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf):
+    """Solver_Engine.py:220-271 -- cubic nonlinear medium, per-cell cubic solve every step, one pass."""
+    (V.tempVarPol, V.tempTempVarE, V.tempVarE, V.tempTempVarPol, V.polarisationCurr, V.Ex, V.Dx,
+     V.Hy) = BaseFDTD11.FieldInit(V, P)
+    V.UpHyMat, V.UpExMat = BaseFDTD11.EmptySpaceCalc(V, P)
+    C_V = BaseFDTD11.CPML_FieldInit(V, P, C_V, C_P)
+    C_V = boundCondManager(V, P, C_V, C_P)
+    _, _, _, V.plasmaFreqE, _ = gStab.spatialStab(P.timeSteps, P.Nz, P.dz, P.freq_in, P.delT, V.plasmaFreqE,
+                                                   V.omega_0E, V.gammaE)
+    Exs, Hys = SourceManager(V, P, C_V, C_P)
+    traces = run_time_loop(V, P, C_V, C_P, "nl", False, Exs, Hys, [P.materialFrontEdge, P.materialRearEdge],
+                           snapshots=True)
+    V.Port1, V.Port2 = traces[0], traces[1]
+    return V.Ex, V.Hy, Exs, Hys, C_V.psi_Ex, C_V.psi_Hy, V.x1ColBe, V.x1ColAf

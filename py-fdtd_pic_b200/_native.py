@@ -1,0 +1,140 @@
+"""ctypes binding of libpyfdtd_b200.so (the C-ABI declared in include/pyfdtd_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or it reports no usable CUDA device
+when a compute entry point is called, this module raises.  PyTorch appears here only as the
+carrier of device buffers (``tensor.data_ptr()``) and of the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpyfdtd_b200.so")
+
+PF_FREE, PF_LORENTZ, PF_NL = 0, 1, 2
+PF_ENGINE_OPS, PF_ENGINE_TILE = 0, 1
+PF_F_TFSF, PF_F_CPML_M, PF_F_CPML_P, PF_F_CANONICAL, PF_F_FMA = 1, 2, 4, 8, 16
+
+_dp = c_void_p  # device pointers travel as integers
+
+
+class PfGrid(ctypes.Structure):
+    """Mirror of ``struct PfGrid`` (include/pyfdtd_b200.h)."""
+    _fields_ = [
+        ("L", c_int32), ("pw", c_int32), ("mf", c_int32), ("mr", c_int32), ("nzsrc", c_int32),
+        ("flags", c_int32), ("n_probes", c_int32), ("probe_stride", c_int32),
+        ("z0", c_int64), ("Lg", c_int64),
+        ("dt_over_dz", c_double), ("eps0", c_double),
+        ("polA", c_double), ("polB", c_double), ("polC", c_double),
+        ("cub_a", c_double), ("cub_b", c_double), ("cub_c", c_double),
+        ("nl_den0", c_double), ("nl_den1", c_double),
+        ("cE0", c_double), ("cE1", c_double), ("cH0", c_double), ("cH1", c_double), ("c2_pml", c_double),
+        ("Ex", _dp), ("Hy", _dp), ("Dx", _dp), ("P", _dp), ("Pprev", _dp), ("psiE", _dp), ("psiH", _dp),
+        ("Acubic", _dp),
+        ("Jx", _dp), ("UpExMat", _dp), ("denE", _dp), ("UpHySelf", _dp), ("UpHyMat", _dp), ("denH", _dp),
+        ("beX", _dp), ("ceX", _dp), ("Cb", _dp), ("bmY", _dp), ("cmY", _dp), ("C2", _dp),
+        ("srcE", _dp), ("srcH", _dp),
+        ("probe_idx", _dp), ("probe_out", _dp),
+    ]
+
+
+class PfPic(ctypes.Structure):
+    """Mirror of ``struct PfPic``."""
+    _fields_ = [
+        ("n", c_int64), ("L", c_int32), ("_pad", c_int32),
+        ("dz", c_double), ("dt", c_double), ("q_over_m", c_double), ("c", c_double), ("mu0", c_double),
+        ("jx_scale", c_double),
+        ("z", _dp), ("ux", _dp), ("uz", _dp), ("w", _dp), ("cell", _dp),
+        ("Ex", _dp), ("Hy", _dp), ("Jx", _dp),
+    ]
+
+
+# every symbol include/pyfdtd_b200.h declares: name -> (restype, argtypes)
+_G = POINTER(PfGrid)
+_PP = POINTER(PfPic)
+SYMBOLS = {
+    "pf_abi_version": (c_int, []),
+    "pf_last_error": (ctypes.c_char_p, []),
+    "pf_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t)]),
+    "pf_sync": (c_int, [c_void_p]),
+    "pf_launch_count": (ctypes.c_ulonglong, []),
+    "pf_ade_ex_update": (c_int, [_G, c_void_p]),
+    "pf_ade_hy_update": (c_int, [_G, c_void_p]),
+    "pf_cpml_psi_e_update": (c_int, [_G, c_void_p]),
+    "pf_cpml_psi_m_update": (c_int, [_G, c_void_p]),
+    "pf_source_inject": (c_int, [_G, c_int, c_void_p]),
+    "pf_ade_dx_update": (c_int, [_G, c_void_p]),
+    "pf_ade_polarisation_update": (c_int, [_G, c_void_p]),
+    "pf_ade_ex_create": (c_int, [_G, c_void_p]),
+    "pf_acubic_finder": (c_int, [_G, c_void_p]),
+    "pf_nonlin_ex_update": (c_int, [_G, c_void_p]),
+    "pf_probe_record": (c_int, [_G, c_int, c_void_p]),
+    "pf_cubic_root0": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "pf_run_pass": (c_int, [_G, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pf_run_batch": (c_int, [_G, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_size_t, c_void_p]),
+    "pf_run_scratch_bytes": (c_size_t, [_G, c_int, c_int]),
+    "pf_tile_config": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "pf_halo_pack": (ctypes.c_longlong, [_G, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pf_halo_unpack": (ctypes.c_longlong, [_G, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pf_pic_push": (c_int, [_PP, c_void_p]),
+    "pf_pic_sort": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
+    "pf_pic_deposit": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
+    "pf_pic_scratch_bytes": (c_size_t, [_PP]),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises NativeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the hot path)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if L.pf_abi_version() != 1:
+            raise NativeError("libpyfdtd_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc < 0:
+        msg = lib().pf_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise NativeError(f"{what}: {msg} (code {rc})")
+    return rc
+
+
+def require_cuda():
+    """Fail loudly when the hot path is asked to run without a GPU."""
+    import torch
+    if not torch.cuda.is_available():
+        raise NativeError("pyfdtd_b200 needs a CUDA device (sm_100a); no CPU fallback exists for the hot path")
+    return torch
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_info():
+    sm, ma, mi = c_int(), c_int(), c_int()
+    fr, to = c_size_t(), c_size_t()
+    check(lib().pf_device_info(sm, ma, mi, fr, to), "pf_device_info")
+    return dict(sm_count=sm.value, cc=(ma.value, mi.value), free_bytes=fr.value, total_bytes=to.value)

@@ -1,0 +1,166 @@
+// pf_common.cuh -- shared device/host helpers for libpyfdtd_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/pyfdtd_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpyfdtd_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace pf {
+
+extern char g_err[512];
+extern unsigned long long g_launches;
+
+int set_err(int code, const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);
+
+#define PF_CUDA(call)                                        \
+    do {                                                     \
+        int _rc = ::pf::check_cuda((call), #call);           \
+        if (_rc) return _rc;                                 \
+    } while (0)
+
+#define PF_LAUNCH_CHECK(name)                                \
+    do {                                                     \
+        ++::pf::g_launches;                                  \
+        int _rc = ::pf::check_cuda(cudaGetLastError(), name);\
+        if (_rc) return _rc;                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Arithmetic policy.  The reference's loops are compiled by numba/LLVM without contraction, so
+// bit-identical results need separately rounded multiplies and adds: Exact uses the _rn
+// intrinsics, which nvcc never fuses.  Fused lets a*b+c become one DFMA (PF_F_FMA).
+// ---------------------------------------------------------------------------------------------
+struct Exact {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    // a*b + c with two roundings
+    static __device__ __forceinline__ double mad(double a, double b, double c) { return __dadd_rn(__dmul_rn(a, b), c); }
+    // c - a*b with two roundings
+    static __device__ __forceinline__ double nmad(double a, double b, double c) { return __dsub_rn(c, __dmul_rn(a, b)); }
+};
+struct Fused {
+    static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+    static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+    static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
+    static __device__ __forceinline__ double mad(double a, double b, double c) { return fma(a, b, c); }
+    static __device__ __forceinline__ double nmad(double a, double b, double c) { return fma(-a, b, c); }
+};
+
+// Correctly rounded x / d for a loop-invariant divisor d with r = RN(1/d) precomputed
+// (Markstein: q = RN(x*r); e = x - q*d exactly by FMA; RN(q + e*r) == RN(x/d)).
+// The two-FMA correction is exact whenever e is representable; for |x| so small that the
+// residual could underflow (or non-finite x) the IEEE divide is used instead.  This is an
+// implementation of the division the reference performs, not a contraction of its arithmetic.
+__device__ __forceinline__ double div_const(double x, double d, double r)
+{
+    double q = __dmul_rn(x, r);
+    double e = __fma_rn(-q, d, x);
+    double q2 = __fma_rn(e, r, q);
+    double ax = fabs(x);
+    if (!(ax > 1e-250 && ax < 1e250)) q2 = __ddiv_rn(x, d);  // rare: denormal range, 0, inf, nan
+    return q2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// First root of a x^3 + b x^2 + c x + d as the reference's solver returns it
+// (CubicEquationSolver.py:29-105; only root[0] is consumed, BaseFDTD11.py:838).
+// Per-run constants (functions of a,b,c only) are hoisted into CubicConsts on the device once per
+// thread; per-cell work is the d-dependent part.  Arithmetic order follows the reference.
+// ---------------------------------------------------------------------------------------------
+struct CubicConsts {
+    double a, b, c;
+    double inv_a;        // RN(1/a) for div_const
+    double f;            // findF(a,b,c)
+    double g_ab;         // (2 b^3)/a^3 - (9 b c)/a^2   (first two terms of findG)
+    double f3_27;        // f^3/27
+    double b_3a;         // b/(3a)
+};
+
+// Device-side constants (generic pf_cubic_root0 entry, where every polynomial has its own a,b,c).
+// Grid runs use cubic_consts_host() instead, which calls the same libm pow() as CPython does.
+__device__ __forceinline__ CubicConsts cubic_consts_dev(double a, double b, double c)
+{
+    CubicConsts k;
+    k.a = a; k.b = b; k.c = c;
+    k.inv_a = 1.0 / a;
+    double a2 = a * a;               // pow(a,2.0) is correctly rounded == a*a
+    double b2 = b * b;
+    // pow(x,3.0) in glibc is correctly rounded to < 1ulp of x^3; x*x*x can differ in the last bit,
+    // so cube through an exact double-double product: x^3 = RN(x2_hi*x + x2_lo*x).
+    double b2lo = __fma_rn(b, b, -b2), a2lo = __fma_rn(a, a, -a2);
+    double b3 = __fma_rn(b2, b, b2lo * b);
+    double a3 = __fma_rn(a2, a, a2lo * a);
+    k.f = __ddiv_rn(__dsub_rn(__ddiv_rn(__dmul_rn(3.0, c), a), __ddiv_rn(b2, a2)), 3.0);
+    k.g_ab = __dsub_rn(__ddiv_rn(__dmul_rn(2.0, b3), a3), __ddiv_rn(__dmul_rn(__dmul_rn(9.0, b), c), a2));
+    double f2 = k.f * k.f, f2lo = __fma_rn(k.f, k.f, -f2);
+    double f3 = __fma_rn(f2, k.f, f2lo * k.f);
+    k.f3_27 = __ddiv_rn(f3, 27.0);
+    k.b_3a = __ddiv_rn(b, __dmul_rn(3.0, a));
+    return k;
+}
+
+__device__ __forceinline__ double signed_cbrt_pow(double v)
+{
+    // reference: v ** (1/3.0) on |v| with the sign restored (CubicEquationSolver.py:76-85)
+    double r = pow(fabs(v), 1.0 / 3.0);
+    return copysign(r, v);
+}
+
+__device__ __forceinline__ double cubic_root0(const CubicConsts &k, double d)
+{
+    if (k.a == 0.0) {  // linear / quadratic fallbacks (CubicEquationSolver.py:30-46); never hit on the NL path
+        if (k.b == 0.0) return __ddiv_rn(-d, k.c);
+        double D = __dsub_rn(__dmul_rn(k.c, k.c), __dmul_rn(__dmul_rn(4.0, k.b), d));
+        double twob = __dmul_rn(2.0, k.b);
+        return (D >= 0.0) ? __ddiv_rn(__dadd_rn(-k.c, sqrt(D)), twob) : __ddiv_rn(-k.c, twob);
+    }
+    double t3 = div_const(__dmul_rn(27.0, d), k.a, k.inv_a);                 // 27*d/a
+    double g = __ddiv_rn(__dadd_rn(k.g_ab, t3), 27.0);                       // findG
+    double gg4 = __dmul_rn(__dmul_rn(g, g), 0.25);                           // g**2/4
+    double h = __dadd_rn(gg4, k.f3_27);                                      // findH
+    double ghalf = __dmul_rn(g, 0.5);
+    if (h > 0.0) {  // one real root -- the only branch the NL path takes
+        double sh = sqrt(h);
+        double S = signed_cbrt_pow(__dadd_rn(-ghalf, sh));
+        double U = signed_cbrt_pow(__dsub_rn(-ghalf, sh));
+        return __dsub_rn(__dadd_rn(S, U), k.b_3a);
+    }
+    if (k.f == 0.0 && g == 0.0 && h == 0.0) {  // triple root
+        double da = __ddiv_rn(d, k.a);
+        return (da >= 0.0) ? -pow(da, 1.0 / 3.0) : pow(-da, 1.0 / 3.0);
+    }
+    // three real roots: x1 = 2 j cos(k/3) - b/(3a)
+    double i = sqrt(__dsub_rn(gg4, h));
+    double j = pow(i, 1.0 / 3.0);
+    double kk = acos(-__ddiv_rn(g, __dmul_rn(2.0, i)));
+    return __dsub_rn(__dmul_rn(__dmul_rn(2.0, j), cos(__ddiv_rn(kk, 3.0))), k.b_3a);
+}
+
+// Acubic of one cell: root0 of [cub, qua, one, -|Dx/eps0|^2] if |d| > 1e-8 else 0
+// (BaseFDTD11.py:793-853).
+__device__ __forceinline__ double acubic_cell(const CubicConsts &k, double dx, double eps0, double inv_eps0)
+{
+    double q = fabs(div_const(dx, eps0, inv_eps0));
+    double d = -__dmul_rn(q, q);
+    return (fabs(d) > 1e-8) ? cubic_root0(k, d) : 0.0;
+}
+
+// Host-side constants, evaluated exactly as CubicEquationSolver.findF/findG/findH do in CPython
+// (float ** float -> libm pow).  Defined in pf_host.cu.
+CubicConsts cubic_consts_host(double a, double b, double c);
+
+// What the kernels see for one grid: the caller's descriptor plus host-derived constants.
+struct GridDev {
+    PfGrid g;
+    CubicConsts k;
+    double inv_eps0;
+};
+GridDev make_grid_dev(const PfGrid &g);
+
+}  // namespace pf

@@ -1,0 +1,567 @@
+// pf_tile.cu -- ENGINE_TILE: the fused, on-chip, temporally blocked integrator.
+//
+// Work decomposition
+//   A launch advances every grid of a batch (sweep members, or one long grid) by up to k steps.
+//   Each CTA owns one TILE of TILE_CELLS consecutive cells of one grid: TILE_CELLS - 2k interior
+//   cells plus a k-cell halo on either side (overlapped / trapezoidal time blocking: after s steps
+//   the s outermost cells on each side are stale, so after k steps exactly the interior is valid).
+//   State is read once from HBM, advanced k steps on chip, interior written once to the other
+//   ping-pong buffer.  HBM traffic per cell-update is (algorithmic bytes)/k * (1 + 2k/W).
+//
+// On-chip layout
+//   Thread t owns the C consecutive cells [t*C, t*C+C) of the tile.  Ex and Hy of those cells
+//   live in registers for the whole launch.  Material state (Dx, P, P^{n-1}), CPML state
+//   (psi_E, psi_H) and the per-cell CPML profiles (b, c_e, c_m) live in shared memory in
+//   [array][j][thread] order, so each thread only ever touches its own slots (no barrier needed,
+//   and lane-consecutive 8-byte words are bank-conflict free).  The only inter-thread traffic is
+//   one Hy value to the right neighbour before the E half-step and one Ex value to the left
+//   neighbour before the H half-step, through a 2*NT-double shared edge buffer: two
+//   __syncthreads per time step.
+//
+// Arithmetic
+//   Identical, operation for operation, to the reference loop bodies (see pf_ops.cu for the
+//   one-kernel-per-leaf-op statement): class A = Exact keeps every multiply and add separately
+//   rounded, so results are independent of the tiling and bit-identical to ENGINE_OPS.
+//
+// Requirements (PF_F_CANONICAL, checked bit-for-bit by the host layer): denE = denH = UpHySelf = 1,
+// bmY == beX, no Jx, UpExMat/UpHyMat two-valued (outside/inside the slab), Cb == UpExMat and
+// C2 == c2_pml on the CPML correction ranges, both 0 at the single cell Lg-pw
+// (the reference's exclusive range end, BaseFDTD11.py:312,326).
+#include <algorithm>
+#include <vector>
+#include "pf_common.cuh"
+
+namespace pf {
+
+constexpr int TILE_CELLS = 2048;
+constexpr int TILE_KMAX = 256;   // halo <= TILE_KMAX per side
+constexpr int TILE_KDEF = 64;    // default steps per launch
+
+struct TileGrid {
+    GridDev d;
+    double *buf[2][7];   // ping-pong state: [which][Ex,Hy,psiE,psiH,Dx,P,Pprev]
+    int nsteps;          // total steps this grid runs in the current pf_run_* call
+    int pad;
+};
+enum { S_EX = 0, S_HY, S_PSIE, S_PSIH, S_DX, S_P, S_PP, S_COUNT };
+
+struct TileDesc {
+    int grid;
+    int base;  // local index of the tile's first cell (interior starts at base + halo)
+};
+
+// shared memory carve-up (doubles)
+template <int MODE, int C>
+struct TileSmem {
+    static constexpr int NT = TILE_CELLS / C;
+    static constexpr int N_ARR = (MODE == PF_LORENTZ) ? 8 : (MODE == PF_NL ? 6 : 5);
+    // order: psiE, psiH, be, ce, cm, [Dx, [P, Pp]]
+    static constexpr size_t bytes = sizeof(double) * ((size_t)N_ARR * TILE_CELLS + 2 * NT + 2 * TILE_KMAX);
+};
+
+template <int MODE, bool POL, int C, class A>
+__global__ void __launch_bounds__(TILE_CELLS / C, 1)
+k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, int src, int n_done,
+       int n0, int ksteps, int halo)
+{
+    constexpr int NT = TILE_CELLS / C;
+    extern __shared__ double smem[];
+    double *sPsiE = smem;
+    double *sPsiH = sPsiE + TILE_CELLS;
+    double *sBe = sPsiH + TILE_CELLS;
+    double *sCe = sBe + TILE_CELLS;
+    double *sCm = sCe + TILE_CELLS;
+    double *sDx = sCm + TILE_CELLS;          // MODE != FREE
+    double *sP = sDx + TILE_CELLS;           // MODE == LORENTZ
+    double *sPp = sP + TILE_CELLS;
+    double *sEdgeH = smem + (size_t)TileSmem<MODE, C>::N_ARR * TILE_CELLS;
+    double *sEdgeE = sEdgeH + NT;
+    double *sSrcE = sEdgeE + NT;
+    double *sSrcH = sSrcE + TILE_KMAX;
+
+    const TileDesc td = tiles[blockIdx.x];
+    const TileGrid &TG = grids[td.grid];
+    const int remaining = TG.nsteps - n_done;
+    const int ks = min(ksteps, remaining);
+    if (ks <= 0) return;
+
+    const PfGrid &g = TG.d.g;
+    const int tid = threadIdx.x;
+    const int L = g.L;
+    const int z0 = (int)g.z0, Lg = (int)g.Lg;
+    const int pw = g.pw, mf = g.mf, mr = g.mr;
+    const int flags = g.flags;
+    const int lz0 = td.base + tid * C;
+
+    const double *__restrict__ inEx = TG.buf[src][S_EX];
+    const double *__restrict__ inHy = TG.buf[src][S_HY];
+
+    // ---- per-cell masks (bit j <-> cell lz0+j) -------------------------------------------
+    unsigned mValid = 0, mUpdE = 0, mUpdH = 0, mPmlE = 0, mPmlH = 0, mSlab = 0, mStore = 0, mQuirk = 0;
+    int jsrc = -1, jtfsf = -1;
+    const bool cpml_m = flags & PF_F_CPML_M, cpml_p = flags & PF_F_CPML_P;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        int lz = lz0 + j, gz = z0 + lz;
+        bool valid = lz >= 0 && lz < L;
+        bool updE = valid && lz >= 1 && gz >= 1 && gz <= Lg - 1;
+        bool updH = valid && lz <= L - 2 && gz >= 1 && gz <= Lg - 2;
+        bool inL = cpml_m && gz < pw, inR = cpml_p && gz >= Lg - pw;
+        bool slab = valid && lz >= 1 && gz >= mf && gz < mr;
+        bool interior = (lz - td.base) >= halo && (lz - td.base) < TILE_CELLS - halo;
+        mValid |= (unsigned)valid << j;
+        mUpdE |= (unsigned)updE << j;
+        mUpdH |= (unsigned)updH << j;
+        mPmlE |= (unsigned)(updE && (inL || inR)) << j;
+        mPmlH |= (unsigned)(updH && (inL || inR)) << j;
+        mSlab |= (unsigned)slab << j;
+        mStore |= (unsigned)(valid && interior) << j;
+        mQuirk |= (unsigned)(gz == Lg - pw) << j;
+        if (valid && gz == g.nzsrc) jsrc = j;
+        if (valid && gz == g.nzsrc - 1 && (flags & PF_F_TFSF)) jtfsf = j;
+    }
+    const bool anyPml = (mPmlE | mPmlH) != 0;
+    const bool anySlab = mSlab != 0;
+
+    // probes owned by this thread (at most 2; the host guarantees that, see tile_supported())
+    int pj0 = -1, pj1 = -1;
+    size_t po0 = 0, po1 = 0;
+    for (int p = 0; p < g.n_probes; ++p) {
+        int lp = g.probe_idx[p] - z0;
+        int j = lp - lz0;
+        if (j >= 0 && j < C && ((mStore >> j) & 1)) {
+            if (pj0 < 0) { pj0 = j; po0 = (size_t)p * g.probe_stride; }
+            else { pj1 = j; po1 = (size_t)p * g.probe_stride; }
+        }
+    }
+
+    // ---- load state ------------------------------------------------------------------------
+    double ex[C], hy[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        bool v = (mValid >> j) & 1;
+        ex[j] = v ? inEx[lz0 + j] : 0.0;
+        hy[j] = v ? inHy[lz0 + j] : 0.0;
+    }
+    if (anyPml) {
+        const double *__restrict__ inPe = TG.buf[src][S_PSIE];
+        const double *__restrict__ inPh = TG.buf[src][S_PSIH];
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            bool pe = (mPmlE >> j) & 1, ph = (mPmlH >> j) & 1;
+            int lz = lz0 + j;
+            sPsiE[j * NT + tid] = pe ? inPe[lz] : 0.0;
+            sPsiH[j * NT + tid] = ph ? inPh[lz] : 0.0;
+            sBe[j * NT + tid] = (pe || ph) ? g.beX[lz] : 0.0;
+            sCe[j * NT + tid] = pe ? g.ceX[lz] : 0.0;
+            sCm[j * NT + tid] = ph ? g.cmY[lz] : 0.0;
+        }
+    }
+    if (MODE != PF_FREE && anySlab) {
+        const double *__restrict__ inDx = TG.buf[src][S_DX];
+#pragma unroll
+        for (int j = 0; j < C; ++j) sDx[j * NT + tid] = ((mSlab >> j) & 1) ? inDx[lz0 + j] : 0.0;
+        if (MODE == PF_LORENTZ) {
+            const double *__restrict__ inP = TG.buf[src][S_P];
+            const double *__restrict__ inPp = TG.buf[src][S_PP];
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                bool s = (mSlab >> j) & 1;
+                sP[j * NT + tid] = s ? inP[lz0 + j] : 0.0;
+                sPp[j * NT + tid] = s ? inPp[lz0 + j] : 0.0;
+            }
+        }
+    }
+    // source tables for the steps of this launch (only the CTA that holds the source cell reads them,
+    // but the load is CTA-uniform so everybody helps)
+    const int nabs0 = n0 + n_done;
+    for (int s = tid; s < ks; s += NT) {
+        sSrcE[s] = g.srcE[nabs0 + s];
+        sSrcH[s] = (flags & PF_F_TFSF) ? g.srcH[nabs0 + s] : 0.0;
+    }
+
+    // ---- constants ---------------------------------------------------------------------------
+    const double cE0 = g.cE0, cE1 = g.cE1, cH0 = g.cH0, cH1 = g.cH1, c2 = g.c2_pml;
+    const double dtdz = g.dt_over_dz, eps0 = g.eps0, inv_eps0 = TG.d.inv_eps0;
+    const double pA = g.polA, pB = g.polB, pC = g.polC;
+    const double den0 = g.nl_den0, den1 = g.nl_den1;
+    CubicConsts kc;
+    if (MODE == PF_NL) kc = TG.d.k;
+    double acub[C];
+    if (MODE == PF_NL) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) acub[j] = 0.0;
+    }
+
+    sEdgeH[tid] = hy[C - 1];
+    __syncthreads();
+
+    // ---- k time steps on chip -----------------------------------------------------------------
+    for (int s = 0; s < ks; ++s) {
+        // ===== E half-step (ADE_TempPolCurr+PolarisationCurrent, ADE_ExUpdate, CPML_Psi_e, source,
+        //                    ADE_DxUpdate, ADE_ExCreate | AcubicFinder+NonLinExUpdate) =====
+        double hl = (tid > 0) ? sEdgeH[tid - 1] : 0.0;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const bool slab = (mSlab >> j) & 1;
+            double e = ex[j];
+            double dH = A::sub(hy[j], hl);
+            hl = hy[j];
+            double pnew = 0.0;
+            if (MODE == PF_LORENTZ) {
+                if (slab) {
+                    pnew = sP[j * NT + tid];
+                    if (POL) {
+                        double pn = pnew;
+                        pnew = A::add(A::add(A::mul(pA, pn), A::mul(pB, sPp[j * NT + tid])), A::mul(pC, e));
+                        sP[j * NT + tid] = pnew;
+                        sPp[j * NT + tid] = pn;
+                    }
+                }
+            }
+            const double cE = slab ? cE1 : cE0;
+            if ((mUpdE >> j) & 1) e = A::add(e, A::mul(dH, cE));
+            if ((mPmlE >> j) & 1) {
+                double psi = A::add(A::mul(sBe[j * NT + tid], sPsiE[j * NT + tid]), A::mul(sCe[j * NT + tid], dH));
+                sPsiE[j * NT + tid] = psi;
+                double cb = ((mQuirk >> j) & 1) ? 0.0 : cE;
+                e = A::sub(e, A::mul(cb, psi));
+            }
+            if (j == jsrc) e = A::add(e, sSrcE[s]);
+            if (MODE != PF_FREE) {
+                if (slab) {
+                    double dx = A::add(sDx[j * NT + tid], A::mul(dH, dtdz));
+                    sDx[j * NT + tid] = dx;
+                    if (MODE == PF_LORENTZ) {
+                        e = div_const(A::sub(dx, pnew), eps0, inv_eps0);
+                    } else {
+                        double a = acubic_cell(kc, dx, eps0, inv_eps0);
+                        acub[j] = a;
+                        e = __ddiv_rn(dx, A::add(den0, A::mul(den1, a)));
+                    }
+                }
+            }
+            ex[j] = e;
+        }
+        sEdgeE[tid] = ex[0];
+        __syncthreads();
+
+        // ===== H half-step (TF/SF correction, ADE_HyUpdate, CPML_Psi_m) =====
+        double er = (tid < NT - 1) ? sEdgeE[tid + 1] : 0.0;
+#pragma unroll
+        for (int j = C - 1; j >= 0; --j) {
+            double h = hy[j];
+            if (j == jtfsf) h = A::sub(h, sSrcH[s]);
+            double dE = A::sub(er, ex[j]);
+            er = ex[j];
+            const bool slabH = ((mSlab >> j) & 1);
+            const double cH = slabH ? cH1 : cH0;
+            if ((mUpdH >> j) & 1) h = A::add(h, A::mul(dE, cH));
+            if ((mPmlH >> j) & 1) {
+                double psi = A::add(A::mul(sBe[j * NT + tid], sPsiH[j * NT + tid]), A::mul(sCm[j * NT + tid], dE));
+                sPsiH[j * NT + tid] = psi;
+                double c2j = ((mQuirk >> j) & 1) ? 0.0 : c2;
+                h = A::add(h, A::mul(c2j, psi));
+            }
+            hy[j] = h;
+        }
+        sEdgeH[tid] = hy[C - 1];
+
+        // ===== probes (Solver_Engine.probeSim): Ex after the step =====
+        if (pj0 >= 0) {
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < C; ++j) v = (j == pj0) ? ex[j] : v;
+            g.probe_out[po0 + nabs0 + s] = v;
+            if (pj1 >= 0) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) v = (j == pj1) ? ex[j] : v;
+                g.probe_out[po1 + nabs0 + s] = v;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- store interior -------------------------------------------------------------------------
+    const int dst = src ^ 1;
+    double *__restrict__ outEx = TG.buf[dst][S_EX];
+    double *__restrict__ outHy = TG.buf[dst][S_HY];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        if ((mStore >> j) & 1) {
+            outEx[lz0 + j] = ex[j];
+            outHy[lz0 + j] = hy[j];
+        }
+    }
+    if (anyPml) {
+        double *__restrict__ outPe = TG.buf[dst][S_PSIE];
+        double *__restrict__ outPh = TG.buf[dst][S_PSIH];
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            if ((mStore >> j) & (mPmlE >> j) & 1) outPe[lz0 + j] = sPsiE[j * NT + tid];
+            if ((mStore >> j) & (mPmlH >> j) & 1) outPh[lz0 + j] = sPsiH[j * NT + tid];
+        }
+    }
+    if (MODE != PF_FREE && anySlab) {
+        double *__restrict__ outDx = TG.buf[dst][S_DX];
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+            if ((mStore >> j) & (mSlab >> j) & 1) outDx[lz0 + j] = sDx[j * NT + tid];
+        if (MODE == PF_LORENTZ) {
+            double *__restrict__ outP = TG.buf[dst][S_P];
+            double *__restrict__ outPp = TG.buf[dst][S_PP];
+#pragma unroll
+            for (int j = 0; j < C; ++j)
+                if ((mStore >> j) & (mSlab >> j) & 1) {
+                    outP[lz0 + j] = sP[j * NT + tid];
+                    outPp[lz0 + j] = sPp[j * NT + tid];
+                }
+        }
+        if (MODE == PF_NL && g.Acubic) {
+#pragma unroll
+            for (int j = 0; j < C; ++j)
+                if ((mStore >> j) & (mSlab >> j) & 1) g.Acubic[lz0 + j] = acub[j];
+        }
+    }
+}
+
+// Copy the interior of every tile from buffer `from` to buffer `to`.  only_odd = 1 restricts it to
+// grids whose result ended in buffer 1 (an odd number of launches), for the final copy-back.
+__global__ void __launch_bounds__(256) k_tile_copy(const TileGrid *__restrict__ grids,
+                                                  const TileDesc *__restrict__ tiles, int halo,
+                                                  int k_block, int mode, int from, int to, int only_odd)
+{
+    const TileDesc td = tiles[blockIdx.x];
+    const TileGrid &TG = grids[td.grid];
+    if (only_odd) {
+        int launches = (TG.nsteps + k_block - 1) / k_block;
+        if ((launches & 1) == 0) return;
+    }
+    int W = TILE_CELLS - 2 * halo;
+    int narr = (mode == PF_LORENTZ) ? 7 : (mode == PF_NL ? 5 : 4);
+    for (int a = 0; a < narr; ++a) {
+        const double *__restrict__ s = TG.buf[from][a];
+        double *__restrict__ d = TG.buf[to][a];
+        for (int i = threadIdx.x; i < W; i += blockDim.x) {
+            int lz = td.base + halo + i;
+            if (lz >= 0 && lz < TG.d.g.L) d[lz] = s[lz];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int n_state_arrays(int mode) { return mode == PF_LORENTZ ? 7 : (mode == PF_NL ? 5 : 4); }
+
+static int tile_supported(const PfGrid &g, int mode)
+{
+    if (!(g.flags & PF_F_CANONICAL)) return set_err(PF_E_UNSUPPORTED, "tile engine needs PF_F_CANONICAL coefficients");
+    if (g.Jx) return set_err(PF_E_UNSUPPORTED, "tile engine: Jx must be NULL");
+    if (mode != PF_FREE && (g.flags & PF_F_TFSF) && g.nzsrc - 1 >= g.mf - 1 && g.nzsrc - 1 < g.mr)
+        return set_err(PF_E_UNSUPPORTED, "tile engine: TF/SF point inside the slab");
+    if (g.n_probes > 64) return set_err(PF_E_UNSUPPORTED, "tile engine: more than 64 probes");
+    if (!g.psiE || !g.psiH || !g.beX || !g.ceX || !g.cmY) return set_err(PF_E_ARG, "CPML arrays missing");
+    if (mode != PF_FREE && !g.Dx) return set_err(PF_E_ARG, "Dx missing");
+    if (mode == PF_LORENTZ && (!g.P || !g.Pprev)) return set_err(PF_E_ARG, "P/Pprev missing");
+    return 0;
+}
+
+struct TilePlan {
+    size_t off_grids, off_tiles, off_state, total;
+    int n_tiles;
+};
+
+static TilePlan tile_plan(const PfGrid *grids, int n, int mode, int halo)
+{
+    TilePlan p;
+    int W = TILE_CELLS - 2 * halo;
+    long long nt = 0;
+    size_t state = 0;
+    for (int m = 0; m < n; ++m) {
+        nt += (grids[m].L + W - 1) / W;
+        state += (size_t)n_state_arrays(mode) * align_up(sizeof(double) * grids[m].L, 256);
+    }
+    p.n_tiles = (int)nt;
+    p.off_grids = 0;
+    p.off_tiles = align_up(sizeof(TileGrid) * (size_t)n, 256);
+    p.off_state = p.off_tiles + align_up(sizeof(TileDesc) * (size_t)nt, 256);
+    p.total = p.off_state + state;
+    return p;
+}
+
+template <int MODE, bool POL, int C>
+static int launch_tile(bool fma, int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
+                       int n0, int ks, int halo, cudaStream_t st)
+{
+    size_t sm = TileSmem<MODE, C>::bytes;
+    if (fma) {
+        static bool set = false;
+        if (!set) { PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, Fused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); set = true; }
+        k_tile<MODE, POL, C, Fused><<<n_tiles, TILE_CELLS / C, sm, st>>>(dg, dt, src, n_done, n0, ks, halo);
+    } else {
+        static bool set = false;
+        if (!set) { PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, Exact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); set = true; }
+        k_tile<MODE, POL, C, Exact><<<n_tiles, TILE_CELLS / C, sm, st>>>(dg, dt, src, n_done, n0, ks, halo);
+    }
+    PF_LAUNCH_CHECK("k_tile");
+    return 0;
+}
+
+constexpr int TILE_C = 8;
+
+static int launch_tile_mode(int mode, int do_pol, bool fma, int n_tiles, const TileGrid *dg, const TileDesc *dt,
+                            int src, int n_done, int n0, int ks, int halo, cudaStream_t st)
+{
+    if (mode == PF_FREE) return launch_tile<PF_FREE, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    if (mode == PF_LORENTZ)
+        return do_pol ? launch_tile<PF_LORENTZ, true, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
+                      : launch_tile<PF_LORENTZ, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    if (mode == PF_NL) return launch_tile<PF_NL, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    return set_err(PF_E_ARG, "bad mode %d", mode);
+}
+
+// Runs the tile engine over n grids.  snap_* only with n == 1.
+int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int *nsteps, int k_block,
+             double *snap_out, int snap_interval, int snap_rows, void *scratch, size_t scratch_bytes,
+             cudaStream_t st)
+{
+    if (n <= 0) return PF_OK;
+    if (k_block <= 0) k_block = TILE_KDEF;
+    if (k_block > TILE_KMAX) k_block = TILE_KMAX;
+    for (int m = 0; m < n; ++m) {
+        int rc = tile_supported(grids[m], mode);
+        if (rc) return rc;
+    }
+    const int halo = k_block;
+    const int W = TILE_CELLS - 2 * halo;
+    TilePlan plan = tile_plan(grids, n, mode, halo);
+    if (!scratch || scratch_bytes < plan.total)
+        return set_err(PF_E_SCRATCH, "tile engine needs %zu bytes of scratch, got %zu", plan.total, scratch_bytes);
+
+    // host images of the device tables
+    std::vector<TileGrid> hg(n);
+    std::vector<TileDesc> ht;
+    ht.reserve(plan.n_tiles);
+    char *sbase = (char *)scratch;
+    size_t off = plan.off_state;
+    int max_steps = 0;
+    bool fma = false;
+    const int na = n_state_arrays(mode);
+    for (int m = 0; m < n; ++m) {
+        const PfGrid &g = grids[m];
+        TileGrid &t = hg[m];
+        t.d = make_grid_dev(g);
+        double *prim[7] = {g.Ex, g.Hy, g.psiE, g.psiH, g.Dx, g.P, g.Pprev};
+        for (int a = 0; a < 7; ++a) {
+            t.buf[0][a] = prim[a];
+            t.buf[1][a] = nullptr;
+            if (a < na) {
+                t.buf[1][a] = (double *)(sbase + off);
+                off += align_up(sizeof(double) * g.L, 256);
+            }
+        }
+        t.nsteps = nsteps[m];
+        t.pad = 0;
+        max_steps = std::max(max_steps, nsteps[m]);
+        fma = fma || (g.flags & PF_F_FMA);
+        int ntile = (g.L + W - 1) / W;
+        for (int i = 0; i < ntile; ++i) ht.push_back(TileDesc{m, i * W - halo});
+    }
+    TileGrid *dg = (TileGrid *)(sbase + plan.off_grids);
+    TileDesc *dt = (TileDesc *)(sbase + plan.off_tiles);
+    PF_CUDA(cudaMemcpyAsync(dg, hg.data(), sizeof(TileGrid) * n, cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaMemcpyAsync(dt, ht.data(), sizeof(TileDesc) * ht.size(), cudaMemcpyHostToDevice, st));
+    // A launch stores only the cells a state array is defined on (psi inside the CPML, Dx/P inside
+    // the slab), so seed the second buffer with the caller's arrays once: the final copy-back then
+    // returns every untouched cell unchanged.
+    k_tile_copy<<<(int)ht.size(), 256, 0, st>>>(dg, dt, halo, k_block, mode, 0, 1, 0);
+    PF_LAUNCH_CHECK("k_tile_copy");
+
+    const bool snaps = snap_out && snap_interval > 0 && n == 1;
+    int n_done = 0, src = 0;
+    while (n_done < max_steps) {
+        int ks = std::min(k_block, max_steps - n_done);
+        if (snaps) {
+            // end this launch right after the next snapshot step (n>0, n % interval == 0)
+            int nabs = n0 + n_done;
+            int next_snap = ((nabs / snap_interval) + 1) * snap_interval;  // first multiple > nabs
+            if (nabs % snap_interval == 0 && nabs > 0) next_snap = nabs;   // step nabs itself is a snapshot step
+            ks = std::min(ks, next_snap - nabs + 1);
+        }
+        int rc = launch_tile_mode(mode, do_pol, fma, (int)ht.size(), dg, dt, src, n_done, n0, ks, halo, st);
+        if (rc) return rc;
+        n_done += ks;
+        src ^= 1;
+        if (snaps) {
+            int nlast = n0 + n_done - 1;
+            if (nlast > 0 && nlast % snap_interval == 0) {
+                int row = nlast / snap_interval;
+                if (row < snap_rows)
+                    PF_CUDA(cudaMemcpyAsync(snap_out + (size_t)row * grids[0].L, hg[0].buf[src][S_EX],
+                                            sizeof(double) * grids[0].L, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+    }
+    if (snaps) {
+        // variable-length launches: parity is not a function of nsteps/k_block; copy back explicitly
+        if (src == 1)
+            for (int a = 0; a < na; ++a)
+                PF_CUDA(cudaMemcpyAsync(hg[0].buf[0][a], hg[0].buf[1][a], sizeof(double) * grids[0].L,
+                                        cudaMemcpyDeviceToDevice, st));
+    } else {
+        k_tile_copy<<<(int)ht.size(), 256, 0, st>>>(dg, dt, halo, k_block, mode, 1, 0, 1);
+        PF_LAUNCH_CHECK("k_tile_copy");
+    }
+    // host vectors go out of scope: the async H2D copies above were issued from pageable memory,
+    // which cudaMemcpyAsync stages before returning.
+    return PF_OK;
+}
+
+int ops_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, double *snap_out,
+                 int snap_interval, int snap_rows, cudaStream_t st);
+
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" {
+
+size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine)
+{
+    if (engine != PF_ENGINE_TILE || !grids || n_grids <= 0) return 0;
+    // sized for the largest state set (Lorentz) and the smallest tile interior (largest tile count)
+    return tile_plan(grids, n_grids, PF_LORENTZ, TILE_KMAX).total;
+}
+
+int pf_tile_config(int *tile_cells, int *k_max, int *threads)
+{
+    if (tile_cells) *tile_cells = TILE_CELLS;
+    if (k_max) *k_max = TILE_KMAX;
+    if (threads) *threads = TILE_CELLS / TILE_C;
+    return PF_OK;
+}
+
+int pf_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, int engine, double *snap_out,
+                int snap_interval, int snap_rows, void *scratch, size_t scratch_bytes, void *stream)
+{
+    if (!g || nsteps < 0) return set_err(PF_E_ARG, "pf_run_pass: bad arguments");
+    if (mode < PF_FREE || mode > PF_NL) return set_err(PF_E_ARG, "pf_run_pass: bad mode %d", mode);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (engine == PF_ENGINE_OPS) return ops_run_pass(g, mode, do_pol, n0, nsteps, snap_out, snap_interval, snap_rows, st);
+    if (engine == PF_ENGINE_TILE)
+        return tile_run(g, 1, mode, do_pol, n0, &nsteps, 0, snap_out, snap_interval, snap_rows, scratch, scratch_bytes, st);
+    return set_err(PF_E_ARG, "pf_run_pass: bad engine %d", engine);
+}
+
+int pf_run_batch(const PfGrid *grids, int n_grids, int mode, int do_pol, int n0, const int *nsteps, int k_block,
+                 void *scratch, size_t scratch_bytes, void *stream)
+{
+    if (!grids || n_grids < 0 || !nsteps) return set_err(PF_E_ARG, "pf_run_batch: bad arguments");
+    if (mode < PF_FREE || mode > PF_NL) return set_err(PF_E_ARG, "pf_run_batch: bad mode %d", mode);
+    return tile_run(grids, n_grids, mode, do_pol, n0, nsteps, k_block, nullptr, 0, 0, scratch, scratch_bytes,
+                    (cudaStream_t)stream);
+}
+
+}  // extern "C"
