@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched dispersive (Lorentz ADE + CPML) 1-D FDTD hot path.
+
+Workload (BASELINE.json configs[1], batched as its `metric` says): a frequency/amplitude sweep of
+M independent Lorentz-slab runs at the reference's default geometry family (9 GHz-class, 0.7 m
+domain, Nlam = 400 -> ~10-15 k cells per member, CPML both sides, TF/SF sine source).  One bench
+"step" = one sweep pass of S time steps for every member, starting from FieldInit state, with the
+polarisation update on (pass 1 of IntegratorLinLor1D) and the reflection probe recorded every step.
+
+  value : Gcell-updates/s with inputs (CPML profiles, source tables) already resident in HBM
+  e2e   : the same step through the host API (sweep.MemberBatch): pinned-host -> device copy of the
+          inputs, on-device state clear, S steps, device -> host copy of the probe traces
+  roofline : the tile kernel's algorithmic HBM bytes (k = 1 figure of SURVEY 8d) / its CUDA-event
+          time, against the measured HBM peak.  The kernel is temporally blocked (k steps per HBM
+          round trip), so a fraction above 1 is the design goal, not an error: `temporal_block_k`
+          and `hbm_bytes_per_launch_model` say how many bytes a launch really moves.
+  cpu_baseline : the oracle's C port of the reference loop on the host cores (bounded sample)
+
+--impl reference times that CPU port with every host thread, same workload family, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+METRIC = "Gcell-updates/s batched dispersive 1D FDTD"
+UNIT = "Gcell-updates/s"
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def member_specs(n_members, n_freq=64):
+    """(frequency, amplitude) of every member: n_freq frequencies x amplitudes."""
+    freqs = np.linspace(6e9, 10.5e9, n_freq)
+    n_amp = max(1, (n_members + n_freq - 1) // n_freq)
+    amps = np.linspace(0.1, 10.0, n_amp) if n_amp > 1 else np.array([1.0])
+    out = []
+    for a in amps:
+        for f in freqs:
+            out.append((float(f), float(a)))
+    return out[:n_members]
+
+
+def alg_bytes_per_cell_step(L, pw, mf, mr):
+    """SURVEY 8(d) state-only bytes per cell-update, summed over one member's cells (k = 1):
+    32 B per cell (Ex, Hy r+w) + 64 B per CPML cell (psi_E, psi_H r+w, 4 profile reads)
+    + 40 B per Lorentz slab cell (Dx r+w, P r+w, Pprev r)."""
+    cpml = max(0, pw - 1) + pw
+    slab = max(0, mr - mf)
+    return 32 * L + 64 * cpml + 40 * slab
+
+
+class ProductWorkload:
+    def __init__(self, n_members, steps_per_pass, n_freq):
+        import pyfdtd_b200  # noqa: F401
+        from pyfdtd_b200 import MasterController as MC, Environment_Setup as envDef, Solver_Engine as SE, sweep
+        self.sweep = sweep
+        specs = member_specs(n_members, n_freq)
+        first_of_freq = {}
+        members, share = [], []
+        for i, (f, amp) in enumerate(specs):
+            if f in first_of_freq:
+                j = first_of_freq[f]
+                base = members[j]
+                V, P, C_V, C_P = base.V, base.P, base.C_V, base.C_P
+                m = sweep.Member(V, P, C_V, C_P, base._Exs * amp, base._Hys * amp, [P.x2Loc], nsteps=steps_per_pass)
+                share.append(j)
+            else:
+                tup = envDef.envSetup(f, 0.7, 7000, 8000, LorMed=True)
+                P = MC.Params(*tup, False, 0.7, f, 20)
+                P.TFSF, P.SineCont, P.Periods, P.LorentzMed, P.FreeSpace = True, True, 1000, True, False
+                V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
+                C_P = MC.CPML_Params(P.dz)
+                C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
+                for _ in range(2):   # pass 1 state of the setup chain (twice-corrected plasma frequency)
+                    C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=True)
+                m = sweep.Member(V, P, C_V, C_P, Exs * amp, Hys * amp, [P.x2Loc], nsteps=steps_per_pass)
+                m._Exs, m._Hys = Exs, Hys
+                first_of_freq[f] = i
+                share.append(i)
+            # only the first steps_per_pass entries of the source tables are used
+            m.T = steps_per_pass
+            m.srcE, m.srcH = m.srcE[:steps_per_pass], m.srcH[:steps_per_pass]
+            members.append(m)
+        self.members = members
+        self.batch = sweep.MemberBatch(members, "lorentz", share_coef=share)
+        self.cell_steps = self.batch.cell_steps
+        self.alg_bytes_per_step = sum(alg_bytes_per_cell_step(m.L, m.scalars["pw"], m.scalars["mf"], m.scalars["mr"])
+                                      for m in members)          # per time step, all members
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=1)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rate(n_members, steps, threads, warmup=1, reps=1):
+    """Time the oracle's C restatement of IntegratorLinLor1D's pass-1 loop on `threads` host threads
+    over `n_members` members of the bench workload family (bounded sample)."""
+    import ctypes
+    import fdtd_oracle as fo
+    specs = member_specs(n_members, n_freq=min(64, n_members))
+    passes = []
+    for f, amp in specs:
+        c = fo.make_case("lorentz", f, 0.7, 7000, 8000, source="sine", periods=1000)
+        wp = c.medium["wp"]
+        for _ in range(2):
+            wp, _ = fo.spatial_stab(c.Nz, c.dz, c.freq, c.dt, wp, c.medium["w0"], c.medium["gam"])
+        Exs, Hys = fo.sources(c)
+        passes.append((c, fo.PassArrays(c, wp, Exs * amp, Hys * amp, [c.x2Loc], False)))
+    Grids = fo.OrcGrid * len(passes)
+    T_tot = (ctypes.c_int * len(passes))(*[c.T for c, _ in passes])
+    cells = sum(c.L for c, _ in passes) * steps
+    lib = fo.lib()
+    times = []
+    for it in range(warmup + reps):
+        for _, pa in passes:
+            for a in (pa.Ex, pa.Hy, pa.Dx, pa.P, pa.Pprev, pa.psiE, pa.psiH):
+                a[:] = 0.0
+        grids = Grids(*[pa.g for _, pa in passes])
+        t0 = time.perf_counter()
+        lib.orc_run_batch(grids, len(passes), 1, 1, 0, steps, T_tot, threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return cells / np.mean(times) / 1e9, float(np.mean(times)), cells
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_members = max(threads, min(args.members, 4 * threads))
+    steps = args.cpu_steps
+    rate, sec, cells = cpu_port_rate(n_members, steps, threads, warmup=args.warmup, reps=args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batched Lorentz-ADE+CPML 1D FDTD sweep (reference IntegratorLinLor1D pass-1 loop), "
+                               f"CPU sample: {n_members} members x {steps} steps, Nz~10-15k cells/member"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_members} members x {steps} steps ({cells/1e9:.2f} Gcell-updates/step), C port of the "
+                                   "reference loop (oracle/fdtd_oracle.c), one member per thread"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--members", type=int, default=1024, help="sweep members per GPU")
+    ap.add_argument("--pass-steps", type=int, default=512, help="time steps per bench step (S)")
+    ap.add_argument("--k-block", type=int, default=0, help="time steps per launch (0 = library default)")
+    ap.add_argument("--n-freq", type=int, default=64)
+    ap.add_argument("--cpu-steps", type=int, default=1024)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fma", action="store_true", help="PF_F_FMA kernels (not bit-identical; reported in config)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import pyfdtd_b200  # noqa: F401
+    from pyfdtd_b200 import Solver_Engine as SE, _native as nat
+    SE.USE_FMA = bool(args.fma)
+    lib = nat.lib()
+    wl = ProductWorkload(args.members, args.pass_steps, args.n_freq)
+    batch = wl.batch
+    kcfg = [nat.c_int(), nat.c_int(), nat.c_int()]
+    lib.pf_tile_config(*kcfg)
+    k_block = args.k_block or 64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        batch.reset_state()
+        batch.run(do_pol=True, k_block=args.k_block)
+
+    def step_e2e():
+        batch.upload()
+        batch.reset_state()
+        batch.run(do_pol=True, k_block=args.k_block)
+        return batch.download_probes()
+
+    batch.upload()
+    for _ in range(args.warmup):
+        step_resident()
+    # ---- timed region: K steps, device-timed, max over ranks -------------------------------
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.pf_launch_count()
+    lib.pf_profile_enable(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    lib.pf_profile_enable(0)
+    clocks = sampler.stop()
+    launches = lib.pf_launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    kms, kn = nat.c_double(), nat.c_int()
+    lib.pf_profile_collect(kms, kn)
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region -------------------------------
+    for _ in range(min(2, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        traces = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    probe_checksum = float(sum(np.abs(t).sum() for t in traces))
+
+    t_dev = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = [float(x) for x in t_dev.cpu()]
+    total_cell_steps = wl.cell_steps * world * args.steps
+    value = total_cell_steps / (ms_total * 1e-3) / 1e9
+    e2e_value = total_cell_steps / (e2e_ms * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))["hbm_gbs"]
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    n_launch_per_step = max(1, kn.value // max(1, args.steps))
+    avg_kernel_ms = kms.value / max(1, kn.value)
+    alg_bytes_per_launch = wl.alg_bytes_per_step * args.pass_steps / n_launch_per_step
+    achieved = alg_bytes_per_launch / (avg_kernel_ms * 1e-3) / 1e9
+    tile_cells, halo = kcfg[0].value, k_block
+    # modelled real HBM traffic of one launch: every tile reads tile_cells of state, writes its interior
+    hbm_model = wl.alg_bytes_per_step * (1.0 + 2.0 * halo / (tile_cells - 2 * halo))
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_tile<PF_LORENTZ,POL,8,Exact>", "peak_source": peak_src,
+                "kernel_ms_avg": avg_kernel_ms, "kernel_launches_timed": kn.value,
+                "kernel_share_of_step": kms.value / ms_total if ms_total else None,
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "temporal_block_k": k_block,
+                "hbm_bytes_per_launch_model": hbm_model,
+                "note": "on-chip temporally blocked: algorithmic (k=1) bytes / time exceeds the HBM roofline by design"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        n_cpu = max(threads, min(args.members, 4 * threads))
+        rate, sec, cells = cpu_port_rate(n_cpu, args.cpu_steps, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n_cpu} members x {args.cpu_steps} steps of the same sweep family on {threads} threads "
+                         f"({sec:.2f} s wall)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"batched Lorentz-ADE+CPML 1D FDTD sweep, {args.members} members/GPU x "
+                                   f"{args.pass_steps} time steps per step, Nz~10-15k cells/member "
+                                   f"({wl.cell_steps/1e9:.2f} Gcell-updates/step/GPU), probes recorded every step",
+                       "members_per_gpu": args.members, "time_steps_per_step": args.pass_steps,
+                       "k_block": k_block, "arithmetic": "fma-contracted" if args.fma else "exact (bit-identical to reference order)",
+                       "l2_policy": f"state {batch.n_state*8/1e6:.0f} MB per GPU > 126 MB L2, re-initialised every step",
+                       "parallelism": f"members sharded over {world} GPU(s), no collectives"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes, "d2h_bytes_per_step": batch.d2h_bytes,
+                    "ms_per_step": e2e_ms / args.steps, "probe_checksum": probe_checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

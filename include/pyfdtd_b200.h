@@ -145,6 +145,12 @@ int pf_run_batch(const PfGrid *grids, int n_grids, int mode, int do_pol, int n0,
                  int k_block, void *scratch, size_t scratch_bytes, void *stream);
 size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine);
 
+/* Per-launch timing of the tile kernel (the dominant kernel): while enabled, every k_tile launch is
+ * bracketed by CUDA events on its own stream; pf_profile_collect() waits for them, returns the summed
+ * kernel time [ms] and the number of launches, and clears the list.                              */
+int pf_profile_enable(int on);
+int pf_profile_collect(double *ms_total, int *n_launches);
+
 /* tile-engine introspection (bench / tests): tile width in cells, max k, threads per CTA       */
 int pf_tile_config(int *tile_cells, int *k_max, int *threads);
 
@@ -168,7 +174,10 @@ typedef struct PfPic {
     double jx_scale;      /* Jx_slot contribution per particle = jx_scale * w * vx * shape       */
     /* particle SoA (device): position z [m], momenta ux = gamma*vx, uz = gamma*vz [m/s], weight */
     double *z, *ux, *uz, *w;
-    int32_t *cell;        /* cell index floor(z/dz), maintained by push                          */
+    int32_t *cell;        /* cell index floor(z/dz) clamped to [0, L-2], maintained by push      */
+    /* output arrays of pf_pic_sort (same sizes); the caller swaps the two sets after a sort       */
+    double *z_alt, *ux_alt, *uz_alt, *w_alt;
+    int32_t *cell_alt;
     /* fields (device, length L): Ex at integer nodes, Hy at half nodes nz+1/2                   */
     const double *Ex, *Hy;
     double *Jx;           /* output current slot, length L (overwritten by deposit)             */
@@ -176,7 +185,8 @@ typedef struct PfPic {
 
 /* relativistic Boris push + linear (CIC) field gather; updates z, ux, uz, cell                  */
 int pf_pic_push(const PfPic *p, void *stream);
-/* sort particles by cell (stable; keys = cell); scratch sized by pf_pic_scratch_bytes          */
+/* stable sort of the particles by cell: reads z,ux,uz,w,cell, writes the *_alt arrays;
+ * scratch sized by pf_pic_scratch_bytes                                                          */
 int pf_pic_sort(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
 /* deterministic cell-sorted deposition of Jx (requires particles sorted by cell)               */
 int pf_pic_deposit(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);

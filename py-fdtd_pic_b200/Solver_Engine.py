@@ -196,41 +196,45 @@ def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=F
     return out["probe_out"]
 
 
-def _linear_probes(V, P):
-    atten = list(atten_probe_cells(V, P)) if P.atten else []
-    return atten
+def prepare_pass(V, P, C_V, C_P, lorentz, nonlinear=False):
+    """Host-side setup the reference repeats at the start of every pass (Solver_Engine.py:144-160,
+    223-232, 278-287): zero the fields, rebuild update / CPML coefficients, re-apply the dispersion
+    correction of the plasma frequency (cumulative!), build the source tables.  Returns (C_V, Exs, Hys)."""
+    (V.tempVarPol, V.tempTempVarE, V.tempVarE, V.tempTempVarPol, V.polarisationCurr, V.Ex, V.Dx,
+     V.Hy) = BaseFDTD11.FieldInit(V, P)
+    V.UpHyMat, V.UpExMat = BaseFDTD11.EmptySpaceCalc(V, P)
+    free = not lorentz and not nonlinear
+    if free:
+        (V.epsilon, V.mu, V.UpExHcompsCo, V.UpExSelf, V.UpHyEcompsCo,
+         V.UpHySelf) = BaseFDTD11.Material(V, P)
+        V.UpHyMat, V.UpExMat = BaseFDTD11.UpdateCoef(V, P)
+    C_V = BaseFDTD11.CPML_FieldInit(V, P, C_V, C_P)
+    C_V = boundCondManager(V, P, C_V, C_P)
+    if not free:
+        _, _, _, V.plasmaFreqE, _ = gStab.spatialStab(P.timeSteps, P.Nz, P.dz, P.freq_in, P.delT,
+                                                       V.plasmaFreqE, V.omega_0E, V.gammaE)
+    Exs, Hys = SourceManager(V, P, C_V, C_P)
+    if free:
+        tauIn = 1 / (P.freq_in / 5)
+        Exs = Sig_Mod(V, P, Exs, tau=tauIn)
+        Hys = Sig_Mod(V, P, Hys, AmpMod=1 / P.CharImp, tau=tauIn)
+    return C_V, Exs, Hys
 
 
 def _two_pass(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf, lorentz):
     """Shared body of IntegratorFreeSpace1D / IntegratorLinLor1D: pass 0 = incident run (probe x1Loc),
     pass 1 = run with the medium's polarisation (probe x2Loc, history, attenuation probes)."""
     n = np.arange(P.timeSteps)
+    mode = "lorentz" if lorentz else "free"
     for i in range(2):
-        (V.tempVarPol, V.tempTempVarE, V.tempVarE, V.tempTempVarPol, V.polarisationCurr, V.Ex, V.Dx,
-         V.Hy) = BaseFDTD11.FieldInit(V, P)
-        V.UpHyMat, V.UpExMat = BaseFDTD11.EmptySpaceCalc(V, P)
-        if not lorentz:
-            (V.epsilon, V.mu, V.UpExHcompsCo, V.UpExSelf, V.UpHyEcompsCo,
-             V.UpHySelf) = BaseFDTD11.Material(V, P)
-            V.UpHyMat, V.UpExMat = BaseFDTD11.UpdateCoef(V, P)
-        C_V = BaseFDTD11.CPML_FieldInit(V, P, C_V, C_P)
-        C_V = boundCondManager(V, P, C_V, C_P)
-        if lorentz:
-            _, _, _, V.plasmaFreqE, _ = gStab.spatialStab(P.timeSteps, P.Nz, P.dz, P.freq_in, P.delT,
-                                                           V.plasmaFreqE, V.omega_0E, V.gammaE)
-        Exs, Hys = SourceManager(V, P, C_V, C_P)
-        if not lorentz:
-            tauIn = 1 / (P.freq_in / 5)
-            Exs = Sig_Mod(V, P, Exs, tau=tauIn)
-            Hys = Sig_Mod(V, P, Hys, AmpMod=1 / P.CharImp, tau=tauIn)
+        C_V, Exs, Hys = prepare_pass(V, P, C_V, C_P, lorentz)
         V.test = 0
         if i == 0:
-            traces = run_time_loop(V, P, C_V, C_P, "lorentz" if lorentz else "free", False, Exs, Hys, [P.x1Loc])
+            traces = run_time_loop(V, P, C_V, C_P, mode, False, Exs, Hys, [P.x1Loc])
             V.x1ColBe = np.where(n <= probeReadFinishBe, traces[0], V.x1ColBe)
         else:
-            atten = _linear_probes(V, P)
-            traces = run_time_loop(V, P, C_V, C_P, "lorentz" if lorentz else "free", lorentz, Exs, Hys,
-                                   [P.x2Loc] + atten, snapshots=True)
+            atten = list(atten_probe_cells(V, P)) if P.atten else []
+            traces = run_time_loop(V, P, C_V, C_P, mode, lorentz, Exs, Hys, [P.x2Loc] + atten, snapshots=True)
             window = n >= probeReadStartAf
             V.x1ColAf = np.where(window, traces[0], V.x1ColAf)
             for k in range(len(atten)):
@@ -250,14 +254,7 @@ def IntegratorLinLor1D(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf):
 
 def IntegratorNL1D(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf):
     """Solver_Engine.py:220-271 -- cubic nonlinear medium, per-cell cubic solve every step, one pass."""
-    (V.tempVarPol, V.tempTempVarE, V.tempVarE, V.tempTempVarPol, V.polarisationCurr, V.Ex, V.Dx,
-     V.Hy) = BaseFDTD11.FieldInit(V, P)
-    V.UpHyMat, V.UpExMat = BaseFDTD11.EmptySpaceCalc(V, P)
-    C_V = BaseFDTD11.CPML_FieldInit(V, P, C_V, C_P)
-    C_V = boundCondManager(V, P, C_V, C_P)
-    _, _, _, V.plasmaFreqE, _ = gStab.spatialStab(P.timeSteps, P.Nz, P.dz, P.freq_in, P.delT, V.plasmaFreqE,
-                                                   V.omega_0E, V.gammaE)
-    Exs, Hys = SourceManager(V, P, C_V, C_P)
+    C_V, Exs, Hys = prepare_pass(V, P, C_V, C_P, lorentz=False, nonlinear=True)
     traces = run_time_loop(V, P, C_V, C_P, "nl", False, Exs, Hys, [P.materialFrontEdge, P.materialRearEdge],
                            snapshots=True)
     V.Port1, V.Port2 = traces[0], traces[1]

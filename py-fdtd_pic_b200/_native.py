@@ -47,6 +47,7 @@ class PfPic(ctypes.Structure):
         ("dz", c_double), ("dt", c_double), ("q_over_m", c_double), ("c", c_double), ("mu0", c_double),
         ("jx_scale", c_double),
         ("z", _dp), ("ux", _dp), ("uz", _dp), ("w", _dp), ("cell", _dp),
+        ("z_alt", _dp), ("ux_alt", _dp), ("uz_alt", _dp), ("w_alt", _dp), ("cell_alt", _dp),
         ("Ex", _dp), ("Hy", _dp), ("Jx", _dp),
     ]
 
@@ -75,6 +76,8 @@ SYMBOLS = {
     "pf_run_pass": (c_int, [_G, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_batch": (c_int, [_G, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_scratch_bytes": (c_size_t, [_G, c_int, c_int]),
+    "pf_profile_enable": (c_int, [c_int]),
+    "pf_profile_collect": (c_int, [POINTER(c_double), POINTER(c_int)]),
     "pf_tile_config": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "pf_halo_pack": (ctypes.c_longlong, [_G, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pf_halo_unpack": (ctypes.c_longlong, [_G, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -391,11 +391,32 @@ static TilePlan tile_plan(const PfGrid *grids, int n, int mode, int halo)
     return p;
 }
 
+// ---- optional per-launch timing of the dominant kernel (bench.py's roofline numerator) ----------
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+
+struct ProfScope {
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit ProfScope(cudaStream_t s) : st(s)
+    {
+        if (g_prof_on && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+    }
+    ~ProfScope()
+    {
+        if (a && b) {
+            cudaEventRecord(b, st);
+            g_prof_events.emplace_back(a, b);
+        }
+    }
+};
+
 template <int MODE, bool POL, int C>
 static int launch_tile(bool fma, int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
                        int n0, int ks, int halo, cudaStream_t st)
 {
     size_t sm = TileSmem<MODE, C>::bytes;
+    ProfScope prof(st);
     if (fma) {
         static bool set = false;
         if (!set) { PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, Fused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); set = true; }
@@ -533,6 +554,31 @@ size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine)
     if (engine != PF_ENGINE_TILE || !grids || n_grids <= 0) return 0;
     // sized for the largest state set (Lorentz) and the smallest tile interior (largest tile count)
     return tile_plan(grids, n_grids, PF_LORENTZ, TILE_KMAX).total;
+}
+
+int pf_profile_enable(int on)
+{
+    g_prof_on = on != 0;
+    return PF_OK;
+}
+
+int pf_profile_collect(double *ms_total, int *n_launches)
+{
+    double tot = 0.0;
+    int n = 0;
+    for (auto &ev : g_prof_events) {
+        float ms = 0.f;
+        PF_CUDA(cudaEventSynchronize(ev.second));
+        PF_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        tot += ms;
+        ++n;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    g_prof_events.clear();
+    if (ms_total) *ms_total = tot;
+    if (n_launches) *n_launches = n;
+    return PF_OK;
 }
 
 int pf_tile_config(int *tile_cells, int *k_max, int *threads)

@@ -1,0 +1,273 @@
+"""Batched sweeps: many independent 1-D runs advanced together by the fused tile engine.
+
+The reference's sweep driver is ``MasterController.LoopedSim(loop=True)`` (:533-569): 20 sequential
+frequency points, each rebuilding Params/Variables and calling ``Controller``.  Members share nothing,
+so here every member becomes one ``PfGrid`` and one ``pf_run_batch`` call advances all of them
+(one CTA per tile of a member, k time steps per launch).  Members may differ in every parameter:
+grid size, step count, dz/dt, medium, source.
+
+Data movement per pass: ONE host->device copy (CPML profiles + source tables of all members; the
+state starts from FieldInit zeros and is cleared on the device) and ONE device->host copy (probe
+traces, optionally final fields).  With several GPUs members are dealt out round-robin
+(``member % world_size``); there is no data-path collective.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import BaseFDTD11, Environment_Setup as envDef, Solver_Engine as SE
+from . import _device as dev
+from . import _native as nat
+
+STATE_NAMES = ("Ex", "Hy", "psiE", "psiH", "Dx", "P", "Pprev", "Acubic")
+COEF_NAMES = ("beX", "ceX", "cmY")
+
+
+class Member:
+    """Host-side description of one sweep member for one pass."""
+
+    def __init__(self, V, P, C_V, C_P, Exs, Hys, probe_idx, nsteps=None):
+        self.V, self.P, self.C_V, self.C_P = V, P, C_V, C_P
+        self.L = len(V.Ex)
+        self.T = int(P.timeSteps)
+        self.nsteps = self.T if nsteps is None else int(nsteps)
+        self.srcE = np.asarray(Exs) / P.courantNo
+        self.srcH = np.asarray(Hys) / P.courantNo
+        self.probe_idx = [int(p) for p in probe_idx]
+        arrs = BaseFDTD11._host_arrays(V, C_V, V.tempVarPol)
+        canon = dev.canonical_form(P, arrs, None)
+        if canon is None or not dev.probes_ok_for_tiles(self.probe_idx):
+            raise ValueError("sweep member is not in the tile engine's canonical form; run it through Controller")
+        self.scalars = BaseFDTD11.grid_scalars(V, P)
+        self.scalars.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
+        self.flags = BaseFDTD11.grid_flags(P, SE.USE_FMA) | nat.PF_F_CANONICAL
+        self.coef = {"beX": C_V.beX, "ceX": C_V.ceX, "cmY": C_V.cmY}
+
+
+class MemberBatch:
+    """Device-resident batch of members + the PfGrid array handed to pf_run_batch."""
+
+    def __init__(self, members, mode, device=None, share_coef=None):
+        torch = nat.require_cuda()
+        self.torch = torch
+        self.members = members
+        self.mode = mode
+        self.mode_id = dev.MODE_ID[mode]
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        M = len(members)
+        # ---- layout (doubles): [state of all members][coef+src of all members][probes of all members]
+        self.off_state, self.off_in, self.off_probe = [], [], []
+        cur = 0
+        for m in members:
+            Lp = (m.L + 31) // 32 * 32
+            self.off_state.append(cur)
+            cur += len(STATE_NAMES) * Lp
+        self.n_state = cur
+        share_coef = share_coef or list(range(M))      # member -> index of the member whose coef it reuses
+        self.share = share_coef
+        for i, m in enumerate(members):
+            Lp = (m.L + 31) // 32 * 32
+            Tp = (m.T + 31) // 32 * 32
+            self.off_in.append(cur)
+            cur += (len(COEF_NAMES) * Lp if share_coef[i] == i else 0) + 2 * Tp
+        self.n_in = cur - self.n_state
+        for m in members:
+            Tp = (m.T + 31) // 32 * 32
+            self.off_probe.append(cur)
+            cur += max(len(m.probe_idx), 1) * Tp
+        self.n_probe = cur - self.n_state - self.n_in
+        self.n_total = cur
+        self.pool = torch.empty(cur, dtype=torch.float64, device=self.device)
+        self.host_in = torch.zeros(self.n_in, dtype=torch.float64).pin_memory()
+        self.host_probe = torch.zeros(self.n_probe, dtype=torch.float64).pin_memory()
+        pidx = np.concatenate([np.asarray(m.probe_idx or [0], dtype=np.int32) for m in members])
+        self.pidx_off = np.concatenate([[0], np.cumsum([max(len(m.probe_idx), 1) for m in members])])
+        self.host_pidx = torch.from_numpy(pidx).pin_memory()
+        self.pidx = torch.empty(len(pidx), dtype=torch.int32, device=self.device)
+        self.grids = (nat.PfGrid * M)()
+        self.nsteps = (ctypes.c_int * M)(*[m.nsteps for m in members])
+        self._fill_host_inputs()
+        self._fill_descriptors()
+        self.scratch_bytes = nat.lib().pf_run_scratch_bytes(self.grids, M, nat.PF_ENGINE_TILE)
+        self.scratch = torch.empty(self.scratch_bytes, dtype=torch.uint8, device=self.device)
+        self.h2d_bytes = self.n_in * 8 + len(pidx) * 4
+        self.d2h_bytes = self.n_probe * 8
+        self.cell_steps = sum(m.L * m.nsteps for m in members)
+
+    # -- host staging -------------------------------------------------------------------------
+    def _coef_offset(self, i, name):
+        j = self.share[i]
+        Lp = (self.members[j].L + 31) // 32 * 32
+        return self.off_in[j] + COEF_NAMES.index(name) * Lp
+
+    def _src_offset(self, i, which):
+        m = self.members[i]
+        Lp = (m.L + 31) // 32 * 32
+        Tp = (m.T + 31) // 32 * 32
+        base = self.off_in[i] + (len(COEF_NAMES) * Lp if self.share[i] == i else 0)
+        return base + which * Tp
+
+    def _fill_host_inputs(self):
+        hv = self.host_in.numpy()
+        o0 = self.n_state
+        for i, m in enumerate(self.members):
+            if self.share[i] == i:
+                for name in COEF_NAMES:
+                    o = self._coef_offset(i, name) - o0
+                    hv[o:o + m.L] = m.coef[name]
+            o = self._src_offset(i, 0) - o0
+            hv[o:o + len(m.srcE)] = m.srcE
+            o = self._src_offset(i, 1) - o0
+            hv[o:o + len(m.srcH)] = m.srcH
+
+    def _fill_descriptors(self):
+        base = self.pool.data_ptr()
+        for i, m in enumerate(self.members):
+            g = self.grids[i]
+            Lp = (m.L + 31) // 32 * 32
+            Tp = (m.T + 31) // 32 * 32
+            s = m.scalars
+            g.L, g.pw, g.mf, g.mr, g.nzsrc = m.L, s["pw"], s["mf"], s["mr"], s["nzsrc"]
+            g.flags = m.flags
+            g.n_probes, g.probe_stride = len(m.probe_idx), Tp
+            g.z0, g.Lg = 0, m.L
+            for k in ("dt_over_dz", "eps0", "polA", "polB", "polC", "cub_a", "cub_b", "cub_c", "nl_den0", "nl_den1",
+                      "cE0", "cE1", "cH0", "cH1", "c2_pml"):
+                setattr(g, k, float(s[k]))
+            for a, name in enumerate(STATE_NAMES):
+                setattr(g, name, base + 8 * (self.off_state[i] + a * Lp))
+            for name in COEF_NAMES:
+                setattr(g, name, base + 8 * self._coef_offset(i, name))
+            g.bmY = g.beX
+            g.srcE = base + 8 * self._src_offset(i, 0)
+            g.srcH = base + 8 * self._src_offset(i, 1)
+            g.probe_idx = self.pidx.data_ptr() + 4 * int(self.pidx_off[i])
+            g.probe_out = base + 8 * self.off_probe[i]
+
+    # -- device side --------------------------------------------------------------------------
+    def upload(self):
+        """H2D of every member's CPML profiles + source tables (one copy) and the probe indices."""
+        self.pool[self.n_state:self.n_state + self.n_in].copy_(self.host_in, non_blocking=True)
+        self.pidx.copy_(self.host_pidx, non_blocking=True)
+
+    def reset_state(self):
+        """FieldInit / CPML_FieldInit on the device: zero fields, polarisation, psi and probe traces."""
+        self.pool[: self.n_state].zero_()
+        self.pool[self.n_state + self.n_in:].zero_()
+
+    def run(self, do_pol, n0=0, k_block=0):
+        nat.check(nat.lib().pf_run_batch(self.grids, len(self.members), self.mode_id, int(do_pol), int(n0),
+                                         self.nsteps, int(k_block), self.scratch.data_ptr(), self.scratch_bytes,
+                                         nat.current_stream_ptr()), "pf_run_batch")
+
+    def download_probes(self):
+        """D2H of all probe traces (one copy) -> list of arrays [n_probes, T] per member."""
+        self.host_probe.copy_(self.pool[self.n_state + self.n_in:], non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        hv = self.host_probe.numpy()
+        out = []
+        o0 = self.n_state + self.n_in
+        for i, m in enumerate(self.members):
+            Tp = (m.T + 31) // 32 * 32
+            n_p = len(m.probe_idx)
+            a = hv[self.off_probe[i] - o0: self.off_probe[i] - o0 + max(n_p, 1) * Tp]
+            out.append(a.reshape(max(n_p, 1), Tp)[:n_p, : m.T].copy())
+        return out
+
+    def state(self, i, name):
+        """Device -> host copy of one state array of member i (tests / final fields)."""
+        m = self.members[i]
+        Lp = (m.L + 31) // 32 * 32
+        o = self.off_state[i] + STATE_NAMES.index(name) * Lp
+        return self.pool[o:o + m.L].cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+def new_member_objects(freq_in, domainSize, lowLimTim, highLimTim, prevV, prevP, template_P):
+    """One iteration of the reference sweep's object construction (MasterController.py:545-551):
+    the grid is sized from the PREVIOUS member's (dispersion-corrected) medium."""
+    from . import MasterController as MC
+    prevP.freq_in = freq_in
+    tup = envDef.envSetup(freq_in, domainSize, lowLimTim, highLimTim, VExists=True, V=prevV, P=prevP)
+    P = MC.Params(*tup, template_P.MORmode, domainSize, freq_in, 20, LorentzMed=template_P.LorentzMed,
+                  SineCont=template_P.SineCont, Gaussian=template_P.Gaussian, TFSF=template_P.TFSF)
+    V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
+    C_P = MC.CPML_Params(P.dz)
+    C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
+    return V, P, C_V, C_P
+
+
+def run_two_pass_batch(objs, lorentz=True, k_block=0, rank=0, world_size=1):
+    """Run the two-pass (incident / with medium) integrator for every (V,P,C_V,C_P) in ``objs`` as a
+    batch.  Fills V.x1ColBe / V.x1ColAf and the final fields of every member owned by this rank
+    (member % world_size == rank) and returns the indices of the owned members."""
+    mode = "lorentz" if lorentz else "free"
+    mine = [i for i in range(len(objs)) if i % world_size == rank]
+    srcs = {}
+    for pass_idx in range(2):
+        members = []
+        for i in mine:
+            V, P, C_V, C_P = objs[i]
+            C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz)
+            objs[i] = (V, P, C_V, C_P)
+            srcs[i] = (Exs, Hys)
+            members.append(Member(V, P, C_V, C_P, Exs, Hys, [P.x1Loc if pass_idx == 0 else P.x2Loc]))
+        if not members:
+            continue
+        batch = MemberBatch(members, mode)
+        batch.upload()
+        batch.reset_state()
+        batch.run(do_pol=(lorentz and pass_idx == 1), k_block=k_block)
+        traces = batch.download_probes()
+        for j, i in enumerate(mine):
+            V, P, C_V, C_P = objs[i]
+            n = np.arange(P.timeSteps)
+            if pass_idx == 0:
+                V.x1ColBe = np.where(n <= int(P.timeSteps * 0.7), traces[j][0], 0.0)
+            else:
+                V.x1ColAf = np.where(n >= int(P.timeSteps * 0.05), traces[j][0], 0.0)
+                V.Ex, V.Hy = batch.state(j, "Ex"), batch.state(j, "Hy")
+    return mine, srcs
+
+
+def frequency_sweep(V, P, domainSize, lowLimTim, highLimTim, Low=3e9, Interval=1e8, points=20, batched=True):
+    """MasterController.LoopedSim(loop=True) :533-569.  Returns (freqs, measured R, analytical R,
+    (V,P,C_V,C_P,Exs,Hys) of the last member)."""
+    from . import MasterController as MC
+    freqs = np.arange(Low, points * Interval + Low, Interval)[:points]
+    # -- setup chain (sequential by construction: member i is sized from member i-1's corrected medium;
+    #    the correction itself is host-side setup, so it does not need member i-1's fields)
+    objs = []
+    prevV, prevP = V, P
+    freq = P.freq_in
+    for _ in range(points):
+        Vi, Pi, CVi, CPi = new_member_objects(freq, domainSize, lowLimTim, highLimTim, prevV, prevP, P)
+        objs.append((Vi, Pi, CVi, CPi))
+        if batched:
+            # what Controller will leave in V.plasmaFreqE after its two passes (Solver_Engine.py:286)
+            shadow = MC.Variables(Pi.Nz, 1, 1, 1)
+            wp = Vi.plasmaFreqE
+            if Pi.LorentzMed:
+                from . import genericStability as gStab
+                for _k in range(2):
+                    wp = gStab.spatialStab(Pi.timeSteps, Pi.Nz, Pi.dz, Pi.freq_in, Pi.delT, wp, Vi.omega_0E, Vi.gammaE)[3]
+            shadow.plasmaFreqE = wp
+            prevV, prevP = shadow, Pi
+        else:
+            MC.Controller(Vi, Pi, CVi, CPi)
+            prevV, prevP = Vi, Pi
+        freq = Pi.freq_in + Interval
+    srcs = {}
+    if batched:
+        _, srcs = run_two_pass_batch(objs, lorentz=bool(P.LorentzMed), k_block=0)
+    measured = np.zeros(points)
+    analytical = np.zeros(points)
+    for i, (Vi, Pi, CVi, CPi) in enumerate(objs):
+        t = np.arange(0, len(Vi.x1ColBe)) * Pi.delT
+        measured[i] = MC.results(Vi, Pi, CVi, CPi, t, RefCo=True)
+        analytical[i] = MC.results(Vi, Pi, CVi, CPi, t, AnalRefCo=True)
+    Vi, Pi, CVi, CPi = objs[-1]
+    Exs, Hys = srcs.get(points - 1, (None, None))
+    return freqs, measured, analytical, (Vi, Pi, CVi, CPi, Exs, Hys)

@@ -1,0 +1,113 @@
+"""The CPU oracle against the outputs of the UNMODIFIED reference (tests/golden, made by
+oracle/make_golden.py).  This is what pins the oracle (the reference's own tests hold
+no vectors).  Bitwise equality is expected when the host libm / numpy SIMD dispatch match the machine
+that generated the goldens; the hard bound is BASELINE's 1e-10 relative."""
+import json
+
+import numpy as np
+import pytest
+
+import fdtd_oracle as fo
+from conftest import load_golden
+
+SINGLE = ["free_sine_eps4", "free_gauss_eps4", "free_gauss_notfsf", "lorentz_sine", "lorentz_gauss",
+          "lorentz_sine_6g", "nl_sine", "nl_sine_amp", "lorentz_default_full", "free_default_full"]
+RTOL = 1e-10
+
+
+def rel_err(got, want):
+    scale = np.max(np.abs(want))
+    if scale == 0:
+        return float(np.max(np.abs(got)))
+    return float(np.max(np.abs(np.asarray(got) - np.asarray(want))) / scale)
+
+
+def case_from_golden(g):
+    s = g["spec"]
+    c = fo.make_case(s["mode"], s["freq"], s["dom"], *s["win"], source=s.get("source", "sine"),
+                     tfsf=s.get("tfsf", True), periods=s.get("periods", 1000.0), epsRe=s.get("epsRe", 1.0),
+                     amplitude=s.get("amplitude", 1.0))
+    return c
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_oracle_matches_reference(name):
+    g = load_golden(name)
+    v = g["versions"]
+    if (v["epsilon_0"], v["mu_0"]) != (fo.EPS0, fo.MU0):
+        pytest.skip("scipy.constants differ from the ones the goldens were generated with")
+    c = case_from_golden(g)
+    assert (c.Nz, c.T, c.pw, c.nzsrc, c.mf, c.mr, c.x1Loc, c.x2Loc) == tuple(
+        int(g[k]) for k in ("Nz", "timeSteps", "pmlWidth", "nzsrc", "mf", "mr", "x1Loc", "x2Loc"))
+    assert c.dz == float(g["dz"]) and c.dt == float(g["delT"]) and c.courantNo == float(g["courantNo"])
+    out = fo.run_case(c, snapshots=True)
+    pairs = [("Ex", "Ex"), ("Hy", "Hy"), ("psi_Ex", "psi_Ex"), ("psi_Hy", "psi_Hy"), ("x1ColBe", "x1ColBe"),
+             ("x1ColAf", "x1ColAf"), ("Exs", "Exs"), ("Hys", "Hys")]
+    if c.mode == "lorentz":
+        pairs += [("P", "polarisationCurr"), ("Dx", "Dx")]
+    if c.mode == "nl":
+        pairs += [("Port1", "Port1"), ("Port2", "Port2"), ("Dx", "Dx"), ("Acubic", "Acubic")]
+    exact = True
+    for mine, theirs in pairs:
+        assert rel_err(out[mine], g[theirs]) <= RTOL, (name, mine)
+        exact &= np.array_equal(out[mine], g[theirs])
+    assert out["plasmaFreqE"] == pytest.approx(float(g["plasmaFreqE"]), rel=1e-14)
+    if "beX" in g:
+        for mine, theirs in (("beX", "beX"), ("ceX", "ceX"), ("cmY", "cmY"), ("Cb", "Cb"), ("C2", "C2"),
+                             ("denE", "den_Exdz"), ("denH", "den_Hydz")):
+            assert rel_err(out["coef"][mine], g[theirs]) <= 1e-14, (name, mine)
+        step = max(1, len(out["Ex_History"]) // 4)
+        assert rel_err(out["Ex_History"][::step], g["Ex_History_rows"]) <= RTOL
+    if c.mode == "lorentz" and np.isfinite(g["reflection"]):
+        assert fo.reflection(out, c) == pytest.approx(float(g["reflection"]), rel=1e-9)
+        m = c.medium
+        assert fo.analytical_reflection(c.freq, out["plasmaFreqE"], m["w0"], m["gam"]) == pytest.approx(
+            float(g["analytical_reflection"]), rel=1e-12)
+    print(f"{name}: oracle {'bitwise ==' if exact else 'within 1e-10 of'} reference")
+
+
+def test_survey_golden_scalars():
+    """SURVEY.md 8c survey-time scalars of the default geometry, re-derived from the golden files."""
+    lor = load_golden("lorentz_default_full")
+    free = load_golden("free_default_full")
+    assert float(lor["sumEx"]) == pytest.approx(-94.55240287165128, rel=1e-12)
+    assert float(lor["maxAbsEx"]) == pytest.approx(1.3231301386834344, rel=1e-12)
+    assert float(free["sumEx"]) == pytest.approx(738.6155800460517, rel=1e-12)
+    assert int(lor["Nz"]) == 13193 and int(lor["timeSteps"]) == 23997 and int(lor["pmlWidth"]) == 2394
+
+
+def test_cubic_root_known_answers():
+    g = load_golden("cubic_roots")
+    lib = fo.lib()
+    co, want = g["coeffs"], g["root0"]
+    got = np.array([lib.orc_cubic_root0(*map(float, row)) for row in co])
+    scale = np.maximum(np.abs(want.real), 1e-300)
+    # root[0] is real in every branch except the complex quadratic fallback (real part compared)
+    assert np.max(np.abs(got - want.real) / scale) <= 1e-12
+    nl_family = co[:, 3] < 0
+    assert np.array_equal(got[: 8 * 43], want.real[: 8 * 43]), "NL-path polynomials must match bit for bit"
+    assert nl_family.any()
+
+
+def test_sweep_reflection_matches_reference():
+    """LoopedSim(loop=True) golden: 20 members, each derived from the previous member's adjusted wp."""
+    g = load_golden("lorentz_sweep")
+    s = g["spec"]
+    med = fo.default_medium()
+    wp_prev = med["wp"]
+    freq = s["freq0"]
+    for i, mem in enumerate(g["members"]):
+        eps = fo.lorentz_eps(wp_prev, med["w0"], med["gam"], freq)
+        c = fo.make_case("lorentz", freq, s["dom"], *s["win"], source="sine", periods=1.0, eps_for_nlam=eps)
+        assert (c.Nz, c.T) == (mem["Nz"], mem["T"]), i
+        if i in (0, 7, 19):   # three members are stepped in full; the rest check the setup chain only
+            out = fo.run_case(c)
+            assert fo.reflection(out, c) == pytest.approx(float(g["measured"][i]), rel=1e-9)
+            wp_prev = out["plasmaFreqE"]
+        else:
+            wp1, _ = fo.spatial_stab(c.Nz, c.dz, c.freq, c.dt, med["wp"], med["w0"], med["gam"])
+            wp_prev, _ = fo.spatial_stab(c.Nz, c.dz, c.freq, c.dt, wp1, med["w0"], med["gam"])
+        assert wp_prev == pytest.approx(mem["wp_after"], rel=1e-14)
+        assert fo.analytical_reflection(freq, wp_prev, med["w0"], med["gam"]) == pytest.approx(
+            float(g["analytical"][i]), rel=1e-12)
+        freq = freq + s["interval"]
