@@ -104,7 +104,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -122,7 +122,7 @@ class ClockSampler(threading.Thread):
                  "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                  "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
                  "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -134,7 +134,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.02)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=1)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}

@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpyfdtd_b200.so")
+LIB_PATH = os.environ.get("PYFDTD_B200_LIB") or os.path.join(HERE, "libpyfdtd_b200.so")  # env override: kernel tuning builds
 
 PF_FREE, PF_LORENTZ, PF_NL = 0, 1, 2
 PF_ENGINE_OPS, PF_ENGINE_TILE = 0, 1

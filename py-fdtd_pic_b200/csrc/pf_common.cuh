@@ -57,13 +57,24 @@ struct Fused {
 // The two-FMA correction is exact whenever e is representable; for |x| so small that the
 // residual could underflow (or non-finite x) the IEEE divide is used instead.  This is an
 // implementation of the division the reference performs, not a contraction of its arithmetic.
+static __device__ __noinline__ double div_const_slow(double x, double d) { return __ddiv_rn(x, d); }
+
 __device__ __forceinline__ double div_const(double x, double d, double r)
 {
     double q = __dmul_rn(x, r);
     double e = __fma_rn(-q, d, x);
     double q2 = __fma_rn(e, r, q);
-    double ax = fabs(x);
-    if (!(ax > 1e-250 && ax < 1e250)) q2 = __ddiv_rn(x, d);  // rare: denormal range, 0, inf, nan
+    // Guard on the exponent field with integer ops (keeps the test off the FP64 pipe): the two-FMA
+    // correction is exact for 2^-823 <= |x| < 2^825.  Outside that range: zero (by far the most
+    // common case -- cells the wave has not reached) already gave q2 = +-0 up to the sign, which q
+    // carries correctly; denormal-range, huge, inf and nan inputs take the IEEE divide, kept out of
+    // line so that it is never evaluated speculatively.
+    const int hi = __double2hiint(x);
+    const unsigned ebits = (unsigned)hi & 0x7ff00000u;
+    if (ebits - 0x0c800000u >= 0x67000000u) {
+        q2 = q;
+        if ((((unsigned)hi & 0x7fffffffu) | (unsigned)__double2loint(x)) != 0u) q2 = div_const_slow(x, d);
+    }
     return q2;
 }
 

@@ -10,10 +10,11 @@
 //
 // On-chip layout
 //   Thread t owns the C consecutive cells [t*C, t*C+C) of the tile.  Ex and Hy of those cells
-//   live in registers for the whole launch.  Material state (Dx, P, P^{n-1}), CPML state
-//   (psi_E, psi_H) and the per-cell CPML profiles (b, c_e, c_m) live in shared memory in
-//   [array][j][thread] order, so each thread only ever touches its own slots (no barrier needed,
-//   and lane-consecutive 8-byte words are bank-conflict free).  The only inter-thread traffic is
+//   and all material (Dx, P, P^{n-1}) and CPML (psi_E, psi_H) state live in registers for the whole
+//   launch.  Per-cell coefficients (CPML profiles b, c_e, c_m; masked update coefficients of mixed
+//   warps) live in shared memory in [array][j][thread] order, so each thread only ever touches its
+//   own slots (no barrier needed, lane-consecutive 8-byte words are bank-conflict free).  Warps are
+//   specialised by cell class (vacuum | slab | CPML | slab+CPML | mixed).  The only inter-thread traffic is
 //   one Hy value to the right neighbour before the E half-step and one Ex value to the left
 //   neighbour before the H half-step, through a 2*NT-double shared edge buffer: two
 //   __syncthreads per time step.
@@ -33,9 +34,21 @@
 
 namespace pf {
 
-constexpr int TILE_CELLS = 2048;
-constexpr int TILE_KMAX = 256;   // halo <= TILE_KMAX per side
-constexpr int TILE_KDEF = 64;    // default steps per launch
+#ifndef PF_TILE_CELLS
+#define PF_TILE_CELLS 2048
+#endif
+#ifndef PF_TILE_C
+#define PF_TILE_C 8
+#endif
+#ifndef PF_TILE_MINBLOCKS
+#define PF_TILE_MINBLOCKS 1
+#endif
+#ifndef PF_TILE_KDEF
+#define PF_TILE_KDEF 64
+#endif
+constexpr int TILE_CELLS = PF_TILE_CELLS;   // cells per tile (interior + 2 halos)
+constexpr int TILE_KMAX = TILE_CELLS / 8;   // halo <= TILE_KMAX per side
+constexpr int TILE_KDEF = PF_TILE_KDEF;     // default steps per launch
 
 struct TileGrid {
     GridDev d;
@@ -50,39 +63,322 @@ struct TileDesc {
     int base;  // local index of the tile's first cell (interior starts at base + halo)
 };
 
-// shared memory carve-up (doubles)
+// shared memory carve-up (doubles): 7 per-cell coefficient arrays + edge exchange + source tables
 template <int MODE, int C>
 struct TileSmem {
     static constexpr int NT = TILE_CELLS / C;
-    static constexpr int N_ARR = (MODE == PF_LORENTZ) ? 8 : (MODE == PF_NL ? 6 : 5);
-    // order: psiE, psiH, be, ce, cm, [Dx, [P, Pp]]
+    static constexpr int N_ARR = 7;
     static constexpr size_t bytes = sizeof(double) * ((size_t)N_ARR * TILE_CELLS + 2 * NT + 2 * TILE_KMAX);
 };
 
+struct TileShared {
+    // per-cell coefficient slots, [j][thread] order (each thread touches only its own slots)
+    double *be, *ce, *cm;      // CPML recursive-convolution profiles (0 outside the CPML)
+    double *cEu, *cHu;         // update coefficient of the cell, 0 where the field is never updated
+    double *cb, *c2u;          // CPML field-correction coefficients, 0 outside / at the quirk cell
+    double *edgeH, *edgeE, *srcE, *srcH;
+};
+
+// CTA-wide barrier usable from warp-uniform divergent code: every warp executes exactly two of
+// these per time step (plus one before the loop), whichever body it runs.
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// per-thread description of its C cells
+struct CellMasks {
+    unsigned valid, updE, updH, pmlE, pmlH, slab, store, quirk;
+    int jsrc, jtfsf, pj0, pj1;
+    size_t po0, po1;
+};
+
+// -------------------------------------------------------------------------------------------------
+// One body for every warp class.  All field / material / CPML state of the thread's C cells lives in
+// registers for the whole launch.
+//   GEN = false : every cell of every thread of the warp is a plain interior cell of one class
+//                 (SLAB? x PML?) -> straight-line code, no masks, scalar coefficients.
+//   GEN = true  : mixed warp (region boundary, grid end, CPML quirk cell).  Same arithmetic with
+//                 every term switched on, per-cell coefficients from shared memory: a coefficient of
+//                 exactly 0 turns its term into an exact no-op (x + y*0 == x), so no per-cell branch
+//                 is needed; only the material law is selected per cell.
+// -------------------------------------------------------------------------------------------------
+// Everything a time step needs besides the per-cell register arrays.
+struct StepConsts {
+    double cEs, cHs, c2s, dtdz, eps0, inv_eps0, pA, pB, pC, den0, den1;
+    int jsrc, jtfsf;
+    bool wSrc;
+    unsigned mSlab;
+};
+
+// One full time step (E half-step, barrier, H half-step) on the thread's C cells.
+//   pc = P^n (current polarisation), pq = P^{n-1}: the new P^{n+1} is written over pq, so the
+//   caller alternates (pc,pq) <-> (pq,pc) instead of shifting the history (no register moves).
+template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML>
+__device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts &K, const CubicConsts &kc, int tid, int s,
+                                          double (&ex)[C], double (&hy)[C], double (&dx)[C], double (&pc)[C],
+                                          double (&pq)[C], double (&pe)[C], double (&ph)[C], double (&acub)[C],
+                                          double (&rbe)[C], double (&rce)[C], double (&rcm)[C])
+{
+    constexpr int NT = TILE_CELLS / C;
+    constexpr bool HAS_MAT = (GEN || SLAB) && MODE != PF_FREE;
+    constexpr bool ALL_MAT = !GEN && SLAB && MODE != PF_FREE;
+    constexpr bool HAS_PML = GEN || PML;
+    // ===== E half-step: history shift + polarisation, ADE_ExUpdate, CPML_Psi_e, source,
+    //                    ADE_DxUpdate, ADE_ExCreate | AcubicFinder + NonLinExUpdate =====
+    double hl = (tid > 0) ? S.edgeH[tid - 1] : 0.0;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const double dH = A::sub(hy[j], hl);
+        hl = hy[j];
+        double e = ex[j];
+        double pnow = 0.0;
+        if (MODE == PF_LORENTZ && HAS_MAT) {
+            if (POL) {
+                pq[j] = A::add(A::add(A::mul(K.pA, pc[j]), A::mul(K.pB, pq[j])), A::mul(K.pC, e));
+                pnow = pq[j];
+            } else {
+                pnow = pc[j];
+            }
+        }
+        if (!ALL_MAT) e = A::add(e, A::mul(dH, GEN ? S.cEu[j * NT + tid] : K.cEs));
+        if (HAS_PML) {
+            const double b = GEN ? S.be[j * NT + tid] : rbe[j];
+            const double c = GEN ? S.ce[j * NT + tid] : rce[j];
+            const double psi = A::add(A::mul(b, pe[j]), A::mul(c, dH));
+            pe[j] = psi;
+            if (!ALL_MAT) e = A::sub(e, A::mul(GEN ? S.cb[j * NT + tid] : K.cEs, psi));
+        }
+        if (!ALL_MAT && K.wSrc && j == K.jsrc) e = A::add(e, S.srcE[s]);
+        if (HAS_MAT) {
+            if (MODE == PF_LORENTZ) {
+                dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));
+                const double em = div_const(A::sub(dx[j], pnow), K.eps0, K.inv_eps0);
+                e = (!GEN || ((K.mSlab >> j) & 1)) ? em : e;
+            } else if (!GEN || ((K.mSlab >> j) & 1)) {
+                dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));
+                const double a = acubic_cell(kc, dx[j], K.eps0, K.inv_eps0);
+                acub[j] = a;
+                e = __ddiv_rn(dx[j], A::add(K.den0, A::mul(K.den1, a)));
+            }
+        }
+        ex[j] = e;
+    }
+    S.edgeE[tid] = ex[0];
+    cta_sync();
+
+    // ===== H half-step: TF/SF correction, ADE_HyUpdate, CPML_Psi_m =====
+    double er = (tid < NT - 1) ? S.edgeE[tid + 1] : 0.0;
+#pragma unroll
+    for (int j = C - 1; j >= 0; --j) {
+        double h = hy[j];
+        if (K.wSrc && j == K.jtfsf) h = A::sub(h, S.srcH[s]);
+        const double dE = A::sub(er, ex[j]);
+        er = ex[j];
+        h = A::add(h, A::mul(dE, GEN ? S.cHu[j * NT + tid] : K.cHs));
+        if (HAS_PML) {
+            const double b = GEN ? S.be[j * NT + tid] : rbe[j];
+            const double c = GEN ? S.cm[j * NT + tid] : rcm[j];
+            const double psi = A::add(A::mul(b, ph[j]), A::mul(c, dE));
+            ph[j] = psi;
+            h = A::add(h, A::mul(GEN ? S.c2u[j * NT + tid] : K.c2s, psi));
+        }
+        hy[j] = h;
+    }
+    S.edgeH[tid] = hy[C - 1];
+}
+
+// -------------------------------------------------------------------------------------------------
+// One body for every warp class.  All field / material / CPML state of the thread's C cells lives in
+// registers for the whole launch.
+//   GEN = false : every cell of every thread of the warp is a plain interior cell of one class
+//                 (SLAB? x PML?) -> straight-line code, no masks, scalar coefficients, CPML
+//                 profiles in registers.
+//   GEN = true  : mixed warp (region boundary, grid end, CPML quirk cell).  Same arithmetic with
+//                 every term switched on, per-cell coefficients from shared memory: a coefficient of
+//                 exactly 0 turns its term into an exact no-op (x + y*0 == x), so no per-cell branch
+//                 is needed; only the material law is selected per cell.
+// -------------------------------------------------------------------------------------------------
+template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML>
+__device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &S, const CellMasks &M,
+                                          int tid, int lz0, int ks, int src, int nabs0)
+{
+    constexpr int NT = TILE_CELLS / C;
+    constexpr bool HAS_MAT = (GEN || SLAB) && MODE != PF_FREE;   // material arrays present
+    constexpr bool HAS_PML = GEN || PML;
+    const PfGrid &g = TG.d.g;
+    const unsigned mSlab = M.slab;
+    double ex[C], hy[C], dx[C], pa[C], pb[C], pe[C], ph[C], acub[C], rbe[C], rce[C], rcm[C];
+
+    // ---- load ---------------------------------------------------------------------------------
+    {
+        const double *__restrict__ inEx = TG.buf[src][S_EX];
+        const double *__restrict__ inHy = TG.buf[src][S_HY];
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            bool v = !GEN || ((M.valid >> j) & 1);
+            ex[j] = v ? inEx[lz0 + j] : 0.0;
+            hy[j] = v ? inHy[lz0 + j] : 0.0;
+        }
+        if (HAS_PML) {
+            const double *__restrict__ inPe = TG.buf[src][S_PSIE];
+            const double *__restrict__ inPh = TG.buf[src][S_PSIH];
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                bool e_ = !GEN || ((M.pmlE >> j) & 1), h_ = !GEN || ((M.pmlH >> j) & 1);
+                int lz = lz0 + j;
+                pe[j] = e_ ? inPe[lz] : 0.0;
+                ph[j] = h_ ? inPh[lz] : 0.0;
+                const double b = (e_ || h_) ? g.beX[lz] : 0.0, c1 = e_ ? g.ceX[lz] : 0.0, c2 = h_ ? g.cmY[lz] : 0.0;
+                if (GEN) {
+                    S.be[j * NT + tid] = b;
+                    S.ce[j * NT + tid] = c1;
+                    S.cm[j * NT + tid] = c2;
+                } else {
+                    rbe[j] = b; rce[j] = c1; rcm[j] = c2;
+                }
+            }
+        }
+        if (HAS_MAT) {
+            const double *__restrict__ inDx = TG.buf[src][S_DX];
+#pragma unroll
+            for (int j = 0; j < C; ++j) dx[j] = (!GEN || ((mSlab >> j) & 1)) ? inDx[lz0 + j] : 0.0;
+            if (MODE == PF_LORENTZ) {
+                const double *__restrict__ inP = TG.buf[src][S_P];
+                const double *__restrict__ inPp = TG.buf[src][S_PP];
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    bool sl = !GEN || ((mSlab >> j) & 1);
+                    pa[j] = sl ? inP[lz0 + j] : 0.0;
+                    pb[j] = sl ? inPp[lz0 + j] : 0.0;
+                }
+            }
+        }
+        if (GEN) {
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const bool sl = (mSlab >> j) & 1, q = (M.quirk >> j) & 1;
+                const double cE = sl ? g.cE1 : g.cE0, cH = sl ? g.cH1 : g.cH0;
+                S.cEu[j * NT + tid] = ((M.updE >> j) & 1) ? cE : 0.0;
+                S.cHu[j * NT + tid] = ((M.updH >> j) & 1) ? cH : 0.0;
+                S.cb[j * NT + tid] = (((M.pmlE >> j) & 1) && !q) ? cE : 0.0;
+                S.c2u[j * NT + tid] = (((M.pmlH >> j) & 1) && !q) ? g.c2_pml : 0.0;
+            }
+        }
+        if (MODE == PF_NL) {
+#pragma unroll
+            for (int j = 0; j < C; ++j) acub[j] = 0.0;
+        }
+    }
+    StepConsts K;
+    K.cEs = SLAB ? g.cE1 : g.cE0; K.cHs = SLAB ? g.cH1 : g.cH0; K.c2s = g.c2_pml;
+    K.dtdz = g.dt_over_dz; K.eps0 = g.eps0; K.inv_eps0 = TG.d.inv_eps0;
+    K.pA = g.polA; K.pB = g.polB; K.pC = g.polC; K.den0 = g.nl_den0; K.den1 = g.nl_den1;
+    K.jsrc = M.jsrc; K.jtfsf = M.jtfsf; K.mSlab = mSlab;
+    K.wSrc = __any_sync(0xffffffffu, M.jsrc >= 0 || M.jtfsf >= 0);
+    CubicConsts kc;
+    if (MODE == PF_NL && HAS_MAT) kc = TG.d.k;
+    const int pj0 = M.pj0, pj1 = M.pj1;
+    const bool wProbe = __any_sync(0xffffffffu, pj0 >= 0);
+
+    auto probes = [&](int s) {   // Solver_Engine.probeSim: Ex after the step
+        if (wProbe && pj0 >= 0) {
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < C; ++j) v = (j == pj0) ? ex[j] : v;
+            g.probe_out[M.po0 + nabs0 + s] = v;
+            if (pj1 >= 0) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) v = (j == pj1) ? ex[j] : v;
+                g.probe_out[M.po1 + nabs0 + s] = v;
+            }
+        }
+    };
+
+    S.edgeH[tid] = hy[C - 1];
+    cta_sync();
+    constexpr bool SWAP = MODE == PF_LORENTZ && HAS_MAT && POL;   // P history alternates between pa and pb
+    int s = 0;
+    for (; s + 1 < ks; s += 2) {
+        tile_step<MODE, POL, C, A, GEN, SLAB, PML>(S, K, kc, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+        probes(s);
+        cta_sync();
+        if (SWAP) tile_step<MODE, POL, C, A, GEN, SLAB, PML>(S, K, kc, tid, s + 1, ex, hy, dx, pb, pa, pe, ph, acub, rbe, rce, rcm);
+        else tile_step<MODE, POL, C, A, GEN, SLAB, PML>(S, K, kc, tid, s + 1, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+        probes(s + 1);
+        cta_sync();
+    }
+    bool swapped = false;   // true: current P is in pb, previous in pa
+    if (s < ks) {
+        tile_step<MODE, POL, C, A, GEN, SLAB, PML>(S, K, kc, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+        probes(s);
+        cta_sync();
+        swapped = SWAP;
+    }
+
+    // ---- store interior ---------------------------------------------------------------------------
+    const int dst = src ^ 1;
+    const unsigned st = M.store;
+    double *__restrict__ outEx = TG.buf[dst][S_EX];
+    double *__restrict__ outHy = TG.buf[dst][S_HY];
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+        if ((st >> j) & 1) { outEx[lz0 + j] = ex[j]; outHy[lz0 + j] = hy[j]; }
+    if (HAS_PML) {
+        double *__restrict__ outPe = TG.buf[dst][S_PSIE];
+        double *__restrict__ outPh = TG.buf[dst][S_PSIH];
+        const unsigned se = GEN ? (st & M.pmlE) : st, sh = GEN ? (st & M.pmlH) : st;
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            if ((se >> j) & 1) outPe[lz0 + j] = pe[j];
+            if ((sh >> j) & 1) outPh[lz0 + j] = ph[j];
+        }
+    }
+    if (HAS_MAT) {
+        const unsigned sm = GEN ? (st & mSlab) : st;
+        double *__restrict__ outDx = TG.buf[dst][S_DX];
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+            if ((sm >> j) & 1) outDx[lz0 + j] = dx[j];
+        if (MODE == PF_LORENTZ) {
+            double *__restrict__ outP = TG.buf[dst][S_P];
+            double *__restrict__ outPp = TG.buf[dst][S_PP];
+#pragma unroll
+            for (int j = 0; j < C; ++j)
+                if ((sm >> j) & 1) {
+                    outP[lz0 + j] = swapped ? pb[j] : pa[j];
+                    outPp[lz0 + j] = swapped ? pa[j] : pb[j];
+                }
+        }
+        if (MODE == PF_NL && g.Acubic) {
+#pragma unroll
+            for (int j = 0; j < C; ++j)
+                if ((sm >> j) & 1) g.Acubic[lz0 + j] = acub[j];
+        }
+    }
+}
+
 template <int MODE, bool POL, int C, class A>
-__global__ void __launch_bounds__(TILE_CELLS / C, 1)
+__global__ void __launch_bounds__(TILE_CELLS / C, PF_TILE_MINBLOCKS)
 k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, int src, int n_done,
        int n0, int ksteps, int halo)
 {
     constexpr int NT = TILE_CELLS / C;
+    constexpr unsigned ALL = (1u << C) - 1u;
     extern __shared__ double smem[];
-    double *sPsiE = smem;
-    double *sPsiH = sPsiE + TILE_CELLS;
-    double *sBe = sPsiH + TILE_CELLS;
-    double *sCe = sBe + TILE_CELLS;
-    double *sCm = sCe + TILE_CELLS;
-    double *sDx = sCm + TILE_CELLS;          // MODE != FREE
-    double *sP = sDx + TILE_CELLS;           // MODE == LORENTZ
-    double *sPp = sP + TILE_CELLS;
-    double *sEdgeH = smem + (size_t)TileSmem<MODE, C>::N_ARR * TILE_CELLS;
-    double *sEdgeE = sEdgeH + NT;
-    double *sSrcE = sEdgeE + NT;
-    double *sSrcH = sSrcE + TILE_KMAX;
+    TileShared S;
+    S.be = smem;
+    S.ce = S.be + TILE_CELLS;
+    S.cm = S.ce + TILE_CELLS;
+    S.cEu = S.cm + TILE_CELLS;
+    S.cHu = S.cEu + TILE_CELLS;
+    S.cb = S.cHu + TILE_CELLS;
+    S.c2u = S.cb + TILE_CELLS;
+    S.edgeH = S.c2u + TILE_CELLS;
+    S.edgeE = S.edgeH + NT;
+    S.srcE = S.edgeE + NT;
+    S.srcH = S.srcE + TILE_KMAX;
 
     const TileDesc td = tiles[blockIdx.x];
     const TileGrid &TG = grids[td.grid];
-    const int remaining = TG.nsteps - n_done;
-    const int ks = min(ksteps, remaining);
+    const int ks = min(ksteps, TG.nsteps - n_done);
     if (ks <= 0) return;
 
     const PfGrid &g = TG.d.g;
@@ -93,12 +389,11 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     const int flags = g.flags;
     const int lz0 = td.base + tid * C;
 
-    const double *__restrict__ inEx = TG.buf[src][S_EX];
-    const double *__restrict__ inHy = TG.buf[src][S_HY];
-
     // ---- per-cell masks (bit j <-> cell lz0+j) -------------------------------------------
-    unsigned mValid = 0, mUpdE = 0, mUpdH = 0, mPmlE = 0, mPmlH = 0, mSlab = 0, mStore = 0, mQuirk = 0;
-    int jsrc = -1, jtfsf = -1;
+    CellMasks M;
+    M.valid = M.updE = M.updH = M.pmlE = M.pmlH = M.slab = M.store = M.quirk = 0;
+    M.jsrc = M.jtfsf = M.pj0 = M.pj1 = -1;
+    M.po0 = M.po1 = 0;
     const bool cpml_m = flags & PF_F_CPML_M, cpml_p = flags & PF_F_CPML_P;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
@@ -109,219 +404,49 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
         bool inL = cpml_m && gz < pw, inR = cpml_p && gz >= Lg - pw;
         bool slab = valid && lz >= 1 && gz >= mf && gz < mr;
         bool interior = (lz - td.base) >= halo && (lz - td.base) < TILE_CELLS - halo;
-        mValid |= (unsigned)valid << j;
-        mUpdE |= (unsigned)updE << j;
-        mUpdH |= (unsigned)updH << j;
-        mPmlE |= (unsigned)(updE && (inL || inR)) << j;
-        mPmlH |= (unsigned)(updH && (inL || inR)) << j;
-        mSlab |= (unsigned)slab << j;
-        mStore |= (unsigned)(valid && interior) << j;
-        mQuirk |= (unsigned)(gz == Lg - pw) << j;
-        if (valid && gz == g.nzsrc) jsrc = j;
-        if (valid && gz == g.nzsrc - 1 && (flags & PF_F_TFSF)) jtfsf = j;
+        M.valid |= (unsigned)valid << j;
+        M.updE |= (unsigned)updE << j;
+        M.updH |= (unsigned)updH << j;
+        M.pmlE |= (unsigned)(updE && (inL || inR)) << j;
+        M.pmlH |= (unsigned)(updH && (inL || inR)) << j;
+        M.slab |= (unsigned)slab << j;
+        M.store |= (unsigned)(valid && interior) << j;
+        M.quirk |= (unsigned)(gz == Lg - pw) << j;
+        if (valid && gz == g.nzsrc) M.jsrc = j;
+        if (valid && gz == g.nzsrc - 1 && (flags & PF_F_TFSF)) M.jtfsf = j;
     }
-    const bool anyPml = (mPmlE | mPmlH) != 0;
-    const bool anySlab = mSlab != 0;
-
-    // probes owned by this thread (at most 2; the host guarantees that, see tile_supported())
-    int pj0 = -1, pj1 = -1;
-    size_t po0 = 0, po1 = 0;
+    // probes owned by this thread (at most 2; guaranteed by the host layer)
     for (int p = 0; p < g.n_probes; ++p) {
-        int lp = g.probe_idx[p] - z0;
-        int j = lp - lz0;
-        if (j >= 0 && j < C && ((mStore >> j) & 1)) {
-            if (pj0 < 0) { pj0 = j; po0 = (size_t)p * g.probe_stride; }
-            else { pj1 = j; po1 = (size_t)p * g.probe_stride; }
+        int j = g.probe_idx[p] - z0 - lz0;
+        if (j >= 0 && j < C && ((M.store >> j) & 1)) {
+            if (M.pj0 < 0) { M.pj0 = j; M.po0 = (size_t)p * g.probe_stride; }
+            else { M.pj1 = j; M.po1 = (size_t)p * g.probe_stride; }
         }
     }
-
-    // ---- load state ------------------------------------------------------------------------
-    double ex[C], hy[C];
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-        bool v = (mValid >> j) & 1;
-        ex[j] = v ? inEx[lz0 + j] : 0.0;
-        hy[j] = v ? inHy[lz0 + j] : 0.0;
-    }
-    if (anyPml) {
-        const double *__restrict__ inPe = TG.buf[src][S_PSIE];
-        const double *__restrict__ inPh = TG.buf[src][S_PSIH];
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            bool pe = (mPmlE >> j) & 1, ph = (mPmlH >> j) & 1;
-            int lz = lz0 + j;
-            sPsiE[j * NT + tid] = pe ? inPe[lz] : 0.0;
-            sPsiH[j * NT + tid] = ph ? inPh[lz] : 0.0;
-            sBe[j * NT + tid] = (pe || ph) ? g.beX[lz] : 0.0;
-            sCe[j * NT + tid] = pe ? g.ceX[lz] : 0.0;
-            sCm[j * NT + tid] = ph ? g.cmY[lz] : 0.0;
-        }
-    }
-    if (MODE != PF_FREE && anySlab) {
-        const double *__restrict__ inDx = TG.buf[src][S_DX];
-#pragma unroll
-        for (int j = 0; j < C; ++j) sDx[j * NT + tid] = ((mSlab >> j) & 1) ? inDx[lz0 + j] : 0.0;
-        if (MODE == PF_LORENTZ) {
-            const double *__restrict__ inP = TG.buf[src][S_P];
-            const double *__restrict__ inPp = TG.buf[src][S_PP];
-#pragma unroll
-            for (int j = 0; j < C; ++j) {
-                bool s = (mSlab >> j) & 1;
-                sP[j * NT + tid] = s ? inP[lz0 + j] : 0.0;
-                sPp[j * NT + tid] = s ? inPp[lz0 + j] : 0.0;
-            }
-        }
-    }
-    // source tables for the steps of this launch (only the CTA that holds the source cell reads them,
-    // but the load is CTA-uniform so everybody helps)
+    // source tables of this launch's steps (CTA-uniform load)
     const int nabs0 = n0 + n_done;
     for (int s = tid; s < ks; s += NT) {
-        sSrcE[s] = g.srcE[nabs0 + s];
-        sSrcH[s] = (flags & PF_F_TFSF) ? g.srcH[nabs0 + s] : 0.0;
+        S.srcE[s] = g.srcE[nabs0 + s];
+        S.srcH[s] = (flags & PF_F_TFSF) ? g.srcH[nabs0 + s] : 0.0;
     }
 
-    // ---- constants ---------------------------------------------------------------------------
-    const double cE0 = g.cE0, cE1 = g.cE1, cH0 = g.cH0, cH1 = g.cH1, c2 = g.c2_pml;
-    const double dtdz = g.dt_over_dz, eps0 = g.eps0, inv_eps0 = TG.d.inv_eps0;
-    const double pA = g.polA, pB = g.polB, pC = g.polC;
-    const double den0 = g.nl_den0, den1 = g.nl_den1;
-    CubicConsts kc;
-    if (MODE == PF_NL) kc = TG.d.k;
-    double acub[C];
-    if (MODE == PF_NL) {
-#pragma unroll
-        for (int j = 0; j < C; ++j) acub[j] = 0.0;
-    }
+    // ---- warp class: 0 vacuum, 1 slab, 2 CPML, 3 slab+CPML, 4 mixed ------------------------
+    // (a source cell inside a material-law cell would be overwritten anyway; it is sent to the
+    //  mixed body only to keep the fast slab body free of the test)
+    int cls = 4;
+    const bool plain = M.valid == ALL && M.updE == ALL && M.updH == ALL && M.quirk == 0;
+    const bool pmlAll = M.pmlE == ALL && M.pmlH == ALL, pmlNone = (M.pmlE | M.pmlH) == 0;
+    const bool slabAll = M.slab == ALL, slabNone = M.slab == 0;
+    if (plain && (pmlAll || pmlNone) && (slabAll || slabNone)) cls = (slabAll ? 1 : 0) + (pmlAll ? 2 : 0);
+    const int cls0 = __shfl_sync(0xffffffffu, cls, 0);
+    cls = __all_sync(0xffffffffu, cls == cls0) ? cls0 : 4;
 
-    sEdgeH[tid] = hy[C - 1];
-    __syncthreads();
-
-    // ---- k time steps on chip -----------------------------------------------------------------
-    for (int s = 0; s < ks; ++s) {
-        // ===== E half-step (ADE_TempPolCurr+PolarisationCurrent, ADE_ExUpdate, CPML_Psi_e, source,
-        //                    ADE_DxUpdate, ADE_ExCreate | AcubicFinder+NonLinExUpdate) =====
-        double hl = (tid > 0) ? sEdgeH[tid - 1] : 0.0;
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            const bool slab = (mSlab >> j) & 1;
-            double e = ex[j];
-            double dH = A::sub(hy[j], hl);
-            hl = hy[j];
-            double pnew = 0.0;
-            if (MODE == PF_LORENTZ) {
-                if (slab) {
-                    pnew = sP[j * NT + tid];
-                    if (POL) {
-                        double pn = pnew;
-                        pnew = A::add(A::add(A::mul(pA, pn), A::mul(pB, sPp[j * NT + tid])), A::mul(pC, e));
-                        sP[j * NT + tid] = pnew;
-                        sPp[j * NT + tid] = pn;
-                    }
-                }
-            }
-            const double cE = slab ? cE1 : cE0;
-            if ((mUpdE >> j) & 1) e = A::add(e, A::mul(dH, cE));
-            if ((mPmlE >> j) & 1) {
-                double psi = A::add(A::mul(sBe[j * NT + tid], sPsiE[j * NT + tid]), A::mul(sCe[j * NT + tid], dH));
-                sPsiE[j * NT + tid] = psi;
-                double cb = ((mQuirk >> j) & 1) ? 0.0 : cE;
-                e = A::sub(e, A::mul(cb, psi));
-            }
-            if (j == jsrc) e = A::add(e, sSrcE[s]);
-            if (MODE != PF_FREE) {
-                if (slab) {
-                    double dx = A::add(sDx[j * NT + tid], A::mul(dH, dtdz));
-                    sDx[j * NT + tid] = dx;
-                    if (MODE == PF_LORENTZ) {
-                        e = div_const(A::sub(dx, pnew), eps0, inv_eps0);
-                    } else {
-                        double a = acubic_cell(kc, dx, eps0, inv_eps0);
-                        acub[j] = a;
-                        e = __ddiv_rn(dx, A::add(den0, A::mul(den1, a)));
-                    }
-                }
-            }
-            ex[j] = e;
-        }
-        sEdgeE[tid] = ex[0];
-        __syncthreads();
-
-        // ===== H half-step (TF/SF correction, ADE_HyUpdate, CPML_Psi_m) =====
-        double er = (tid < NT - 1) ? sEdgeE[tid + 1] : 0.0;
-#pragma unroll
-        for (int j = C - 1; j >= 0; --j) {
-            double h = hy[j];
-            if (j == jtfsf) h = A::sub(h, sSrcH[s]);
-            double dE = A::sub(er, ex[j]);
-            er = ex[j];
-            const bool slabH = ((mSlab >> j) & 1);
-            const double cH = slabH ? cH1 : cH0;
-            if ((mUpdH >> j) & 1) h = A::add(h, A::mul(dE, cH));
-            if ((mPmlH >> j) & 1) {
-                double psi = A::add(A::mul(sBe[j * NT + tid], sPsiH[j * NT + tid]), A::mul(sCm[j * NT + tid], dE));
-                sPsiH[j * NT + tid] = psi;
-                double c2j = ((mQuirk >> j) & 1) ? 0.0 : c2;
-                h = A::add(h, A::mul(c2j, psi));
-            }
-            hy[j] = h;
-        }
-        sEdgeH[tid] = hy[C - 1];
-
-        // ===== probes (Solver_Engine.probeSim): Ex after the step =====
-        if (pj0 >= 0) {
-            double v = 0.0;
-#pragma unroll
-            for (int j = 0; j < C; ++j) v = (j == pj0) ? ex[j] : v;
-            g.probe_out[po0 + nabs0 + s] = v;
-            if (pj1 >= 0) {
-#pragma unroll
-                for (int j = 0; j < C; ++j) v = (j == pj1) ? ex[j] : v;
-                g.probe_out[po1 + nabs0 + s] = v;
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- store interior -------------------------------------------------------------------------
-    const int dst = src ^ 1;
-    double *__restrict__ outEx = TG.buf[dst][S_EX];
-    double *__restrict__ outHy = TG.buf[dst][S_HY];
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-        if ((mStore >> j) & 1) {
-            outEx[lz0 + j] = ex[j];
-            outHy[lz0 + j] = hy[j];
-        }
-    }
-    if (anyPml) {
-        double *__restrict__ outPe = TG.buf[dst][S_PSIE];
-        double *__restrict__ outPh = TG.buf[dst][S_PSIH];
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            if ((mStore >> j) & (mPmlE >> j) & 1) outPe[lz0 + j] = sPsiE[j * NT + tid];
-            if ((mStore >> j) & (mPmlH >> j) & 1) outPh[lz0 + j] = sPsiH[j * NT + tid];
-        }
-    }
-    if (MODE != PF_FREE && anySlab) {
-        double *__restrict__ outDx = TG.buf[dst][S_DX];
-#pragma unroll
-        for (int j = 0; j < C; ++j)
-            if ((mStore >> j) & (mSlab >> j) & 1) outDx[lz0 + j] = sDx[j * NT + tid];
-        if (MODE == PF_LORENTZ) {
-            double *__restrict__ outP = TG.buf[dst][S_P];
-            double *__restrict__ outPp = TG.buf[dst][S_PP];
-#pragma unroll
-            for (int j = 0; j < C; ++j)
-                if ((mStore >> j) & (mSlab >> j) & 1) {
-                    outP[lz0 + j] = sP[j * NT + tid];
-                    outPp[lz0 + j] = sPp[j * NT + tid];
-                }
-        }
-        if (MODE == PF_NL && g.Acubic) {
-#pragma unroll
-            for (int j = 0; j < C; ++j)
-                if ((mStore >> j) & (mSlab >> j) & 1) g.Acubic[lz0 + j] = acub[j];
-        }
+    switch (cls) {
+    case 0: tile_body<MODE, POL, C, A, false, false, false>(TG, S, M, tid, lz0, ks, src, nabs0); break;
+    case 1: tile_body<MODE, POL, C, A, false, true, false>(TG, S, M, tid, lz0, ks, src, nabs0); break;
+    case 2: tile_body<MODE, POL, C, A, false, false, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
+    case 3: tile_body<MODE, POL, C, A, false, true, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
+    default: tile_body<MODE, POL, C, A, true, true, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
     }
 }
 
@@ -430,7 +555,7 @@ static int launch_tile(bool fma, int n_tiles, const TileGrid *dg, const TileDesc
     return 0;
 }
 
-constexpr int TILE_C = 8;
+constexpr int TILE_C = PF_TILE_C;
 
 static int launch_tile_mode(int mode, int do_pol, bool fma, int n_tiles, const TileGrid *dg, const TileDesc *dt,
                             int src, int n_done, int n0, int ks, int halo, cudaStream_t st)

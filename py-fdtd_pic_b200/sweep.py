@@ -189,8 +189,11 @@ def new_member_objects(freq_in, domainSize, lowLimTim, highLimTim, prevV, prevP,
     """One iteration of the reference sweep's object construction (MasterController.py:545-551):
     the grid is sized from the PREVIOUS member's (dispersion-corrected) medium."""
     from . import MasterController as MC
-    prevP.freq_in = freq_in
-    tup = envDef.envSetup(freq_in, domainSize, lowLimTim, highLimTim, VExists=True, V=prevV, P=prevP)
+    import types
+    # the reference has already advanced prevP.freq_in by Interval when it sizes the next member
+    # (MasterController.py:559); the previous member's own P must not change before it has run
+    probe_P = types.SimpleNamespace(freq_in=freq_in, permit_0=prevP.permit_0)
+    tup = envDef.envSetup(freq_in, domainSize, lowLimTim, highLimTim, VExists=True, V=prevV, P=probe_P)
     P = MC.Params(*tup, template_P.MORmode, domainSize, freq_in, 20, LorentzMed=template_P.LorentzMed,
                   SineCont=template_P.SineCont, Gaussian=template_P.Gaussian, TFSF=template_P.TFSF)
     V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
@@ -269,5 +272,6 @@ def frequency_sweep(V, P, domainSize, lowLimTim, highLimTim, Low=3e9, Interval=1
         measured[i] = MC.results(Vi, Pi, CVi, CPi, t, RefCo=True)
         analytical[i] = MC.results(Vi, Pi, CVi, CPi, t, AnalRefCo=True)
     Vi, Pi, CVi, CPi = objs[-1]
+    Pi.freq_in = Pi.freq_in + Interval          # the reference leaves the last P advanced (:559)
     Exs, Hys = srcs.get(points - 1, (None, None))
     return freqs, measured, analytical, (Vi, Pi, CVi, CPi, Exs, Hys)
