@@ -78,6 +78,27 @@ __device__ __forceinline__ double div_const(double x, double d, double r)
     return q2;
 }
 
+// The same division split in two for loops over several cells: div_const_fast() is the unguarded
+// two-FMA path and folds the guard quantity into `key` (max over cells; integer pipe only);
+// div_const_in_range(key) tells whether every cell of the loop was inside the exact range, and
+// div_const_fix() redoes one cell exactly when it was not.
+constexpr unsigned DIVC_LO = 0x0c800000u, DIVC_RANGE = 0x67000000u;
+__device__ __forceinline__ double div_const_fast(double x, double d, double r, unsigned &key)
+{
+    const double q = __dmul_rn(x, r);
+    const double e = __fma_rn(-q, d, x);
+    key = max(key, ((unsigned)__double2hiint(x) & 0x7ff00000u) - DIVC_LO);
+    return __fma_rn(e, r, q);
+}
+__device__ __forceinline__ bool div_const_in_range(unsigned key) { return key < DIVC_RANGE; }
+__device__ __forceinline__ double div_const_fix(double x, double d, double r, double fast)
+{
+    const int hi = __double2hiint(x);
+    if ((((unsigned)hi & 0x7ff00000u) - DIVC_LO) < DIVC_RANGE) return fast;
+    if ((((unsigned)hi & 0x7fffffffu) | (unsigned)__double2loint(x)) == 0u) return __dmul_rn(x, r);   // +-0
+    return div_const_slow(x, d);
+}
+
 // ---------------------------------------------------------------------------------------------
 // First root of a x^3 + b x^2 + c x + d as the reference's solver returns it
 // (CubicEquationSolver.py:29-105; only root[0] is consumed, BaseFDTD11.py:838).

@@ -35,13 +35,13 @@
 namespace pf {
 
 #ifndef PF_TILE_CELLS
-#define PF_TILE_CELLS 2048
+#define PF_TILE_CELLS 1024
 #endif
 #ifndef PF_TILE_C
-#define PF_TILE_C 8
+#define PF_TILE_C 4
 #endif
 #ifndef PF_TILE_MINBLOCKS
-#define PF_TILE_MINBLOCKS 1
+#define PF_TILE_MINBLOCKS 2
 #endif
 #ifndef PF_TILE_KDEF
 #define PF_TILE_KDEF 64
@@ -124,6 +124,7 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
     // ===== E half-step: history shift + polarisation, ADE_ExUpdate, CPML_Psi_e, source,
     //                    ADE_DxUpdate, ADE_ExCreate | AcubicFinder + NonLinExUpdate =====
     double hl = (tid > 0) ? S.edgeH[tid - 1] : 0.0;
+    unsigned divkey = 0;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
         const double dH = A::sub(hy[j], hl);
@@ -146,11 +147,10 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
             pe[j] = psi;
             if (!ALL_MAT) e = A::sub(e, A::mul(GEN ? S.cb[j * NT + tid] : K.cEs, psi));
         }
-        if (!ALL_MAT && K.wSrc && j == K.jsrc) e = A::add(e, S.srcE[s]);
         if (HAS_MAT) {
             if (MODE == PF_LORENTZ) {
                 dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));
-                const double em = div_const(A::sub(dx[j], pnow), K.eps0, K.inv_eps0);
+                const double em = div_const_fast(A::sub(dx[j], pnow), K.eps0, K.inv_eps0, divkey);
                 e = (!GEN || ((K.mSlab >> j) & 1)) ? em : e;
             } else if (!GEN || ((K.mSlab >> j) & 1)) {
                 dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));
@@ -161,15 +161,37 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
         }
         ex[j] = e;
     }
+    if (MODE == PF_LORENTZ && HAS_MAT && !div_const_in_range(divkey)) {
+        // some cell's (Dx - P) was zero, in the denormal range or non-finite: redo those divisions
+        // exactly (rare once the wave has arrived; integer tests only for the zero case)
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            if (!GEN || ((K.mSlab >> j) & 1)) {
+                const double x = A::sub(dx[j], POL ? pq[j] : pc[j]);
+                ex[j] = div_const_fix(x, K.eps0, K.inv_eps0, ex[j]);
+            }
+        }
+    }
+    if (!ALL_MAT && K.wSrc) {
+        // soft source (Solver_Engine.py:307): the last E operation of a non-material cell; a source
+        // inside a material-law cell is overwritten by ADE_ExCreate in the reference too
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+            if (j == K.jsrc && !(HAS_MAT && ((K.mSlab >> j) & 1))) ex[j] = A::add(ex[j], S.srcE[s]);
+    }
     S.edgeE[tid] = ex[0];
     cta_sync();
+    if (K.wSrc) {   // one-point TF/SF correction (Solver_Engine.py:309-310), before ADE_HyUpdate
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+            if (j == K.jtfsf) hy[j] = A::sub(hy[j], S.srcH[s]);
+    }
 
     // ===== H half-step: TF/SF correction, ADE_HyUpdate, CPML_Psi_m =====
     double er = (tid < NT - 1) ? S.edgeE[tid + 1] : 0.0;
 #pragma unroll
     for (int j = C - 1; j >= 0; --j) {
         double h = hy[j];
-        if (K.wSrc && j == K.jtfsf) h = A::sub(h, S.srcH[s]);
         const double dE = A::sub(er, ex[j]);
         er = ex[j];
         h = A::add(h, A::mul(dE, GEN ? S.cHu[j * NT + tid] : K.cHs));
@@ -430,7 +452,7 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
         S.srcH[s] = (flags & PF_F_TFSF) ? g.srcH[nabs0 + s] : 0.0;
     }
 
-    // ---- warp class: 0 vacuum, 1 slab, 2 CPML, 3 slab+CPML, 4 mixed ------------------------
+    // ---- warp class: 0 vacuum, 1 slab, 2 CPML, 3 slab+CPML, 4 mixed, 5 dead ------------------
     // (a source cell inside a material-law cell would be overwritten anyway; it is sent to the
     //  mixed body only to keep the fast slab body free of the test)
     int cls = 4;
@@ -438,6 +460,7 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     const bool pmlAll = M.pmlE == ALL && M.pmlH == ALL, pmlNone = (M.pmlE | M.pmlH) == 0;
     const bool slabAll = M.slab == ALL, slabNone = M.slab == 0;
     if (plain && (pmlAll || pmlNone) && (slabAll || slabNone)) cls = (slabAll ? 1 : 0) + (pmlAll ? 2 : 0);
+    if (M.valid == 0) cls = 5;                    // cells beyond the end of the grid
     const int cls0 = __shfl_sync(0xffffffffu, cls, 0);
     cls = __all_sync(0xffffffffu, cls == cls0) ? cls0 : 4;
 
@@ -446,6 +469,13 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     case 1: tile_body<MODE, POL, C, A, false, true, false>(TG, S, M, tid, lz0, ks, src, nabs0); break;
     case 2: tile_body<MODE, POL, C, A, false, false, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
     case 3: tile_body<MODE, POL, C, A, false, true, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
+    case 5:
+        // nothing to compute: publish zero edges once, then only keep the CTA's barrier count
+        S.edgeH[tid] = 0.0;
+        S.edgeE[tid] = 0.0;
+        cta_sync();
+        for (int s = 0; s < ks; ++s) { cta_sync(); cta_sync(); }
+        break;
     default: tile_body<MODE, POL, C, A, true, true, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
     }
 }

@@ -152,10 +152,33 @@ class MemberBatch:
         self.pool[self.n_state:self.n_state + self.n_in].copy_(self.host_in, non_blocking=True)
         self.pidx.copy_(self.host_pidx, non_blocking=True)
 
-    def reset_state(self):
-        """FieldInit / CPML_FieldInit on the device: zero fields, polarisation, psi and probe traces."""
-        self.pool[: self.n_state].zero_()
+    def reset_state(self, template=False):
+        """FieldInit / CPML_FieldInit on the device: zero fields, polarisation, psi and probe traces.
+        template=True starts from the synthetic state made by randomize_state() instead of zeros."""
+        if template:
+            self.pool[: self.n_state].copy_(self.state_template)
+        else:
+            self.pool[: self.n_state].zero_()
         self.pool[self.n_state + self.n_in:].zero_()
+
+    # physically plausible magnitudes: E ~ 1 V/m, H ~ E/377, D and P ~ eps0*E, psi_E ~ 1e-7, psi_H ~ 1
+    STATE_SCALE = {"Ex": 1.0, "Hy": 1.0 / 376.73, "psiE": 1e-7, "psiH": 1.0, "Dx": 8.85e-12, "P": 8.85e-12,
+                   "Pprev": 8.85e-12, "Acubic": 0.0}
+
+    def randomize_state(self, seed=1234):
+        """Synthetic non-zero state for benchmarks: every cell of every state array gets a uniform
+        random value of the field's natural magnitude, so no kernel path is favoured by zeros."""
+        torch = self.torch
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(seed)
+        self.state_template = torch.empty(self.n_state, dtype=torch.float64, device=self.device)
+        for i, m in enumerate(self.members):
+            Lp = (m.L + 31) // 32 * 32
+            for a, name in enumerate(STATE_NAMES):
+                o = self.off_state[i] + a * Lp
+                r = torch.rand(Lp, dtype=torch.float64, device=self.device, generator=gen) * 2 - 1
+                self.state_template[o:o + Lp] = r * self.STATE_SCALE[name]
+        return self.state_template
 
     def run(self, do_pol, n0=0, k_block=0):
         nat.check(nat.lib().pf_run_batch(self.grids, len(self.members), self.mode_id, int(do_pol), int(n0),
