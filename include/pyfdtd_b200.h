@@ -145,6 +145,16 @@ int pf_run_batch(const PfGrid *grids, int n_grids, int mode, int do_pol, int n0,
                  int k_block, void *scratch, size_t scratch_bytes, void *stream);
 size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine);
 
+/* Caller-managed ping-pong variant for long / domain-decomposed grids: ONE launch advances every grid
+ * by `ksteps` steps (absolute steps n0 .. n0+ksteps-1), reading the arrays of src[m] and writing the
+ * arrays of dst[m]; the caller alternates the two buffer sets and exchanges ghost cells in between
+ * (pf_halo_pack / pf_halo_unpack).  `halo` (>= ksteps) is the overlap the tiles are cut with.  Arrays
+ * that exist only on CPML / slab cells may be NULL for a piece that holds no such cell.  Both buffer
+ * sets must start out identical.  scratch: pf_run_block_scratch_bytes() bytes (tile tables only).   */
+int pf_run_block(const PfGrid *src, const PfGrid *dst, int n_grids, int mode, int do_pol, int n0, int ksteps, int halo,
+                 void *scratch, size_t scratch_bytes, void *stream);
+size_t pf_run_block_scratch_bytes(const PfGrid *grids, int n_grids, int halo);
+
 /* Per-launch timing of the tile kernel (the dominant kernel): while enabled, every k_tile launch is
  * bracketed by CUDA events on its own stream; pf_profile_collect() waits for them, returns the summed
  * kernel time [ms] and the number of launches, and clears the list.                              */

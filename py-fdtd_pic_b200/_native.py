@@ -76,6 +76,8 @@ SYMBOLS = {
     "pf_run_pass": (c_int, [_G, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_batch": (c_int, [_G, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_scratch_bytes": (c_size_t, [_G, c_int, c_int]),
+    "pf_run_block": (c_int, [_G, _G, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pf_run_block_scratch_bytes": (c_size_t, [_G, c_int, c_int]),
     "pf_profile_enable": (c_int, [c_int]),
     "pf_profile_collect": (c_int, [POINTER(c_double), POINTER(c_int)]),
     "pf_tile_config": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(256) k_tile_copy(const TileGrid *__restrict__ 
     for (int a = 0; a < narr; ++a) {
         const double *__restrict__ s = TG.buf[from][a];
         double *__restrict__ d = TG.buf[to][a];
+        if (!s || !d) continue;
         for (int i = threadIdx.x; i < W; i += blockDim.x) {
             int lz = td.base + halo + i;
             if (lz >= 0 && lz < TG.d.g.L) d[lz] = s[lz];
@@ -510,6 +511,16 @@ __global__ void __launch_bounds__(256) k_tile_copy(const TileGrid *__restrict__ 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int n_state_arrays(int mode) { return mode == PF_LORENTZ ? 7 : (mode == PF_NL ? 5 : 4); }
 
+// does the piece [z0, z0+L) of the global grid contain CPML / slab cells?
+static inline bool piece_has_pml(const PfGrid &g)
+{
+    long long a = g.z0, b = g.z0 + g.L;   // [a, b)
+    bool left = (g.flags & PF_F_CPML_M) && a < g.pw;
+    bool right = (g.flags & PF_F_CPML_P) && b > g.Lg - g.pw;
+    return g.pw > 0 && (left || right);
+}
+static inline bool piece_has_slab(const PfGrid &g) { return g.z0 < g.mr && g.z0 + g.L > g.mf; }
+
 static int tile_supported(const PfGrid &g, int mode)
 {
     if (!(g.flags & PF_F_CANONICAL)) return set_err(PF_E_UNSUPPORTED, "tile engine needs PF_F_CANONICAL coefficients");
@@ -517,9 +528,14 @@ static int tile_supported(const PfGrid &g, int mode)
     if (mode != PF_FREE && (g.flags & PF_F_TFSF) && g.nzsrc - 1 >= g.mf - 1 && g.nzsrc - 1 < g.mr)
         return set_err(PF_E_UNSUPPORTED, "tile engine: TF/SF point inside the slab");
     if (g.n_probes > 64) return set_err(PF_E_UNSUPPORTED, "tile engine: more than 64 probes");
-    if (!g.psiE || !g.psiH || !g.beX || !g.ceX || !g.cmY) return set_err(PF_E_ARG, "CPML arrays missing");
-    if (mode != PF_FREE && !g.Dx) return set_err(PF_E_ARG, "Dx missing");
-    if (mode == PF_LORENTZ && (!g.P || !g.Pprev)) return set_err(PF_E_ARG, "P/Pprev missing");
+    if (!g.Ex || !g.Hy) return set_err(PF_E_ARG, "Ex/Hy missing");
+    // arrays that only exist on CPML / slab cells may be NULL for a piece of a decomposed grid that
+    // holds no such cell (the kernel never dereferences them there)
+    if (piece_has_pml(g) && (!g.psiE || !g.psiH || !g.beX || !g.ceX || !g.cmY)) return set_err(PF_E_ARG, "CPML arrays missing");
+    if (mode != PF_FREE && piece_has_slab(g)) {
+        if (!g.Dx) return set_err(PF_E_ARG, "Dx missing");
+        if (mode == PF_LORENTZ && (!g.P || !g.Pprev)) return set_err(PF_E_ARG, "P/Pprev missing");
+    }
     return 0;
 }
 
@@ -536,7 +552,10 @@ static TilePlan tile_plan(const PfGrid *grids, int n, int mode, int halo)
     size_t state = 0;
     for (int m = 0; m < n; ++m) {
         nt += (grids[m].L + W - 1) / W;
-        state += (size_t)n_state_arrays(mode) * align_up(sizeof(double) * grids[m].L, 256);
+        const PfGrid &g = grids[m];
+        const double *prim[7] = {g.Ex, g.Hy, g.psiE, g.psiH, g.Dx, g.P, g.Pprev};
+        for (int a = 0; a < n_state_arrays(mode); ++a)
+            if (prim[a]) state += align_up(sizeof(double) * g.L, 256);
     }
     p.n_tiles = (int)nt;
     p.off_grids = 0;
@@ -633,7 +652,7 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
         for (int a = 0; a < 7; ++a) {
             t.buf[0][a] = prim[a];
             t.buf[1][a] = nullptr;
-            if (a < na) {
+            if (a < na && prim[a]) {
                 t.buf[1][a] = (double *)(sbase + off);
                 off += align_up(sizeof(double) * g.L, 256);
             }
@@ -684,7 +703,7 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
         // variable-length launches: parity is not a function of nsteps/k_block; copy back explicitly
         if (src == 1)
             for (int a = 0; a < na; ++a)
-                PF_CUDA(cudaMemcpyAsync(hg[0].buf[0][a], hg[0].buf[1][a], sizeof(double) * grids[0].L,
+                if (hg[0].buf[1][a]) PF_CUDA(cudaMemcpyAsync(hg[0].buf[0][a], hg[0].buf[1][a], sizeof(double) * grids[0].L,
                                         cudaMemcpyDeviceToDevice, st));
     } else {
         k_tile_copy<<<(int)ht.size(), 256, 0, st>>>(dg, dt, halo, k_block, mode, 1, 0, 1);
@@ -693,6 +712,48 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
     // host vectors go out of scope: the async H2D copies above were issued from pageable memory,
     // which cudaMemcpyAsync stages before returning.
     return PF_OK;
+}
+
+// One launch: advance n grids by `ks` steps (absolute steps n0 .. n0+ks-1) reading the arrays of
+// src[m] and writing the arrays of dst[m] (the caller owns both buffers and alternates them).
+// halo >= ks is the overlap the tiles are cut with.  scratch holds only the tile tables.
+int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol, int n0, int ks, int halo,
+               void *scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    if (n <= 0 || ks <= 0) return PF_OK;
+    if (halo < ks) halo = ks;
+    if (halo > TILE_KMAX) return set_err(PF_E_ARG, "pf_run_block: ksteps/halo %d exceeds the tile engine limit %d", halo, TILE_KMAX);
+    const int W = TILE_CELLS - 2 * halo;
+    std::vector<TileGrid> hg(n);
+    std::vector<TileDesc> ht;
+    bool fma = false;
+    for (int m = 0; m < n; ++m) {
+        int rc = tile_supported(src[m], mode);
+        if (rc) return rc;
+        if (dst[m].L != src[m].L) return set_err(PF_E_ARG, "pf_run_block: src/dst length mismatch in grid %d", m);
+        TileGrid &t = hg[m];
+        t.d = make_grid_dev(src[m]);
+        double *a0[7] = {src[m].Ex, src[m].Hy, src[m].psiE, src[m].psiH, src[m].Dx, src[m].P, src[m].Pprev};
+        double *a1[7] = {dst[m].Ex, dst[m].Hy, dst[m].psiE, dst[m].psiH, dst[m].Dx, dst[m].P, dst[m].Pprev};
+        for (int a = 0; a < 7; ++a) {
+            if ((a0[a] == nullptr) != (a1[a] == nullptr)) return set_err(PF_E_ARG, "pf_run_block: array %d present in only one buffer", a);
+            t.buf[0][a] = a0[a];
+            t.buf[1][a] = a1[a];
+        }
+        t.nsteps = ks;
+        t.pad = 0;
+        fma = fma || (src[m].flags & PF_F_FMA);
+        int ntile = (src[m].L + W - 1) / W;
+        for (int i = 0; i < ntile; ++i) ht.push_back(TileDesc{m, i * W - halo});
+    }
+    size_t off_tiles = align_up(sizeof(TileGrid) * (size_t)n, 256);
+    size_t need = off_tiles + align_up(sizeof(TileDesc) * ht.size(), 256);
+    if (!scratch || scratch_bytes < need) return set_err(PF_E_SCRATCH, "pf_run_block needs %zu bytes of scratch, got %zu", need, scratch_bytes);
+    TileGrid *dg = (TileGrid *)scratch;
+    TileDesc *dt = (TileDesc *)((char *)scratch + off_tiles);
+    PF_CUDA(cudaMemcpyAsync(dg, hg.data(), sizeof(TileGrid) * n, cudaMemcpyHostToDevice, st));
+    PF_CUDA(cudaMemcpyAsync(dt, ht.data(), sizeof(TileDesc) * ht.size(), cudaMemcpyHostToDevice, st));
+    return launch_tile_mode(mode, do_pol, fma, (int)ht.size(), dg, dt, 0, 0, n0, ks, halo, st);
 }
 
 int ops_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, double *snap_out,
@@ -734,6 +795,24 @@ int pf_profile_collect(double *ms_total, int *n_launches)
     if (ms_total) *ms_total = tot;
     if (n_launches) *n_launches = n;
     return PF_OK;
+}
+
+int pf_run_block(const PfGrid *src, const PfGrid *dst, int n_grids, int mode, int do_pol, int n0, int ksteps, int halo,
+                 void *scratch, size_t scratch_bytes, void *stream)
+{
+    if (!src || !dst || n_grids < 0) return set_err(PF_E_ARG, "pf_run_block: bad arguments");
+    if (mode < PF_FREE || mode > PF_NL) return set_err(PF_E_ARG, "pf_run_block: bad mode %d", mode);
+    return tile_block(src, dst, n_grids, mode, do_pol, n0, ksteps, halo, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+size_t pf_run_block_scratch_bytes(const PfGrid *grids, int n_grids, int halo)
+{
+    if (!grids || n_grids <= 0) return 0;
+    if (halo <= 0 || halo > TILE_KMAX) halo = TILE_KMAX;
+    const int W = TILE_CELLS - 2 * halo;
+    size_t nt = 0;
+    for (int m = 0; m < n_grids; ++m) nt += (grids[m].L + W - 1) / W;
+    return align_up(sizeof(TileGrid) * (size_t)n_grids, 256) + align_up(sizeof(TileDesc) * nt, 256);
 }
 
 int pf_tile_config(int *tile_cells, int *k_max, int *threads)

@@ -1,0 +1,104 @@
+"""Electron-beam PIC coupled to the 1-D FDTD grid through the reference's Jx slot.
+
+The reference has no particle code (only the title and TODOs) but its E update already
+subtracts a current slot: ``Ex += (Hy[nz]-Hy[nz-1]-Jx[nz]) * UpExMat * den`` (BaseFDTD11.py:667) with
+``V.Jx`` identically zero.  This module supplies what fills that slot: a relativistic Boris push with
+linear gather, a stable sort by cell, and a deterministic cell-sorted CIC deposition (csrc/pf_pic.cu;
+model spec in DESIGN.md, CPU definition in oracle/pic_oracle.py).  Units: positions in metres,
+momenta u = gamma*v in m/s, weights = real particles per macro-particle per unit transverse area, so
+that with ``jx_scale = q`` the deposited array is J_phys*dz -- the unit the slot is subtracted in.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _native as nat
+
+ELECTRON_Q = -1.602176634e-19
+ELECTRON_Q_OVER_M = -1.75882001076e11
+C0 = 299792458.0
+MU0 = 1.25663706127e-06
+
+
+class ParticleSet:
+    """Device-resident SoA particle arrays (double-buffered for the sort) + the PfPic descriptor."""
+
+    def __init__(self, z, ux, uz, w, L, dz, dt, *, q_over_m=ELECTRON_Q_OVER_M, jx_scale=ELECTRON_Q, c=C0, mu0=MU0,
+                 device=None):
+        torch = nat.require_cuda()
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.n, self.L, self.dz, self.dt = int(len(z)), int(L), float(dz), float(dt)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.cur = {k: torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64), **f64)
+                    for k, v in (("z", z), ("ux", ux), ("uz", uz), ("w", w))}
+        self.alt = {k: torch.empty_like(v) for k, v in self.cur.items()}
+        cell = np.clip(np.floor(np.asarray(z) * (1.0 / dz)).astype(np.int64), 0, L - 2).astype(np.int32)
+        self.cell = torch.as_tensor(cell, device=self.device)
+        self.cell_alt = torch.empty_like(self.cell)
+        self.Jx = torch.zeros(L, **f64)
+        self.p = nat.PfPic()
+        self.p.n, self.p.L = self.n, self.L
+        self.p.dz, self.p.dt, self.p.q_over_m, self.p.c, self.p.mu0, self.p.jx_scale = dz, dt, q_over_m, c, mu0, jx_scale
+        self._bind()
+        sb = nat.lib().pf_pic_scratch_bytes(ctypes.byref(self.p))
+        self.scratch = torch.empty(sb, dtype=torch.uint8, device=self.device)
+        self.scratch_bytes = sb
+        self.sorted = False
+
+    def _bind(self):
+        p = self.p
+        p.z, p.ux, p.uz, p.w = (self.cur[k].data_ptr() for k in ("z", "ux", "uz", "w"))
+        p.z_alt, p.ux_alt, p.uz_alt, p.w_alt = (self.alt[k].data_ptr() for k in ("z", "ux", "uz", "w"))
+        p.cell, p.cell_alt = self.cell.data_ptr(), self.cell_alt.data_ptr()
+        p.Jx = self.Jx.data_ptr()
+
+    def push(self, Ex, Hy):
+        """Advance every particle one step in the fields Ex, Hy (device tensors of length L)."""
+        self.p.Ex, self.p.Hy = Ex.data_ptr(), Hy.data_ptr()
+        nat.check(nat.lib().pf_pic_push(ctypes.byref(self.p), nat.current_stream_ptr()), "pf_pic_push")
+        self.sorted = False
+
+    def sort(self):
+        """Stable sort by cell; swaps the double buffers."""
+        nat.check(nat.lib().pf_pic_sort(ctypes.byref(self.p), self.scratch.data_ptr(), self.scratch_bytes,
+                                        nat.current_stream_ptr()), "pf_pic_sort")
+        self.cur, self.alt = self.alt, self.cur
+        self.cell, self.cell_alt = self.cell_alt, self.cell
+        self._bind()
+        self.sorted = True
+
+    def deposit(self):
+        """Deposit Jx (requires cell-sorted particles; sorts first if needed).  Returns the Jx tensor."""
+        if not self.sorted:
+            self.sort()
+        nat.check(nat.lib().pf_pic_deposit(ctypes.byref(self.p), self.scratch.data_ptr(), self.scratch_bytes,
+                                           nat.current_stream_ptr()), "pf_pic_deposit")
+        return self.Jx
+
+    def host(self):
+        return {k: v.cpu().numpy() for k, v in self.cur.items()} | {"cell": self.cell.cpu().numpy()}
+
+
+class CoupledPIC:
+    """PIC step coupled to one FDTD grid: deposit -> field step (Jx subtracted in ADE_ExUpdate) -> push.
+
+    ``grid`` is a _device.DeviceGrid whose descriptor gets its Jx pointer from the particle set; the
+    field step runs through ENGINE_OPS (the engine that carries per-cell arrays, including Jx)."""
+
+    def __init__(self, grid, particles, mode="free"):
+        from . import _device as dev
+        self.grid, self.particles = grid, particles
+        self.mode_id = dev.MODE_ID[mode]
+        self.grid.g.Jx = particles.Jx.data_ptr()
+        self.n = 0
+
+    def step(self, do_pol=False):
+        lib = nat.lib()
+        self.particles.deposit()
+        nat.check(lib.pf_run_pass(self.grid.ref(), self.mode_id, int(do_pol), self.n, 1, nat.PF_ENGINE_OPS, None, 0, 0,
+                                  None, 0, nat.current_stream_ptr()), "pf_run_pass")
+        self.particles.push(self.grid.tensor_view("Ex"), self.grid.tensor_view("Hy"))
+        self.n += 1

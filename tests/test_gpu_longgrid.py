@@ -1,0 +1,66 @@
+"""GPU tests of the long-grid / domain-decomposition path: a grid far beyond the reference's Nz cap,
+cut into several pieces with ghost exchange every k steps, must equal the CPU oracle's undecomposed
+run bit for bit (same operations in the same order on every owned cell)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import fdtd_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lg():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pyfdtd_b200  # noqa: F401
+    from pyfdtd_b200 import longgrid
+    return longgrid
+
+
+def oracle_long(info, Lg, T, nsteps, mode="lorentz"):
+    c = fo.Case(mode=mode, freq=9e9, Nz=Lg - 1, T=T, pw=info["pw"], mf=info["mf"], mr=info["mr"], nzsrc=info["nzsrc"],
+                x1Loc=info["mf"] - 20, x2Loc=info["nzsrc"] - 100, dz=info["dz"], dt=info["dt"],
+                courantNo=info["courantNo"], period=1 / 9e9, source="sine", tfsf=True, Periods=1000.0)
+    pa = fo.PassArrays(c, info["V"].plasmaFreqE, info["Exs"], info["Hys"], [info["nzsrc"] - 100], False)
+    fo.lib().orc_run(ctypes.byref(pa.g), fo.MODE_ID[mode], 1, 0, nsteps, T)
+    return pa
+
+
+@pytest.mark.parametrize("k,max_piece", [(64, 9000), (17, 7000), (64, 1 << 27)])
+def test_decomposed_long_grid_is_bit_identical_to_oracle(lg, k, max_piece):
+    Lg, T, nsteps = 40_000, 512, 300
+    grid, info = lg.lorentz_long_grid(Lg, T=T, k=k, max_piece=max_piece)
+    assert Lg > 25000, "beyond the reference's grid-size guard"
+    if max_piece < Lg:
+        assert len(grid.pieces) >= 4
+    grid.run(nsteps, do_pol=True)
+    pa = oracle_long(info, Lg, T, nsteps)
+    for name, want in (("Ex", pa.Ex), ("Hy", pa.Hy), ("Dx", pa.Dx), ("P", pa.P), ("Pprev", pa.Pprev), ("psiH", pa.psiH)):
+        got = grid.gather_owned(name)
+        if name in ("Dx", "P", "Pprev"):      # only defined on the slab
+            sl = slice(info["mf"], info["mr"])
+            assert np.array_equal(got[sl], want[sl]), name
+        elif name == "psiH":
+            pw = info["pw"]
+            assert np.array_equal(got[1:pw], want[1:pw]) and np.array_equal(got[Lg - pw:Lg - 1], want[Lg - pw:Lg - 1])
+        else:
+            assert np.array_equal(got, want), name
+    assert np.max(np.abs(pa.Ex)) > 0
+    probe = grid.probe_out[0, :nsteps].cpu().numpy()
+    assert np.array_equal(probe, pa.probe_out[0, :nsteps])
+
+
+def test_long_free_space_grid(lg):
+    Lg, T, nsteps = 30_000, 256, 200
+    grid, info = lg.lorentz_long_grid(Lg, T=T, k=32, max_piece=8000, mode="free")
+    grid.run(nsteps, do_pol=False)
+    c = fo.Case(mode="free", freq=9e9, Nz=Lg - 1, T=T, pw=info["pw"], mf=info["mf"], mr=info["mr"], nzsrc=info["nzsrc"],
+                x1Loc=info["mf"] - 20, x2Loc=info["nzsrc"] - 100, dz=info["dz"], dt=info["dt"],
+                courantNo=info["courantNo"], period=1 / 9e9, source="sine", tfsf=True, Periods=1000.0)
+    pa = fo.PassArrays(c, 0.0, info["Exs"], info["Hys"], [], False)
+    fo.lib().orc_run(ctypes.byref(pa.g), 0, 0, 0, nsteps, T)
+    assert np.array_equal(grid.gather_owned("Ex"), pa.Ex) and np.array_equal(grid.gather_owned("Hy"), pa.Hy)

@@ -1,0 +1,104 @@
+"""CPU tests of the multi-GPU plumbing (no GPU needed): piece planning, the ghost-exchange schedule,
+and the exchange itself over torch.distributed with the gloo backend at world_size 2, using tensor
+slicing as a stand-in for the pack / unpack kernels.  Also the round-robin sharding of sweep members."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import pyfdtd_b200  # noqa: F401
+from pyfdtd_b200 import longgrid as lgm
+
+
+@pytest.mark.parametrize("Lg,pw,world,k", [(100_000, 2394, 1, 64), (100_000, 2394, 2, 64), (1_000_000, 2394, 8, 64),
+                                           (40_000, 2394, 4, 17), (20_000, 300, 3, 64)])
+def test_plan_pieces_covers_grid(Lg, pw, world, k):
+    pieces = lgm.plan_pieces(Lg, pw, world, k, max_piece=30_000)
+    assert pieces[0]["lo"] == 0 and pieces[-1]["hi"] == Lg
+    for a, b in zip(pieces[:-1], pieces[1:]):
+        assert a["hi"] == b["lo"] and a["rank"] <= b["rank"]
+    assert sorted({p["rank"] for p in pieces}) == list(range(world))
+    for p in pieces:
+        assert p["hi"] - p["lo"] >= 2 * k or len(pieces) == 1
+        assert p["hi"] - p["lo"] <= 30_000 + 1
+    for r in range(world):      # every rank owns exactly its contiguous share
+        own = [p for p in pieces if p["rank"] == r]
+        assert own[0]["lo"] == r * Lg // world and own[-1]["hi"] == (r + 1) * Lg // world
+    assert pieces[0]["ghost_l"] == 0 and pieces[-1]["ghost_r"] == 0
+    assert all(p["ghost_l"] == k for p in pieces[1:]) and all(p["ghost_r"] == k for p in pieces[:-1])
+
+
+def test_exchange_schedule_is_symmetric():
+    pieces = lgm.plan_pieces(200_000, 2394, 2, 64, max_piece=40_000)
+    s0, s1 = lgm.exchange_schedule(pieces, 0), lgm.exchange_schedule(pieces, 1)
+    sends0 = [(i, j) for kind, i, side, j in s0 if kind == "send"]
+    recvs1 = [(j, i) for kind, i, side, j in s1 if kind == "recv"]
+    assert sends0 == recvs1 and len(sends0) == 1      # one rank boundary -> one message each way
+    assert sum(1 for kind, *_ in s0 if kind == "local") == sum(1 for p in pieces if p["rank"] == 0) - 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, Lg, pw, k, n_arr, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pieces = lgm.plan_pieces(Lg, pw, world, k, max_piece=3000)
+    mine = [p for p in pieces if p["rank"] == rank]
+    # "state": value of global cell z in array a is a*1e6 + z ; ghosts start as -1
+    local = {}
+    for p in mine:
+        z0 = p["lo"] - p["ghost_l"]
+        L = p["hi"] + p["ghost_r"] - z0
+        arr = torch.full((n_arr, L), -1.0, dtype=torch.float64)
+        own = torch.arange(p["lo"], p["hi"], dtype=torch.float64)
+        for a in range(n_arr):
+            arr[a, p["ghost_l"]: p["ghost_l"] + len(own)] = a * 1e6 + own
+        local[p["index"]] = arr
+
+    def pack(i, side):          # stand-in for pf_halo_pack: the k owned cells next to the edge
+        arr, p = local[i], pieces[i]
+        L = arr.shape[1]
+        sl = slice(k, 2 * k) if side == 0 else slice(L - 2 * k, L - k)
+        assert p["ghost_l" if side == 0 else "ghost_r"] == k
+        return arr[:, sl].reshape(-1).clone()
+
+    def unpack(i, side, buf):   # stand-in for pf_halo_unpack: the k ghost cells at the edge
+        arr = local[i]
+        L = arr.shape[1]
+        sl = slice(0, k) if side == 0 else slice(L - k, L)
+        arr[:, sl] = buf.reshape(n_arr, k)
+
+    sched = lgm.exchange_schedule(pieces, rank)
+    lgm.run_exchange(sched, pieces, pack, unpack, dist=dist, make_buffer=lambda i, side: torch.empty(n_arr * k, dtype=torch.float64))
+    ok = True
+    for p in mine:               # every ghost cell now holds its global cell's value
+        z0 = p["lo"] - p["ghost_l"]
+        arr = local[p["index"]]
+        z = torch.arange(z0, z0 + arr.shape[1], dtype=torch.float64)
+        for a in range(n_arr):
+            ok &= bool(torch.equal(arr[a], a * 1e6 + z))
+    # sweep-member sharding: member % world == rank, results gathered on rank 0 without a data-path collective
+    members = list(range(11))
+    mine_m = [m for m in members if m % world == rank]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {m: m * m for m in mine_m})
+    merged = {k_: v for d in gathered for k_, v in d.items()}
+    ok &= merged == {m: m * m for m in members}
+    np.save(os.path.join(result_dir, f"ok{rank}.npy"), np.array([ok]))
+    dist.destroy_process_group()
+
+
+def test_ghost_exchange_over_gloo_world2(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, 24_000, 700, 32, 7, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert bool(np.load(tmp_path / f"ok{r}.npy")[0])
