@@ -184,7 +184,7 @@ static int validate_pic(const PfPic *p)
     if (!p) return set_err(PF_E_ARG, "null PfPic");
     if (p->n < 0 || p->n > 2000000000LL) return set_err(PF_E_ARG, "particle count out of range");
     if (p->L < 3) return set_err(PF_E_ARG, "PIC grid too small");
-    if (!p->z || !p->ux || !p->uz || !p->w || !p->cell) return set_err(PF_E_ARG, "particle arrays missing");
+    if (p->n > 0 && (!p->z || !p->ux || !p->uz || !p->w || !p->cell)) return set_err(PF_E_ARG, "particle arrays missing");
     return 0;
 }
 
@@ -196,8 +196,8 @@ extern "C" {
 
 size_t pf_pic_scratch_bytes(const PfPic *p)
 {
-    if (!p || p->n <= 0) return 256;
-    return pic_plan(p).total;
+    if (!p) return 256;
+    return pic_plan(p).total;   // n = 0 still needs the per-cell accumulators of the deposit
 }
 
 int pf_pic_push(const PfPic *p, void *stream)
@@ -216,9 +216,9 @@ int pf_pic_sort(const PfPic *p, void *scratch, size_t scratch_bytes, void *strea
 {
     int rc = validate_pic(p);
     if (rc) return rc;
+    if (p->n == 0) return PF_OK;
     if (!p->z_alt || !p->ux_alt || !p->uz_alt || !p->w_alt || !p->cell_alt)
         return set_err(PF_E_ARG, "pf_pic_sort: alternate (output) arrays missing");
-    if (p->n == 0) return PF_OK;
     PicPlan pl = pic_plan(p);
     if (!scratch || scratch_bytes < pl.total) return set_err(PF_E_SCRATCH, "pf_pic_sort needs %zu bytes of scratch", pl.total);
     cudaStream_t st = (cudaStream_t)stream;
