@@ -102,6 +102,102 @@ class ProductWorkload:
                                       for m in members)          # per time step, all members
 
 
+# ------------------------------------------------------------------------------------------------ other BASELINE configs
+def _time_cuda(torch, fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def extras(torch, peak_gbs, quick=False):
+    """Short measurements of the other BASELINE.json configs (device-resident, synthetic non-zero state)."""
+    import pyfdtd_b200  # noqa: F401
+    from pyfdtd_b200 import MasterController as MC, Environment_Setup as envDef, Solver_Engine as SE, longgrid, pic, sweep
+    out = {}
+    # --- config 1 / 5: one long grid, streaming with k-step temporal blocking
+    for name, mode, cells, alg in (("free_long_grid", "free", 1 << 24, 32.0),
+                                   ("lorentz_long_grid", "lorentz", (1 << 24) if quick else 100_000_000, 32.0 + 0.7 * 40.0)):
+        steps = 128
+        grid, info = longgrid.lorentz_long_grid(cells, T=steps + 64, k=64, mode=mode)
+        for which in (0, 1):
+            for arrs in grid.bufs[which]:
+                for n, t in arrs.items():
+                    if t is not None:
+                        t.copy_((torch.rand_like(t) * 2 - 1) * sweep.MemberBatch.STATE_SCALE[n])
+        for arrs0, arrs1 in zip(*grid.bufs):
+            for n in arrs0:
+                if arrs0[n] is not None:
+                    arrs1[n].copy_(arrs0[n])
+        sec = _time_cuda(torch, lambda: grid.run(steps, do_pol=(mode == "lorentz")), 2)
+        rate = cells * steps / sec / 1e9
+        out[name] = {"cells": cells, "steps": steps, "pieces": len(grid.pieces), "Gcell_updates_per_s": rate,
+                     "algorithmic_GBps_k1": rate * alg, "frac_of_hbm_peak_k1": rate * alg / peak_gbs, "temporal_block_k": 64}
+        del grid
+        torch.cuda.empty_cache()
+    # --- config 3: nonlinear (cubic solve per slab cell per step) sweep batch
+    M, S = (64, 64) if quick else (256, 128)
+    freqs = np.linspace(6e9, 10.5e9, 16)
+    members, share, first = [], [], {}
+    for i in range(M):
+        f = float(freqs[i % 16])
+        if f in first:
+            b = members[first[f]]
+            m = sweep.Member(b.V, b.P, b.C_V, b.C_P, b._Exs * (1 + i / M), b._Hys * (1 + i / M), [b.P.materialFrontEdge], nsteps=S)
+            share.append(first[f])
+        else:
+            tup = envDef.envSetup(f, 0.7, 7000, 8000, nonLinMed=True)
+            P = MC.Params(*tup, False, 0.7, f, 20)
+            P.TFSF, P.SineCont, P.Periods, P.nonLinMed, P.FreeSpace, P.LorentzMed = True, True, 1000, True, False, False
+            V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
+            C_P = MC.CPML_Params(P.dz)
+            C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
+            C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=False, nonlinear=True)
+            m = sweep.Member(V, P, C_V, C_P, Exs, Hys, [P.materialFrontEdge], nsteps=S)
+            m._Exs, m._Hys = Exs, Hys
+            first[f] = i
+            share.append(i)
+        m.T = S
+        m.srcE, m.srcH = m.srcE[:S], m.srcH[:S]
+        members.append(m)
+    batch = sweep.MemberBatch(members, "nl", share_coef=share)
+    batch.upload()
+    batch.randomize_state()
+
+    def nl_step():
+        batch.reset_state(template=True)
+        batch.run(do_pol=False)
+    sec = _time_cuda(torch, nl_step, 2)
+    slab_cells = sum(m.scalars["mr"] - m.scalars["mf"] for m in members)
+    out["nl_cubic_sweep"] = {"members": M, "steps": S, "Gcell_updates_per_s": batch.cell_steps / sec / 1e9,
+                             "cubic_solves_per_s": slab_cells * S / sec}
+    del batch
+    torch.cuda.empty_cache()
+    # --- config 4: PIC push + cell sort + deterministic deposit
+    import pic_oracle as po
+    L, dz, dt = 13194, 8.3276e-5, 2.6389e-13
+    n = 2_000_000 if quick else 20_000_000
+    z, ux, uz, w, cell = po.make_beam(n, L, dz, seed=1)
+    ps = pic.ParticleSet(z, ux, uz, w, L, dz, dt)
+    Ex = (torch.rand(L, dtype=torch.float64, device="cuda") * 2 - 1) * 1e5
+    Hy = (torch.rand(L, dtype=torch.float64, device="cuda") * 2 - 1) * 3e2
+
+    def pic_step():
+        ps.push(Ex, Hy)
+        ps.deposit()       # sorts first (particles left their cells), then deposits
+    sec = _time_cuda(torch, pic_step, 5)
+    sec_push = _time_cuda(torch, lambda: ps.push(Ex, Hy), 5)
+    out["pic"] = {"particles": n, "particle_steps_per_s": n / sec, "push_only_particles_per_s": n / sec_push,
+                  "algorithmic_GBps": 60.0 * n / sec / 1e9, "frac_of_hbm_peak": 60.0 * n / sec / 1e9 / peak_gbs,
+                  "note": "step = Boris push + stable radix sort by cell + warp-per-cell deterministic deposit"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
     def __init__(self, index):
@@ -214,6 +310,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--fma", action="store_true", help="PF_F_FMA kernels (not bit-identical; reported in config)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--quick-extras", action="store_true", help="smaller extras (smoke)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -331,6 +429,16 @@ def main():
                "sample": f"{n_cpu} members x {args.cpu_steps} steps of the same sweep family on {threads} threads "
                          f"({sec:.2f} s wall)"}
 
+    cfg_cells, cfg_state_mb, h2d_b, d2h_b = wl.cell_steps, batch.n_state * 8 / 1e6, batch.h2d_bytes, batch.d2h_bytes
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del wl, batch
+        torch.cuda.empty_cache()
+        try:
+            extra = extras(torch, peak, quick=args.quick_extras)
+        except Exception as e:   # the headline line must survive a failing extra
+            extra = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -338,12 +446,12 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"batched Lorentz-ADE+CPML 1D FDTD sweep, {args.members} members/GPU x "
                                    f"{args.pass_steps} time steps per step, Nz~10-15k cells/member "
-                                   f"({wl.cell_steps/1e9:.2f} Gcell-updates/step/GPU), probes recorded every step",
+                                   f"({cfg_cells/1e9:.2f} Gcell-updates/step/GPU), probes recorded every step",
                        "members_per_gpu": args.members, "time_steps_per_step": args.pass_steps,
                        "k_block": k_block, "arithmetic": "fma-contracted" if args.fma else "exact (bit-identical to reference order)",
-                       "l2_policy": f"state {batch.n_state*8/1e6:.0f} MB per GPU > 126 MB L2, restored from a random template every step",
+                       "l2_policy": f"state {cfg_state_mb:.0f} MB per GPU > 126 MB L2, restored from a random template every step",
                        "parallelism": f"members sharded over {world} GPU(s), no collectives"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes, "d2h_bytes_per_step": batch.d2h_bytes,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
                     "ms_per_step": e2e_ms / args.steps, "probe_checksum": probe_checksum},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -351,6 +459,8 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if extra is not None:
+            line["other_configs"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
