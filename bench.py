@@ -63,6 +63,18 @@ def alg_bytes_per_cell_step(L, pw, mf, mr):
     return 32 * L + 64 * cpml + 40 * slab
 
 
+def dp_instr_per_cell_step(L, pw, mf, mr):
+    """Separately rounded fp64 instructions of the reference's own arithmetic per time step, summed over one
+    member's cells (exact mode, pass 1 of the Lorentz integrator): vacuum cell 6 (Ex 3 + Hy 3); CPML cell +10
+    (psi_E 3 + correction 2 + psi_H 3 + correction 2); Lorentz slab cell 15 (P 5, dH 1, Dx 2, Dx-P 1, /eps0 3, Hy 3;
+    its Ex += ... is dead because ADE_ExCreate overwrites it) and +6 where the slab lies inside the CPML."""
+    cpml_left = max(0, pw - 1)
+    slab = max(0, mr - mf)
+    slab_in_cpml = max(0, mr - max(mf, L - pw))
+    vac = L - slab
+    return 6 * vac + 10 * (cpml_left + 2) + 15 * slab + 6 * slab_in_cpml
+
+
 class ProductWorkload:
     def __init__(self, n_members, steps_per_pass, n_freq):
         import pyfdtd_b200  # noqa: F401
@@ -98,6 +110,8 @@ class ProductWorkload:
         self.members = members
         self.batch = sweep.MemberBatch(members, "lorentz", share_coef=share)
         self.cell_steps = self.batch.cell_steps
+        self.dp_instr_per_step = sum(dp_instr_per_cell_step(m.L, m.scalars["pw"], m.scalars["mf"], m.scalars["mr"])
+                                     for m in members)
         self.alg_bytes_per_step = sum(alg_bytes_per_cell_step(m.L, m.scalars["pw"], m.scalars["mf"], m.scalars["mr"])
                                       for m in members)          # per time step, all members
 
@@ -412,12 +426,22 @@ def main():
     tile_cells, halo = kcfg[0].value, k_block
     # modelled real HBM traffic of one launch: every tile reads tile_cells of state, writes its interior
     hbm_model = wl.alg_bytes_per_step * (1.0 + 2.0 * halo / (tile_cells - 2 * halo))
+    fp64_peak, fp64_src = 1.85e13, "fallback (round-1 probe on this pool)"
+    probe_path = os.path.join(ROOT, "profiles", "r1_fp64_probe.json")
+    if os.path.exists(probe_path):
+        fp64_peak = 2.0 * json.load(open(probe_path))["dmul_dadd_pairs_per_s_t1024"]
+        fp64_src = "measured (tools/fp64_probe.cu, profiles/r1_fp64_probe.json: separately rounded DMUL+DADD stream)"
+    dp_per_launch = wl.dp_instr_per_step * args.pass_steps / n_launch_per_step
+    fp64 = {"achieved_dp_instr_per_s": dp_per_launch / (avg_kernel_ms * 1e-3), "peak_dp_instr_per_s": fp64_peak,
+            "frac": dp_per_launch / (avg_kernel_ms * 1e-3) / fp64_peak, "peak_source": fp64_src,
+            "note": "algorithmic fp64 instructions of the reference arithmetic (exact mode, no FMA contraction) / kernel time; "
+                    "this, not HBM, is the pipe that bounds the temporally blocked kernel"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "k_tile<PF_LORENTZ,POL,8,Exact>", "peak_source": peak_src,
                 "kernel_ms_avg": avg_kernel_ms, "kernel_launches_timed": kn.value,
                 "kernel_share_of_step": kms.value / ms_total if ms_total else None,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "temporal_block_k": k_block,
-                "hbm_bytes_per_launch_model": hbm_model,
+                "hbm_bytes_per_launch_model": hbm_model, "fp64_pipe": fp64,
                 "note": "on-chip temporally blocked: algorithmic (k=1) bytes / time exceeds the HBM roofline by design"}
 
     cpu = None

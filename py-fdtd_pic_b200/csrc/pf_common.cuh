@@ -137,11 +137,22 @@ __device__ __forceinline__ CubicConsts cubic_consts_dev(double a, double b, doub
     return k;
 }
 
+// v ** (1/3.0) on |v| with the sign restored (CubicEquationSolver.py:76-85).  The reference's
+// exponent is the double nearest to 1/3, c = 1/3 - 1.85e-17, so pow(x, c) = cbrt(x) * x^(c - 1/3)
+// = cbrt(x) * (1 + (c - 1/3) ln x + O(1e-31)).  cbrt() is ~5x cheaper than CUDA's pow() and the
+// correction is below 1e-15, so single-precision ln is ample.  Accuracy ~1.5 ulp -- the same class as
+// CUDA pow() (2 ulp) against glibc pow(), which is what the 1e-10 tolerance on Acubic covers.
+__device__ __forceinline__ double pow_third(double x)   // x >= 0
+{
+    const double c_minus_third = -1.850371707708594e-17;   // double(1/3.0) - 1/3, exactly
+    const double s = cbrt(x);
+    const double lnx = (double)__logf((float)x);
+    return (x > 0.0) ? __fma_rn(s, c_minus_third * lnx, s) : s;
+}
+
 __device__ __forceinline__ double signed_cbrt_pow(double v)
 {
-    // reference: v ** (1/3.0) on |v| with the sign restored (CubicEquationSolver.py:76-85)
-    double r = pow(fabs(v), 1.0 / 3.0);
-    return copysign(r, v);
+    return copysign(pow_third(fabs(v)), v);
 }
 
 __device__ __forceinline__ double cubic_root0(const CubicConsts &k, double d)
@@ -153,7 +164,7 @@ __device__ __forceinline__ double cubic_root0(const CubicConsts &k, double d)
         return (D >= 0.0) ? __ddiv_rn(__dadd_rn(-k.c, sqrt(D)), twob) : __ddiv_rn(-k.c, twob);
     }
     double t3 = div_const(__dmul_rn(27.0, d), k.a, k.inv_a);                 // 27*d/a
-    double g = __ddiv_rn(__dadd_rn(k.g_ab, t3), 27.0);                       // findG
+    double g = div_const(__dadd_rn(k.g_ab, t3), 27.0, 1.0 / 27.0);           // findG
     double gg4 = __dmul_rn(__dmul_rn(g, g), 0.25);                           // g**2/4
     double h = __dadd_rn(gg4, k.f3_27);                                      // findH
     double ghalf = __dmul_rn(g, 0.5);
@@ -181,6 +192,46 @@ __device__ __forceinline__ double acubic_cell(const CubicConsts &k, double dx, d
     double q = fabs(div_const(dx, eps0, inv_eps0));
     double d = -__dmul_rn(q, q);
     return (fabs(d) > 1e-8) ? cubic_root0(k, d) : 0.0;
+}
+
+// The whole nonlinear material law of one cell (AcubicFinder + NonLinExUpdate, BaseFDTD11.py:793-877),
+// deliberately OUT OF LINE: inlined C times into an unrolled time-step body it overflows the
+// instruction cache (ncu: stall_no_instruction 8.3 per issue), and at ~200 instructions per call the
+// call overhead is noise.  Constants are read through the pointer (L1-resident).
+struct NlResult {
+    double a, e;
+};
+static __device__ __noinline__ NlResult nl_material_law(const CubicConsts *__restrict__ kc, double dx, double eps0,
+                                                       double inv_eps0, double den0, double den1)
+{
+    NlResult r;
+    r.a = acubic_cell(*kc, dx, eps0, inv_eps0);
+    r.e = __ddiv_rn(dx, __dadd_rn(den0, __dmul_rn(den1, r.a)));
+    return r;
+}
+
+// C cells at once (all of a thread's cells lie in the slab): one out-of-line copy whose C independent
+// dependency chains the scheduler can interleave.
+template <int C>
+struct NlVec {
+    double v[C];
+};
+template <int C>
+struct NlResultVec {
+    double a[C], e[C];
+};
+template <int C>
+static __device__ __noinline__ NlResultVec<C> nl_material_law_vec(const CubicConsts *__restrict__ kc, NlVec<C> dx, double eps0,
+                                                                double inv_eps0, double den0, double den1)
+{
+    NlResultVec<C> r;
+    const CubicConsts k = *kc;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        r.a[j] = acubic_cell(k, dx.v[j], eps0, inv_eps0);
+        r.e[j] = __ddiv_rn(dx.v[j], __dadd_rn(den0, __dmul_rn(den1, r.a[j])));
+    }
+    return r;
 }
 
 // Host-side constants, evaluated exactly as CubicEquationSolver.findF/findG/findH do in CPython

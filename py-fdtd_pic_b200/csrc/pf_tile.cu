@@ -112,7 +112,7 @@ struct StepConsts {
 //   pc = P^n (current polarisation), pq = P^{n-1}: the new P^{n+1} is written over pq, so the
 //   caller alternates (pc,pq) <-> (pq,pc) instead of shifting the history (no register moves).
 template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML>
-__device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts &K, const CubicConsts &kc, int tid, int s,
+__device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts &K, const CubicConsts *kcp, int tid, int s,
                                           double (&ex)[C], double (&hy)[C], double (&dx)[C], double (&pc)[C],
                                           double (&pq)[C], double (&pe)[C], double (&ph)[C], double (&acub)[C],
                                           double (&rbe)[C], double (&rce)[C], double (&rcm)[C])
@@ -152,14 +152,24 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
                 dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));
                 const double em = div_const_fast(A::sub(dx[j], pnow), K.eps0, K.inv_eps0, divkey);
                 e = (!GEN || ((K.mSlab >> j) & 1)) ? em : e;
-            } else if (!GEN || ((K.mSlab >> j) & 1)) {
+            } else if (!GEN) {
+                dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));      // the material law of all C cells follows the loop
+            } else if ((K.mSlab >> j) & 1) {
                 dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));
-                const double a = acubic_cell(kc, dx[j], K.eps0, K.inv_eps0);
-                acub[j] = a;
-                e = __ddiv_rn(dx[j], A::add(K.den0, A::mul(K.den1, a)));
+                const NlResult nl = nl_material_law(kcp, dx[j], K.eps0, K.inv_eps0, K.den0, K.den1);
+                acub[j] = nl.a;
+                e = nl.e;
             }
         }
         ex[j] = e;
+    }
+    if (MODE == PF_NL && ALL_MAT) {
+        NlVec<C> dv;
+#pragma unroll
+        for (int j = 0; j < C; ++j) dv.v[j] = dx[j];
+        const NlResultVec<C> nl = nl_material_law_vec<C>(kcp, dv, K.eps0, K.inv_eps0, K.den0, K.den1);
+#pragma unroll
+        for (int j = 0; j < C; ++j) { acub[j] = nl.a[j]; ex[j] = nl.e[j]; }
     }
     if (MODE == PF_LORENTZ && HAS_MAT && !div_const_in_range(divkey)) {
         // some cell's (Dx - P) was zero, in the denormal range or non-finite: redo those divisions
@@ -295,8 +305,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
     K.pA = g.polA; K.pB = g.polB; K.pC = g.polC; K.den0 = g.nl_den0; K.den1 = g.nl_den1;
     K.jsrc = M.jsrc; K.jtfsf = M.jtfsf; K.mSlab = mSlab;
     K.wSrc = __any_sync(0xffffffffu, M.jsrc >= 0 || M.jtfsf >= 0);
-    CubicConsts kc;
-    if (MODE == PF_NL && HAS_MAT) kc = TG.d.k;
+    const CubicConsts *kc = &TG.d.k;
     const int pj0 = M.pj0, pj1 = M.pj1;
     const bool wProbe = __any_sync(0xffffffffu, pj0 >= 0);
 
