@@ -154,6 +154,27 @@ def extras(torch, peak_gbs, quick=False):
                      "algorithmic_GBps_k1": rate * alg, "frac_of_hbm_peak_k1": rate * alg / peak_gbs, "temporal_block_k": 64}
         del grid
         torch.cuda.empty_cache()
+    # --- configs 1/2 as the reference runs them: ONE default-geometry run through Controller (host API, e2e)
+    import time as _t
+    for name, lor in (("single_run_free_default", False), ("single_run_lorentz_default", True)):
+        tup = envDef.envSetup(9e9, 0.7, 7000, 8000, LorMed=lor)
+        P = MC.Params(*tup, False, 0.7, 9e9, 20)
+        P.TFSF, P.SineCont, P.Periods, P.LorentzMed, P.FreeSpace = True, True, 1000, lor, not lor
+        V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 10)
+        C_P = MC.CPML_Params(P.dz)
+        C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
+        best = None
+        for _ in range(2):
+            t0 = _t.perf_counter()
+            MC.Controller(V, P, C_V, C_P)
+            torch.cuda.synchronize()
+            dtc = _t.perf_counter() - t0
+            best = dtc if best is None else min(best, dtc)
+        cu = 2 * P.timeSteps * (P.Nz + 1)
+        out[name] = {"Nz": P.Nz, "timeSteps": P.timeSteps, "passes": 2, "seconds_e2e": best, "Mcell_updates_per_s": cu / best / 1e6,
+                     "reference_seconds_build_container": 130.2 if lor else 7.3,
+                     "note": "Controller() incl. host setup, H2D/D2H, Ex_History snapshots every 50 steps; reference time = "
+                             "unmodified reference on the build container CPU (tests/golden/*_default_full.npz: ref_wall_seconds)"}
     # --- config 3: nonlinear (cubic solve per slab cell per step) sweep batch
     M, S = (64, 64) if quick else (256, 128)
     freqs = np.linspace(6e9, 10.5e9, 16)

@@ -125,6 +125,9 @@ int pf_probe_record(const PfGrid *g, int n, void *stream);  /* Solver_Engine.py:
 /* CubicEquationSolver.solve root[0] (CubicEquationSolver.py:29-105) for n polynomials,
  * coeffs = [n][4] (a,b,c,d) device, root0 = [n] device                                          */
 int pf_cubic_root0(const double *coeffs, double *root0, int n, void *stream);
+/* every root, as CubicEquationSolver.solve returns them: roots = [n][3][2] (re, im) device,
+ * nroots = [n] device (1 linear, 2 quadratic, 3 cubic)                                          */
+int pf_cubic_solve(const double *coeffs, double *roots, int *nroots, int n, void *stream);
 
 /* ---- integrator passes ------------------------------------------------------------------ */
 /* One pass of `nsteps` steps starting at absolute step n0 on ONE grid: the body of the

@@ -157,9 +157,14 @@ def run_cubic(name="cubic_roots"):
              (0.0, 1.0, 2.0, 5.0), (1.0, 0.0, 0.0, 8.0)]
     coeffs = np.array(rows, dtype=np.float64)
     root0 = np.zeros(len(rows), dtype=np.complex128)
+    roots = np.full((len(rows), 3), np.nan + 0j, dtype=np.complex128)     # all roots, NaN-padded
+    nroots = np.zeros(len(rows), dtype=np.int32)
     for i, (a, b, c, d) in enumerate(coeffs):
-        root0[i] = solve(float(a), float(b), float(c), float(d))[0]
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), coeffs=coeffs, root0=root0,
+        r = np.asarray(solve(float(a), float(b), float(c), float(d)), dtype=np.complex128)
+        root0[i] = r[0]
+        roots[i, : len(r)] = r
+        nroots[i] = len(r)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), coeffs=coeffs, root0=root0, roots=roots, nroots=nroots,
                         versions=json.dumps(versions()))
     print(f"{name}: {len(rows)} polynomials", flush=True)
 

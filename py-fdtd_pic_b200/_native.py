@@ -73,6 +73,7 @@ SYMBOLS = {
     "pf_nonlin_ex_update": (c_int, [_G, c_void_p]),
     "pf_probe_record": (c_int, [_G, c_int, c_void_p]),
     "pf_cubic_root0": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "pf_cubic_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pf_run_pass": (c_int, [_G, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_batch": (c_int, [_G, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_scratch_bytes": (c_size_t, [_G, c_int, c_int]),

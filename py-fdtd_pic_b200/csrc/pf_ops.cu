@@ -156,6 +156,70 @@ __global__ void __launch_bounds__(OPS_THREADS) k_cubic_root0(const double *__res
     out[i] = cubic_root0(k, d);
 }
 
+// All roots of a x^3 + b x^2 + c x + d as CubicEquationSolver.solve returns them
+// (CubicEquationSolver.py:29-90): roots[i][r] = (re, im), nroots[i] in {1,2,3}.
+__global__ void __launch_bounds__(OPS_THREADS) k_cubic_solve(const double *__restrict__ co, double *__restrict__ roots,
+                                                            int *__restrict__ nroots, int n)
+{
+    int i = blockIdx.x * OPS_THREADS + threadIdx.x;
+    if (i >= n) return;
+    const double a = co[4 * i], b = co[4 * i + 1], c = co[4 * i + 2], d = co[4 * i + 3];
+    double re[3] = {0, 0, 0}, im[3] = {0, 0, 0};
+    int nr = 3;
+    if (a == 0.0 && b == 0.0) {                      // linear
+        re[0] = __ddiv_rn(__dmul_rn(-d, 1.0), c);
+        nr = 1;
+    } else if (a == 0.0) {                           // quadratic
+        double D = __dsub_rn(__dmul_rn(c, c), __dmul_rn(__dmul_rn(4.0, b), d));
+        const double twob = __dmul_rn(2.0, b);
+        if (D >= 0.0) {
+            D = sqrt(D);
+            re[0] = __ddiv_rn(__dadd_rn(-c, D), twob);
+            re[1] = __ddiv_rn(__dsub_rn(-c, D), twob);
+        } else {
+            D = sqrt(-D);
+            re[0] = __ddiv_rn(-c, twob); im[0] = __ddiv_rn(D, twob);
+            re[1] = __ddiv_rn(-c, twob); im[1] = __ddiv_rn(-D, twob);
+        }
+        nr = 2;
+    } else {
+        const CubicConsts k = cubic_consts_dev(a, b, c);
+        const double g = __ddiv_rn(__dadd_rn(k.g_ab, __ddiv_rn(__dmul_rn(27.0, d), a)), 27.0);
+        const double gg4 = __dmul_rn(__dmul_rn(g, g), 0.25);
+        const double h = __dadd_rn(gg4, k.f3_27);
+        const double ghalf = __dmul_rn(g, 0.5);
+        if (k.f == 0.0 && g == 0.0 && h == 0.0) {    // three equal real roots
+            const double da = __ddiv_rn(d, a);
+            const double x = (da >= 0.0) ? -pow_third(da) : pow_third(-da);
+            re[0] = re[1] = re[2] = x;
+        } else if (h <= 0.0) {                       // three real roots
+            const double ii = sqrt(__dsub_rn(gg4, h));
+            const double j = pow_third(ii);
+            const double kk = acos(-__ddiv_rn(g, __dmul_rn(2.0, ii)));
+            const double Lm = -j, M = cos(__ddiv_rn(kk, 3.0)), N = __dmul_rn(sqrt(3.0), sin(__ddiv_rn(kk, 3.0)));
+            const double P = -k.b_3a;
+            re[0] = __dsub_rn(__dmul_rn(__dmul_rn(2.0, j), M), k.b_3a);
+            re[1] = __dadd_rn(__dmul_rn(Lm, __dadd_rn(M, N)), P);
+            re[2] = __dadd_rn(__dmul_rn(Lm, __dsub_rn(M, N)), P);
+        } else {                                     // one real root, two complex
+            const double sh = sqrt(h);
+            const double S = signed_cbrt_pow(__dadd_rn(-ghalf, sh));
+            const double U = signed_cbrt_pow(__dsub_rn(-ghalf, sh));
+            const double SU = __dadd_rn(S, U);
+            re[0] = __dsub_rn(SU, k.b_3a);
+            const double rr = __dsub_rn(__ddiv_rn(-SU, 2.0), k.b_3a);
+            const double ii2 = __dmul_rn(__dmul_rn(__dsub_rn(S, U), sqrt(3.0)), 0.5);
+            re[1] = rr; im[1] = ii2;
+            re[2] = rr; im[2] = -ii2;
+        }
+    }
+    for (int r = 0; r < 3; ++r) {
+        roots[6 * i + 2 * r] = re[r];
+        roots[6 * i + 2 * r + 1] = im[r];
+    }
+    nroots[i] = nr;
+}
+
 static int validate(const PfGrid *g)
 {
     if (!g) return set_err(PF_E_ARG, "null grid");
@@ -275,6 +339,15 @@ int pf_probe_record(const PfGrid *g, int n, void *stream)
     if (g->n_probes <= 0) return PF_OK;
     k_probe<<<(g->n_probes + 31) / 32, 32, 0, (cudaStream_t)stream>>>(*g, n);
     PF_LAUNCH_CHECK("k_probe");
+    return PF_OK;
+}
+
+int pf_cubic_solve(const double *coeffs, double *roots, int *nroots, int n, void *stream)
+{
+    if (!coeffs || !roots || !nroots || n < 0) return set_err(PF_E_ARG, "pf_cubic_solve: bad arguments");
+    if (n == 0) return PF_OK;
+    k_cubic_solve<<<ops_blocks(n), OPS_THREADS, 0, (cudaStream_t)stream>>>(coeffs, roots, nroots, n);
+    PF_LAUNCH_CHECK("k_cubic_solve");
     return PF_OK;
 }
 

@@ -291,3 +291,22 @@ def test_batched_sweep_matches_reference_sweep(pk):
     np.testing.assert_allclose(measured, g["measured"], rtol=1e-9)
     np.testing.assert_allclose(analytical, g["analytical"], rtol=1e-12)
     np.testing.assert_allclose(freqs, g["freqs"], rtol=0, atol=0)
+
+
+def test_cubic_solver_mirror_all_roots(pk):
+    """CubicEquationSolver.solve mirror: every root of every branch against the reference's outputs."""
+    from pyfdtd_b200 import CubicEquationSolver as CES
+    g = load_golden("cubic_roots")
+    roots, nr = CES.solve_many(g["coeffs"])
+    assert np.array_equal(nr, g["nroots"])
+    want = g["roots"]
+    a, b = g["coeffs"][:, 0], g["coeffs"][:, 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mag = np.where(a != 0, np.abs(b / (3 * a)), 1.0)
+    for r in range(3):
+        sel = nr > r
+        scale = np.maximum(np.maximum(np.abs(want[sel, r]), mag[sel]), 1e-300)
+        assert np.max(np.abs(roots[sel, r] - want[sel, r]) / scale) <= 1e-12, r
+    one = CES.solve(1.0, -6.0, 11.0, -6.0)        # (x-1)(x-2)(x-3)
+    assert np.allclose(np.sort(np.real(one)), [1.0, 2.0, 3.0], atol=1e-12)
+    assert CES.solve(CES.CubicSolver(0.0, 0.0, 4.0, -2.0))[0] == 0.5
