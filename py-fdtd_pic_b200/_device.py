@@ -62,7 +62,7 @@ def canonical_form(P, arrs, Jx=None):
 
 
 def probes_ok_for_tiles(probe_idx, cells_per_thread=8):
-    """The tile kernel lets one thread own at most two probe cells."""
+    """The tile kernel lets one thread own at most two probe cells (a thread owns <= 8 consecutive cells)."""
     p = np.sort(np.asarray(probe_idx, dtype=np.int64))
     return len(p) < 3 or bool(np.all(p[2:] - p[:-2] >= cells_per_thread))
 

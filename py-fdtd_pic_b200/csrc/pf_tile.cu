@@ -38,7 +38,7 @@ namespace pf {
 #define PF_TILE_CELLS 1024
 #endif
 #ifndef PF_TILE_C
-#define PF_TILE_C 4
+#define PF_TILE_C 2
 #endif
 #ifndef PF_TILE_MINBLOCKS
 #define PF_TILE_MINBLOCKS 2
