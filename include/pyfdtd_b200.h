@@ -201,6 +201,12 @@ int pf_pic_push(const PfPic *p, void *stream);
 /* stable sort of the particles by cell: reads z,ux,uz,w,cell, writes the *_alt arrays;
  * scratch sized by pf_pic_scratch_bytes                                                          */
 int pf_pic_sort(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
+/* push + stable re-sort fused, for a set that IS sorted by cell on entry: exploits |v| dt < dz (a
+ * particle changes cell by at most one per step) -- count pass, cell scan, move pass; reads the primary
+ * arrays, writes the pushed AND sorted particles to the *_alt arrays (caller swaps).  Bit-identical to
+ * pf_pic_push followed by pf_pic_sort.  pf_pic_check returns 1 if a particle crossed more than one cell. */
+int pf_pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
+int pf_pic_check(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
 /* deterministic cell-sorted deposition of Jx (requires particles sorted by cell)               */
 int pf_pic_deposit(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
 size_t pf_pic_scratch_bytes(const PfPic *p);

@@ -86,6 +86,8 @@ SYMBOLS = {
     "pf_halo_unpack": (ctypes.c_longlong, [_G, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pf_pic_push": (c_int, [_PP, c_void_p]),
     "pf_pic_sort": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
+    "pf_pic_push_sorted": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
+    "pf_pic_check": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
     "pf_pic_deposit": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
     "pf_pic_scratch_bytes": (c_size_t, [_PP]),
 }

@@ -24,14 +24,17 @@ namespace pf {
 constexpr int PIC_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------------ push
-__global__ void __launch_bounds__(PIC_THREADS) k_pic_push(PfPic p)
+struct Pushed {
+    double z, ux, uz;
+    int cell;
+};
+
+// Boris push of one particle (the single definition used by every kernel, so that the counting pass
+// and the moving pass of the fused re-sort see bit-identical results).
+__device__ __forceinline__ Pushed pic_push_one(const PfPic &p, double z, double ux, double uz)
 {
-    long long i = (long long)blockIdx.x * PIC_THREADS + threadIdx.x;
-    if (i >= p.n) return;
     const double inv_dz = 1.0 / p.dz;
     const double zmax = (double)(p.L - 1) * p.dz;
-    double z = p.z[i], ux = p.ux[i], uz = p.uz[i];
-
     // gather Ex (integer nodes)
     double s = z * inv_dz;
     int c = (int)floor(s);
@@ -68,12 +71,138 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_push(PfPic p)
     if (z < 0.0) { z = -z; uzn = -uzn; }
     if (z > zmax) { z = 2.0 * zmax - z; uzn = -uzn; }
     z = fmin(fmax(z, 0.0), zmax);
-
-    p.z[i] = z;
-    p.ux[i] = uxn;
-    p.uz[i] = uzn;
+    Pushed r;
+    r.z = z; r.ux = uxn; r.uz = uzn;
     int cn = (int)floor(z * inv_dz);
-    p.cell[i] = max(0, min(cn, p.L - 2));
+    r.cell = max(0, min(cn, p.L - 2));
+    return r;
+}
+
+__global__ void __launch_bounds__(PIC_THREADS) k_pic_push(PfPic p)
+{
+    long long i = (long long)blockIdx.x * PIC_THREADS + threadIdx.x;
+    if (i >= p.n) return;
+    Pushed r = pic_push_one(p, p.z[i], p.ux[i], p.uz[i]);
+    p.z[i] = r.z;
+    p.ux[i] = r.ux;
+    p.uz[i] = r.uz;
+    p.cell[i] = r.cell;
+}
+
+// ------------------------------------------------------------------------------------------------ fused push + re-sort
+// A particle moves less than one cell per step (|v| dt < c dt = 0.95 dz), so a cell-sorted set stays
+// sorted up to exchanges between neighbouring cells.  The stable sort by new cell is then a counting
+// problem: the new population of cell c is [right-movers of c-1][stayers of c][left-movers of c+1], each
+// group in its old order.  Two passes, one warp per (old) cell, no radix sort, no gather:
+//   count : push the cell's particles in registers, count left / stay / right            (reads z,ux,uz)
+//   scan  : new_start = exclusive scan of nR[c-1] + nS[c] + nL[c+1]
+//   move  : push again (bit-identical), rank by ballot in index order, write every particle straight to
+//           its final slot of the alternate arrays                                     (reads 32 B, writes 36 B)
+__global__ void __launch_bounds__(PIC_THREADS) k_pic_cell_start(const int *__restrict__ cell, long long n, int L,
+                                                                long long *__restrict__ start)
+{
+    int c = blockIdx.x * PIC_THREADS + threadIdx.x;
+    if (c > L) return;
+    long long lo = 0, hi = n;            // lower bound of c in the sorted cell array
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (cell[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    start[c] = lo;
+}
+
+__global__ void __launch_bounds__(PIC_THREADS) k_pic_count(PfPic p, const long long *__restrict__ start, int *__restrict__ counts,
+                                                           int *__restrict__ err)
+{
+    const int c = (blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= p.L) return;
+    const long long a = start[c], b = start[c + 1];
+    int nl = 0, ns = 0, nr = 0;
+    for (long long i0 = a; i0 < b; i0 += 32) {
+        const long long i = i0 + lane;
+        int d = 2;                        // 2 = no particle in this lane
+        if (i < b) {
+            Pushed r = pic_push_one(p, p.z[i], p.ux[i], p.uz[i]);
+            d = r.cell - c;
+            if (d < -1 || d > 1) { atomicExch(err, 1); d = max(-1, min(1, d)); }
+        }
+        nl += __popc(__ballot_sync(0xffffffffu, d == -1));
+        ns += __popc(__ballot_sync(0xffffffffu, d == 0));
+        nr += __popc(__ballot_sync(0xffffffffu, d == 1));
+    }
+    if (lane == 0) {
+        counts[3 * c] = nl;
+        counts[3 * c + 1] = ns;
+        counts[3 * c + 2] = nr;
+    }
+}
+
+// single CTA: new_start[c] = sum_{c' < c} (nR[c'-1] + nS[c'] + nL[c'+1])
+__global__ void __launch_bounds__(1024) k_pic_scan(const int *__restrict__ counts, int L, long long *__restrict__ new_start)
+{
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    const int per = (L + 1023) / 1024;
+    const int c0 = t * per, c1 = min(L, c0 + per);
+    long long sum = 0;
+    for (int c = c0; c < c1; ++c)
+        sum += (c > 0 ? counts[3 * (c - 1) + 2] : 0) + counts[3 * c + 1] + (c + 1 < L ? counts[3 * (c + 1)] : 0);
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {     // inclusive Hillis-Steele scan of the 1024 partials
+        long long v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long run = part[t] - sum;                 // exclusive prefix of this thread's chunk
+    for (int c = c0; c < c1; ++c) {
+        new_start[c] = run;
+        run += (c > 0 ? counts[3 * (c - 1) + 2] : 0) + counts[3 * c + 1] + (c + 1 < L ? counts[3 * (c + 1)] : 0);
+    }
+    if (t == 1023) new_start[L] = part[1023];
+}
+
+__global__ void __launch_bounds__(PIC_THREADS) k_pic_move(PfPic p, const long long *__restrict__ start, const int *__restrict__ counts,
+                                                          const long long *__restrict__ new_start)
+{
+    const int c = (blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= p.L) return;
+    const long long a = start[c], b = start[c + 1];
+    if (a == b) return;
+    const unsigned lt = (1u << lane) - 1u;
+    // first slot of each group in the new order
+    long long posL = 0, posS, posR = 0;
+    if (c > 0) posL = new_start[c - 1] + (c > 1 ? counts[3 * (c - 2) + 2] : 0) + counts[3 * (c - 1) + 1];
+    posS = new_start[c] + (c > 0 ? counts[3 * (c - 1) + 2] : 0);
+    if (c + 1 < p.L) posR = new_start[c + 1];
+    for (long long i0 = a; i0 < b; i0 += 32) {
+        const long long i = i0 + lane;
+        int d = 2;
+        Pushed r;
+        double w = 0.0;
+        if (i < b) {
+            r = pic_push_one(p, p.z[i], p.ux[i], p.uz[i]);
+            w = p.w[i];
+            d = max(-1, min(1, r.cell - c));
+        }
+        const unsigned bl = __ballot_sync(0xffffffffu, d == -1);
+        const unsigned bs = __ballot_sync(0xffffffffu, d == 0);
+        const unsigned br = __ballot_sync(0xffffffffu, d == 1);
+        if (i < b) {
+            long long dst = (d == -1) ? posL + __popc(bl & lt) : (d == 0) ? posS + __popc(bs & lt) : posR + __popc(br & lt);
+            p.z_alt[dst] = r.z;
+            p.ux_alt[dst] = r.ux;
+            p.uz_alt[dst] = r.uz;
+            p.w_alt[dst] = w;
+            p.cell_alt[dst] = c + d;
+        }
+        posL += __popc(bl);
+        posS += __popc(bs);
+        posR += __popc(br);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ sort
@@ -104,7 +233,7 @@ static int key_bits(int L)
 }
 
 struct PicPlan {
-    size_t off_idx_in, off_idx_out, off_cub, off_acc, cub_bytes, total;
+    size_t off_idx_in, off_idx_out, off_cub, off_acc, off_start, off_new_start, off_counts, off_err, cub_bytes, total;
 };
 
 static PicPlan pic_plan(const PfPic *p)
@@ -118,7 +247,11 @@ static PicPlan pic_plan(const PfPic *p)
     pl.off_idx_out = al256(sizeof(int) * n);
     pl.off_cub = pl.off_idx_out + al256(sizeof(int) * n);
     pl.off_acc = pl.off_cub + al256(pl.cub_bytes);
-    pl.total = pl.off_acc + al256(sizeof(double) * 2 * (size_t)p->L);
+    pl.off_start = pl.off_acc + al256(sizeof(double) * 2 * (size_t)p->L);
+    pl.off_new_start = pl.off_start + al256(sizeof(long long) * ((size_t)p->L + 1));
+    pl.off_counts = pl.off_new_start + al256(sizeof(long long) * ((size_t)p->L + 1));
+    pl.off_err = pl.off_counts + al256(sizeof(int) * 3 * (size_t)p->L);
+    pl.total = pl.off_err + 256;
     return pl;
 }
 
@@ -210,6 +343,44 @@ int pf_pic_push(const PfPic *p, void *stream)
     k_pic_push<<<blocks, PIC_THREADS, 0, (cudaStream_t)stream>>>(*p);
     PF_LAUNCH_CHECK("k_pic_push");
     return PF_OK;
+}
+
+int pf_pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream)
+{
+    int rc = validate_pic(p);
+    if (rc) return rc;
+    if (!p->Ex || !p->Hy) return set_err(PF_E_ARG, "pf_pic_push_sorted: field arrays missing");
+    if (p->n == 0) return PF_OK;
+    if (!p->z_alt || !p->ux_alt || !p->uz_alt || !p->w_alt || !p->cell_alt)
+        return set_err(PF_E_ARG, "pf_pic_push_sorted: alternate (output) arrays missing");
+    PicPlan pl = pic_plan(p);
+    if (!scratch || scratch_bytes < pl.total) return set_err(PF_E_SCRATCH, "pf_pic_push_sorted needs %zu bytes of scratch", pl.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *s = (char *)scratch;
+    long long *start = (long long *)(s + pl.off_start), *new_start = (long long *)(s + pl.off_new_start);
+    int *counts = (int *)(s + pl.off_counts), *err = (int *)(s + pl.off_err);
+    PF_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    k_pic_cell_start<<<(p->L + 1 + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(p->cell, p->n, p->L, start);
+    PF_LAUNCH_CHECK("k_pic_cell_start");
+    unsigned wblocks = (unsigned)(((long long)p->L * 32 + PIC_THREADS - 1) / PIC_THREADS);
+    k_pic_count<<<wblocks, PIC_THREADS, 0, st>>>(*p, start, counts, err);
+    PF_LAUNCH_CHECK("k_pic_count");
+    k_pic_scan<<<1, 1024, 0, st>>>(counts, p->L, new_start);
+    PF_LAUNCH_CHECK("k_pic_scan");
+    k_pic_move<<<wblocks, PIC_THREADS, 0, st>>>(*p, start, counts, new_start);
+    PF_LAUNCH_CHECK("k_pic_move");
+    return PF_OK;
+}
+
+int pf_pic_check(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream)
+{
+    // 1 if the last pf_pic_push_sorted saw a particle cross more than one cell (CFL violation), else 0
+    PicPlan pl = pic_plan(p);
+    if (!scratch || scratch_bytes < pl.total) return set_err(PF_E_SCRATCH, "pf_pic_check: scratch too small");
+    int h = 0;
+    PF_CUDA(cudaMemcpyAsync(&h, (char *)scratch + pl.off_err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return h;
 }
 
 int pf_pic_sort(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream)
