@@ -171,13 +171,13 @@ class MemberBatch:
         torch = self.torch
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed)
-        self.state_template = torch.empty(self.n_state, dtype=torch.float64, device=self.device)
-        for i, m in enumerate(self.members):
+        self.state_template = torch.rand(self.n_state, dtype=torch.float64, device=self.device, generator=gen) * 2 - 1
+        scale = torch.tensor([self.STATE_SCALE[name] for name in STATE_NAMES], dtype=torch.float64,
+                             device=self.device)[:, None]
+        for i, m in enumerate(self.members):      # a member's state arrays are one contiguous [8, Lp] block
             Lp = (m.L + 31) // 32 * 32
-            for a, name in enumerate(STATE_NAMES):
-                o = self.off_state[i] + a * Lp
-                r = torch.rand(Lp, dtype=torch.float64, device=self.device, generator=gen) * 2 - 1
-                self.state_template[o:o + Lp] = r * self.STATE_SCALE[name]
+            o = self.off_state[i]
+            self.state_template[o:o + len(STATE_NAMES) * Lp].view(len(STATE_NAMES), Lp).mul_(scale)
         return self.state_template
 
     def run(self, do_pol, n0=0, k_block=0):

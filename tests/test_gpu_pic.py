@@ -125,7 +125,9 @@ def test_coupled_step_feeds_the_jx_slot(pic):
     assert np.max(np.abs(Jo)) > 0
     assert np.array_equal(out["Ex"], pa.Ex) and np.array_equal(out["Hy"], pa.Hy)
     zo, uxo, uzo, co = po.push(ps0[0], ps0[1], ps0[2], pa.Ex, pa.Hy, dz=P.dz, dt=P.delT, q_over_m=QM, c=C0, mu0=MU0)
+    zo, uxo, uzo, wo, co = po.sort_by_cell(zo, uxo, uzo, ps0[3], co)      # the coupled step keeps the set cell-sorted
     h = ps.host()
+    assert np.array_equal(h["cell"], co)
     assert rel(h["z"], zo) <= 1e-12 and rel(h["ux"], uxo) <= 1e-12
 
 
