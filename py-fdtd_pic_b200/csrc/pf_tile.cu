@@ -71,17 +71,46 @@ struct TileSmem {
     static constexpr size_t bytes = sizeof(double) * ((size_t)N_ARR * TILE_CELLS + 2 * NT + 2 * TILE_KMAX);
 };
 
+// Shared memory is addressed as pf_smem[offset + index] with plain integer offsets: going through
+// generic double* members made the compiler re-derive the shared window (S2R SR_CgaCtaId + LEA) after
+// every barrier, on the critical path (ncu r1_final: ~10 % of the hot loop's stall samples).
+extern __shared__ double pf_smem[];
+
+// One 8-byte shared-memory slot addressed in the shared state space (ld.shared / st.shared with a
+// 32-bit address): reads and writes look like array accesses at the call sites.
+struct SmemSlot {
+    unsigned addr;
+    __device__ __forceinline__ operator double() const
+    {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void operator=(double v) const
+    {
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+    }
+};
+struct SmemArray {
+    unsigned base;   // byte address in the shared window
+    __device__ __forceinline__ SmemSlot operator[](int i) const { return SmemSlot{base + 8u * (unsigned)i}; }
+};
+
 struct TileShared {
     // per-cell coefficient slots, [j][thread] order (each thread touches only its own slots)
-    double *be, *ce, *cm;      // CPML recursive-convolution profiles (0 outside the CPML)
-    double *cEu, *cHu;         // update coefficient of the cell, 0 where the field is never updated
-    double *cb, *c2u;          // CPML field-correction coefficients, 0 outside / at the quirk cell
-    double *edgeH, *edgeE, *srcE, *srcH;
+    SmemArray be, ce, cm;      // CPML recursive-convolution profiles (0 outside the CPML)
+    SmemArray cEu, cHu;        // update coefficient of the cell, 0 where the field is never updated
+    SmemArray cb, c2u;         // CPML field-correction coefficients, 0 outside / at the quirk cell
+    SmemArray edgeH, edgeE, srcE, srcH;
 };
 
 // CTA-wide barrier usable from warp-uniform divergent code: every warp executes exactly two of
 // these per time step (plus one before the loop), whichever body it runs.
+#ifdef PF_EXPERIMENT_NO_SYNC   // timing experiment only (results are wrong): upper bound of a barrier-free design
+__device__ __forceinline__ void cta_sync() { __syncwarp(); }
+#else
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+#endif
 
 // per-thread description of its C cells
 struct CellMasks {
@@ -171,7 +200,9 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
 #pragma unroll
         for (int j = 0; j < C; ++j) { acub[j] = nl.a[j]; ex[j] = nl.e[j]; }
     }
-    if (MODE == PF_LORENTZ && HAS_MAT && !div_const_in_range(divkey)) {
+    // warp-uniform test: a per-lane branch here opens a divergent region, which costs the uniform
+    // registers holding the shared-memory window (re-read with S2UR after every step)
+    if (MODE == PF_LORENTZ && HAS_MAT && __any_sync(0xffffffffu, !div_const_in_range(divkey))) {
         // some cell's (Dx - P) was zero, in the denormal range or non-finite: redo those divisions
         // exactly (rare once the wave has arrived; integer tests only for the zero case)
 #pragma unroll
@@ -393,19 +424,22 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
 {
     constexpr int NT = TILE_CELLS / C;
     constexpr unsigned ALL = (1u << C) - 1u;
-    extern __shared__ double smem[];
     TileShared S;
-    S.be = smem;
-    S.ce = S.be + TILE_CELLS;
-    S.cm = S.ce + TILE_CELLS;
-    S.cEu = S.cm + TILE_CELLS;
-    S.cHu = S.cEu + TILE_CELLS;
-    S.cb = S.cHu + TILE_CELLS;
-    S.c2u = S.cb + TILE_CELLS;
-    S.edgeH = S.c2u + TILE_CELLS;
-    S.edgeE = S.edgeH + NT;
-    S.srcE = S.edgeE + NT;
-    S.srcH = S.srcE + TILE_KMAX;
+    unsigned sbase = (unsigned)__cvta_generic_to_shared(pf_smem);
+    // keep the window address in an ordinary (per-thread) register: as a uniform value it is
+    // re-derived from SR_CgaCtaId after every potentially divergent region of the time loop
+    asm volatile("xor.b32 %0, %0, %1;" : "+r"(sbase) : "r"(threadIdx.x & 0u));
+    S.be.base = sbase;
+    S.ce.base = S.be.base + 8u * TILE_CELLS;
+    S.cm.base = S.ce.base + 8u * TILE_CELLS;
+    S.cEu.base = S.cm.base + 8u * TILE_CELLS;
+    S.cHu.base = S.cEu.base + 8u * TILE_CELLS;
+    S.cb.base = S.cHu.base + 8u * TILE_CELLS;
+    S.c2u.base = S.cb.base + 8u * TILE_CELLS;
+    S.edgeH.base = S.c2u.base + 8u * TILE_CELLS;
+    S.edgeE.base = S.edgeH.base + 8u * NT;
+    S.srcE.base = S.edgeE.base + 8u * NT;
+    S.srcH.base = S.srcE.base + 8u * TILE_KMAX;
 
     const TileDesc td = tiles[blockIdx.x];
     const TileGrid &TG = grids[td.grid];
