@@ -229,12 +229,13 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
     }
 
     // ===== H half-step: TF/SF correction, ADE_HyUpdate, CPML_Psi_m =====
-    double er = (tid < NT - 1) ? S.edgeE[tid + 1] : 0.0;
+    // the neighbour's Ex is requested first and consumed last (cell C-1), behind the cells that only
+    // need the thread's own Ex, so the shared-memory latency is covered
+    const double exr = (tid < NT - 1) ? S.edgeE[tid + 1] : 0.0;
 #pragma unroll
-    for (int j = C - 1; j >= 0; --j) {
+    for (int j = 0; j < C; ++j) {
         double h = hy[j];
-        const double dE = A::sub(er, ex[j]);
-        er = ex[j];
+        const double dE = A::sub((j == C - 1) ? exr : ex[(j + 1) % C], ex[j]);
         h = A::add(h, A::mul(dE, GEN ? S.cHu[j * NT + tid] : K.cHs));
         if (HAS_PML) {
             const double b = GEN ? S.be[j * NT + tid] : rbe[j];

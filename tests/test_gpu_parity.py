@@ -310,3 +310,114 @@ def test_cubic_solver_mirror_all_roots(pk):
     one = CES.solve(1.0, -6.0, 11.0, -6.0)        # (x-1)(x-2)(x-3)
     assert np.allclose(np.sort(np.real(one)), [1.0, 2.0, 3.0], atol=1e-12)
     assert CES.solve(CES.CubicSolver(0.0, 0.0, 4.0, -2.0))[0] == 0.5
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def _oracle_pass(spec, V, P, Exs, Hys, probes, mode, do_pol, nsteps, cpml_m=1, cpml_p=1, n0=0, state=None):
+    c = oracle_case(spec)
+    pa = fo.PassArrays(c, V.plasmaFreqE, Exs, Hys, probes, False)
+    pa.g.cpml_m, pa.g.cpml_p, pa.g.tfsf = cpml_m, cpml_p, int(P.TFSF)
+    if state is not None:
+        for k, v in state.items():
+            getattr(pa, k)[:] = v
+    fo.lib().orc_run(ctypes.byref(pa.g), fo.MODE_ID[mode], int(do_pol), n0, nsteps, c.T)
+    return pa
+
+
+@pytest.mark.parametrize("engine", ["tile", "ops"])
+@pytest.mark.parametrize("flags", [(True, False), (False, True), (False, False)])
+def test_one_sided_and_no_cpml(pk, engine, flags):
+    """P.CPMLXm / P.CPMLXp switched off individually (BaseFDTD11.py:368,372,385,389)."""
+    spec = dict(mode="lorentz", freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000)
+    V, P, C_V, C_P = pk.build_objects(spec)
+    P.CPMLXm, P.CPMLXp = flags
+    for _ in range(2):
+        C_V, Exs, Hys = pk.SE.prepare_pass(V, P, C_V, C_P, lorentz=True)
+    pk.SE.ENGINE = engine
+    try:
+        traces = pk.SE.run_time_loop(V, P, C_V, C_P, "lorentz", True, Exs, Hys, [P.x2Loc])
+    finally:
+        pk.SE.ENGINE = "auto"
+    if any(flags):
+        pa = _oracle_pass(spec, V, P, Exs, Hys, [P.x2Loc], "lorentz", True, P.timeSteps, int(flags[0]), int(flags[1]))
+        # with one side off the reference still builds both profiles; only the psi updates are skipped
+        assert np.array_equal(V.Ex, pa.Ex) and np.array_equal(V.Hy, pa.Hy) and np.array_equal(traces[0], pa.probe_out[0])
+        assert np.array_equal(C_V.psi_Hy, pa.psiH)
+    else:
+        assert np.all(np.isfinite(V.Ex)) and not np.any(C_V.psi_Ex) and not np.any(C_V.psi_Hy)
+
+
+def test_run_in_two_halves_equals_one_run(pk):
+    """Continuation: steps [0, n) then [n, T) from the saved state == one run of T steps."""
+    spec = dict(mode="lorentz", freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000)
+    V, P, C_V, C_P = pk.build_objects(spec)
+    for _ in range(2):
+        C_V, Exs, Hys = pk.SE.prepare_pass(V, P, C_V, C_P, lorentz=True)
+    n_half = 333
+    t1 = pk.SE.run_time_loop(V, P, C_V, C_P, "lorentz", True, Exs, Hys, [P.x2Loc], n0=0, nsteps=n_half)
+    t2 = pk.SE.run_time_loop(V, P, C_V, C_P, "lorentz", True, Exs, Hys, [P.x2Loc], n0=n_half, nsteps=P.timeSteps - n_half)
+    pa = _oracle_pass(spec, V, P, Exs, Hys, [P.x2Loc], "lorentz", True, P.timeSteps)
+    assert np.array_equal(V.Ex, pa.Ex) and np.array_equal(V.polarisationCurr, pa.P) and np.array_equal(V.tempVarPol, pa.Pprev)
+    assert np.array_equal(t1[0][:n_half], pa.probe_out[0][:n_half]) and np.array_equal(t2[0][n_half:], pa.probe_out[0][n_half:])
+
+
+def test_attenuation_probes(pk):
+    """P.atten: probes every 25 cells from the slab front edge (Solver_Engine.py:31-38), windowed like x1ColAf."""
+    spec = dict(mode="lorentz", freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000)
+    V, P, C_V, C_P = pk.build_objects(spec)
+    P.atten = True
+    V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    cells = list(pk.SE.atten_probe_cells(V, P))
+    assert len(cells) == 10 and cells[1] - cells[0] == 25
+    c = oracle_case(spec)
+    pa = fo.PassArrays(c, V.plasmaFreqE, Exs, Hys, [c.x2Loc] + cells, False)
+    fo.lib().orc_run(ctypes.byref(pa.g), 1, 1, 0, c.T, c.T)
+    n = np.arange(c.T)
+    for k in range(10):
+        assert np.array_equal(V.x1Atten[k], np.where(n >= int(c.T * 0.05), pa.probe_out[1 + k], 0.0))
+    # results(attenRead=True) needs a spectral peak in every trace; like the reference (which exits) the
+    # mirror raises when a deep probe has seen no wave yet in this short run
+    if np.all([np.argmax(np.abs(np.fft.fft(r))) != 0 for r in V.x1Atten]):
+        att = pk.MC.results(V, P, C_V, C_P, None, attenRead=True)
+        assert att.shape == (10,) and np.all(np.isfinite(att))
+
+
+def test_maximum_reference_size(pk):
+    """The largest grid / step count the reference's guards admit (Nz = 25000, BaseFDTD11.py:48; timeSteps just
+    under 2**15, Environment_Setup.py:123) through the tile engine, one free-space pass, against the oracle."""
+    from pyfdtd_b200 import MasterController as MC, Environment_Setup as envDef
+    tup = envDef.envSetup(9e9, 0.7, 7000, 8000)
+    P = MC.Params(*tup, False, 0.7, 9e9, 20)
+    P.Nz, P.timeSteps = 25000, 2 ** 15 - 1
+    P.materialRearEdge = P.Nz - 1
+    P.TFSF, P.SineCont, P.Periods, P.FreeSpace, P.epsRe = True, True, 1000, True, 4.0
+    V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
+    C_P = MC.CPML_Params(P.dz)
+    C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
+    C_V, Exs, Hys = pk.SE.prepare_pass(V, P, C_V, C_P, lorentz=False)
+    traces = pk.SE.run_time_loop(V, P, C_V, C_P, "free", False, Exs, Hys, [P.x1Loc, P.x2Loc])
+    assert pk.SE.LAST_RUN_INFO["engine"] == "tile"
+    c = fo.Case(mode="free", freq=9e9, Nz=P.Nz, T=P.timeSteps, pw=P.pmlWidth, mf=P.materialFrontEdge, mr=P.materialRearEdge,
+                nzsrc=P.nzsrc, x1Loc=P.x1Loc, x2Loc=P.x2Loc, dz=P.dz, dt=P.delT, courantNo=P.courantNo, period=P.period,
+                source="sine", tfsf=True, Periods=1000.0, epsRe=4.0)
+    pa = fo.PassArrays(c, 0.0, Exs, Hys, [P.x1Loc, P.x2Loc], False)
+    fo.lib().orc_run(ctypes.byref(pa.g), 0, 0, 0, c.T, c.T)
+    assert np.array_equal(V.Ex, pa.Ex) and np.array_equal(V.Hy, pa.Hy) and np.array_equal(traces, pa.probe_out)
+    P.Nz = 25001
+    with pytest.raises(ValueError):
+        pk.B.FieldInit(V, P)
+
+
+def test_bad_arguments_are_reported(pk):
+    lib = pk.nat.lib()
+    assert lib.pf_run_pass(None, 1, 0, 0, 1, 0, None, 0, 0, None, 0, None) == -1
+    assert b"bad arguments" in lib.pf_last_error()
+    members, _ = _lorentz_members(pk, [9e9], nsteps=4)
+    batch = pk.sweep.MemberBatch(members, "lorentz")
+    assert lib.pf_run_batch(batch.grids, 1, 7, 0, 0, batch.nsteps, 0, batch.scratch.data_ptr(), batch.scratch_bytes, None) == -1
+    assert lib.pf_run_batch(batch.grids, 1, 1, 0, 0, batch.nsteps, 0, batch.scratch.data_ptr(), 16, None) == -4   # scratch too small
+    g = batch.grids[0]
+    flags = g.flags
+    g.flags = flags & ~pk.nat.PF_F_CANONICAL
+    assert lib.pf_run_batch(batch.grids, 1, 1, 0, 0, batch.nsteps, 0, batch.scratch.data_ptr(), batch.scratch_bytes, None) == -3
+    g.flags = flags
