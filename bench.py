@@ -464,8 +464,11 @@ def main():
             "frac": dp_per_launch / (avg_kernel_ms * 1e-3) / fp64_peak, "peak_source": fp64_src,
             "note": "algorithmic fp64 instructions of the reference arithmetic (exact mode, no FMA contraction) / kernel time; "
                     "this, not HBM, is the pipe that bounds the temporally blocked kernel"}
+    # DRAM bytes of one launch of this kernel from the committed ncu --set full capture of the DEFAULT workload
+    # (profiles/r1_final_k_tile_ncu.txt: dram__bytes_read.sum 537.6 MB + dram__bytes_write.sum 472.0 MB)
+    traffic = 537.582592e6 + 471.976704e6 if (args.members == 1024 and k_block == 64 and args.n_freq == 64) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_tile<PF_LORENTZ,POL,8,Exact>", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "k_tile<PF_LORENTZ,POL,8,Exact>", "peak_source": peak_src,
                 "kernel_ms_avg": avg_kernel_ms, "kernel_launches_timed": kn.value,
                 "kernel_share_of_step": kms.value / ms_total if ms_total else None,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "temporal_block_k": k_block,
