@@ -29,6 +29,7 @@
 // C2 == c2_pml on the CPML correction ranges, both 0 at the single cell Lg-pw
 // (the reference's exclusive range end, BaseFDTD11.py:312,326).
 #include <algorithm>
+#include <cstring>
 #include <vector>
 #include "pf_common.cuh"
 
@@ -661,12 +662,29 @@ static int launch_tile_mode(int mode, int do_pol, bool fma, int n_tiles, const T
     return set_err(PF_E_ARG, "bad mode %d", mode);
 }
 
+// Tile tables of the last pf_run_block call, kept on the device (in the caller's scratch) so that the
+// steady state of a long run -- the same two buffer sets, alternating -- costs no host-side rebuild and no
+// H2D copy per block: the tables hold both buffer sets and the kernel's `src` argument selects the
+// direction.
+struct BlockCache {
+    void *scratch = nullptr;
+    int n = 0, mode = -1, halo = 0, n_tiles = 0;
+    std::vector<PfGrid> a, b;   // descriptors the tables were built from (buffer 0 / buffer 1)
+};
+static BlockCache g_block_cache;
+
+static bool same_grids(const std::vector<PfGrid> &v, const PfGrid *g, int n)
+{
+    return (int)v.size() == n && memcmp(v.data(), g, sizeof(PfGrid) * (size_t)n) == 0;
+}
+
 // Runs the tile engine over n grids.  snap_* only with n == 1.
 int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int *nsteps, int k_block,
              double *snap_out, int snap_interval, int snap_rows, void *scratch, size_t scratch_bytes,
              cudaStream_t st)
 {
     if (n <= 0) return PF_OK;
+    g_block_cache.scratch = nullptr;   // this call writes its own tables; never trust a stale block cache
     if (k_block <= 0) k_block = TILE_KDEF;
     if (k_block > TILE_KMAX) k_block = TILE_KMAX;
     for (int m = 0; m < n; ++m) {
@@ -767,10 +785,22 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
     if (n <= 0 || ks <= 0) return PF_OK;
     if (halo < ks) halo = ks;
     if (halo > TILE_KMAX) return set_err(PF_E_ARG, "pf_run_block: ksteps/halo %d exceeds the tile engine limit %d", halo, TILE_KMAX);
+    BlockCache &bc = g_block_cache;
+    const size_t off_tiles = align_up(sizeof(TileGrid) * (size_t)n, 256);
+    TileGrid *dg = (TileGrid *)scratch;
+    TileDesc *dt = (TileDesc *)((char *)scratch + off_tiles);
+    bool fma = false;
+    for (int m = 0; m < n; ++m) fma = fma || (src[m].flags & PF_F_FMA);
+    if (bc.scratch == scratch && bc.n == n && bc.mode == mode && bc.halo == halo) {
+        if (same_grids(bc.a, src, n) && same_grids(bc.b, dst, n))
+            return launch_tile_mode(mode, do_pol, fma, bc.n_tiles, dg, dt, 0, 0, n0, ks, halo, st);
+        if (same_grids(bc.b, src, n) && same_grids(bc.a, dst, n))
+            return launch_tile_mode(mode, do_pol, fma, bc.n_tiles, dg, dt, 1, 0, n0, ks, halo, st);
+    }
+    bc.scratch = nullptr;
     const int W = TILE_CELLS - 2 * halo;
     std::vector<TileGrid> hg(n);
     std::vector<TileDesc> ht;
-    bool fma = false;
     for (int m = 0; m < n; ++m) {
         int rc = tile_supported(src[m], mode);
         if (rc) return rc;
@@ -784,19 +814,19 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
             t.buf[0][a] = a0[a];
             t.buf[1][a] = a1[a];
         }
-        t.nsteps = ks;
+        t.nsteps = 1 << 30;   // the step count of a block launch is the kernel's ksteps argument
         t.pad = 0;
-        fma = fma || (src[m].flags & PF_F_FMA);
         int ntile = (src[m].L + W - 1) / W;
         for (int i = 0; i < ntile; ++i) ht.push_back(TileDesc{m, i * W - halo});
     }
-    size_t off_tiles = align_up(sizeof(TileGrid) * (size_t)n, 256);
     size_t need = off_tiles + align_up(sizeof(TileDesc) * ht.size(), 256);
     if (!scratch || scratch_bytes < need) return set_err(PF_E_SCRATCH, "pf_run_block needs %zu bytes of scratch, got %zu", need, scratch_bytes);
-    TileGrid *dg = (TileGrid *)scratch;
-    TileDesc *dt = (TileDesc *)((char *)scratch + off_tiles);
     PF_CUDA(cudaMemcpyAsync(dg, hg.data(), sizeof(TileGrid) * n, cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaMemcpyAsync(dt, ht.data(), sizeof(TileDesc) * ht.size(), cudaMemcpyHostToDevice, st));
+    bc.scratch = scratch;
+    bc.n = n; bc.mode = mode; bc.halo = halo; bc.n_tiles = (int)ht.size();
+    bc.a.assign(src, src + n);
+    bc.b.assign(dst, dst + n);
     return launch_tile_mode(mode, do_pol, fma, (int)ht.size(), dg, dt, 0, 0, n0, ks, halo, st);
 }
 

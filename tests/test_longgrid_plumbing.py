@@ -32,6 +32,24 @@ def test_plan_pieces_covers_grid(Lg, pw, world, k):
     assert all(p["ghost_l"] == k for p in pieces[1:]) and all(p["ghost_r"] == k for p in pieces[:-1])
 
 
+def test_rank_cuts_balance_work_not_cells():
+    Lg, pw, world = 2_000_000, 2394, 4
+    mf, mr = int(0.3 * Lg), Lg - 2
+    cuts = lgm.balanced_rank_cuts(Lg, pw, world, mf, mr)
+    assert cuts[0] == 0 and cuts[-1] == Lg and all(b > a for a, b in zip(cuts[:-1], cuts[1:]))
+
+    def work(a, b):
+        z = np.arange(a, b)
+        w = np.where((z >= mf) & (z < mr), lgm.CELL_COST["slab"], lgm.CELL_COST["vacuum"])
+        w = w + np.where((z < pw) | (z >= Lg - pw), lgm.CELL_COST["cpml"], 0.0)
+        return float(w.sum())
+    loads = [work(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert max(loads) / min(loads) < 1.01
+    assert cuts[1] > Lg // world          # the vacuum-side rank takes more cells
+    pieces = lgm.plan_pieces(Lg, pw, world, 64, mf=mf, mr=mr)
+    assert [p["lo"] for p in pieces if p["ghost_l"] == 64 and p["rank"] != pieces[p["index"] - 1]["rank"]] == cuts[1:-1]
+
+
 def test_exchange_schedule_is_symmetric():
     pieces = lgm.plan_pieces(200_000, 2394, 2, 64, max_piece=40_000)
     s0, s1 = lgm.exchange_schedule(pieces, 0), lgm.exchange_schedule(pieces, 1)

@@ -28,6 +28,21 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 grid, info = longgrid.lorentz_long_grid(a.cells, T=a.steps, k=a.k, rank=rank, world_size=world)
 grid.run(a.k, do_pol=True)           # warm-up block
+if os.environ.get("PF_LONGGRID_BREAKDOWN"):
+    import ctypes
+    from pyfdtd_b200 import _native as nat
+    for blk in range(3):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        if len(grid.pieces) > 1:
+            grid.exchange()
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        nat.check(nat.lib().pf_run_block(grid.grids[grid.cur], grid.grids[grid.cur ^ 1], len(grid.mine), grid.mode_id, 1,
+                                         grid.n_done, a.k, a.k, grid.scratch.data_ptr(), grid.scratch_bytes,
+                                         nat.current_stream_ptr()), "pf_run_block")
+        t2 = time.perf_counter()
+        torch.cuda.synchronize(); t3 = time.perf_counter()
+        grid.cur ^= 1; grid.n_done += a.k
+        print(f"rank {rank} block {blk}: exchange {1e3*(t1-t0):.2f} ms, launch call {1e3*(t2-t1):.2f} ms, kernel {1e3*(t3-t2):.2f} ms", flush=True)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
