@@ -421,3 +421,28 @@ def test_bad_arguments_are_reported(pk):
     g.flags = flags & ~pk.nat.PF_F_CANONICAL
     assert lib.pf_run_batch(batch.grids, 1, 1, 0, 0, batch.nsteps, 0, batch.scratch.data_ptr(), batch.scratch_bytes, None) == -3
     g.flags = flags
+
+
+def test_broadband_reflection_spectrum_matches_fresnel(pk):
+    """BASELINE config 2: one broadband (Gaussian) pulse on the Lorentz half-space at the default geometry;
+    |FFT(reflected)| / |FFT(incident)| per bin over 6-10 GHz against the analytic Fresnel coefficient
+    (BaseFDTD11.AnalyticalReflectionE :882-923) -- the reference's own physics check --
+    and against the oracle's spectrum."""
+    from pyfdtd_b200 import TransformHandler as TH
+    spec = dict(mode="lorentz", freq=9e9, dom=0.7, win=[7000, 8000], source="gauss", periods=1000)
+    V, P, C_V, C_P = pk.build_objects(spec)
+    V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    f, R = TH.reflection_spectrum(V.x1ColBe, V.x1ColAf, P.delT, 6e9, 10e9)
+    assert len(f) > 20
+    f0 = P.freq_in
+    analytic = []
+    for ff in f:
+        P.freq_in = ff
+        analytic.append(pk.B.AnalyticalReflectionE(V, P))
+    P.freq_in = f0
+    analytic = np.array(analytic)
+    assert np.max(np.abs(R - analytic) / analytic) < 0.05
+    assert 0.22 < R.min() and R.max() < 0.28          # the reference's published figure: 0.24-0.27 over 6-10 GHz
+    want = fo.run_case(oracle_case(spec))
+    fo_f, fo_R = TH.reflection_spectrum(want["x1ColBe"], want["x1ColAf"], P.delT, 6e9, 10e9)
+    np.testing.assert_allclose(R, fo_R, rtol=1e-10)
