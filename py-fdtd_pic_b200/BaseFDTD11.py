@@ -123,13 +123,13 @@ def CPML_ScalingCalc(V, P, C_V, C_P):
     """BaseFDTD11.py:222-272 -- polynomial grading of sigma/kappa/alpha, mirrored on the right.
     The Hy profiles alias the Ex profiles, as in the reference."""
     pw, L = int(P.pmlWidth), len(V.Ex)
-    kap, sig, alp = np.empty(pw), np.empty(pw), np.empty(pw)
-    for n in range(pw):
-        depth = (pw - n) / pw
-        graded = math.pow(depth, C_P.r_scale)
-        kap[n] = 1 + (C_P.kappaMax - 1) * graded
-        sig[n] = C_P.sigmaOpt * graded
-        alp[n] = C_P.alphaMax * math.pow((n + 1) / pw, C_P.r_a_scale)
+    n = np.arange(pw)
+    depth = (pw - n) / pw
+    graded = np.fromiter((math.pow(d, C_P.r_scale) for d in depth), dtype=np.float64, count=pw)       # libm pow, as numba calls it
+    ramp = np.fromiter((math.pow(d, C_P.r_a_scale) for d in (n + 1) / pw), dtype=np.float64, count=pw)
+    kap = 1 + (C_P.kappaMax - 1) * graded
+    sig = C_P.sigmaOpt * graded
+    alp = C_P.alphaMax * ramp
     for dst, prof in ((C_V.kappa_Ex, kap), (C_V.sigma_Ex, sig), (C_V.alpha_Ex, alp)):
         dst[:pw] = prof
         dst[L - pw:L] = prof[::-1]
@@ -145,16 +145,21 @@ def _cpml_cells(P, L):
 
 
 def _recursive_conv_coefs(P, sigma, kappa, alpha, cells, per_dz):
+    """b = exp(-(sigma dt/(kappa eps0) + alpha dt/eps0)), c = (b-1) sigma / (sigma kappa + alpha kappa^2 [* dz]) on
+    the CPML cells.  Everything but the exponential is elementwise IEEE arithmetic (NumPy evaluates it exactly
+    like the reference's compiled loop); the exponential goes through libm one value at a time, because that
+    is what the numba-compiled reference calls and NumPy's SIMD exp differs from it in the last bit."""
+    cells = np.asarray(cells, dtype=np.int64)
+    s, k, a = sigma[cells], kappa[cells], alpha[cells]
+    arg = -((s * P.delT / (k * P.permit_0)) + ((a * P.delT) / P.permit_0))
+    bn = np.fromiter((math.exp(v) for v in arg), dtype=np.float64, count=len(arg))
+    den = s * k + a * k * k
+    if per_dz:
+        den = den * P.dz
     b = np.zeros(len(sigma))
     c = np.zeros(len(sigma))
-    for nz in cells:
-        s, k, a = sigma[nz], kappa[nz], alpha[nz]
-        bn = math.exp(-((s * P.delT / (k * P.permit_0)) + ((a * P.delT) / P.permit_0)))
-        den = s * k + a * k * k
-        if per_dz:
-            den = den * P.dz
-        b[nz] = bn
-        c[nz] = (bn - 1) * s / den
+    b[cells] = bn
+    c[cells] = (bn - 1) * s / den
     return b, c
 
 
