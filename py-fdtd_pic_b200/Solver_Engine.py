@@ -187,7 +187,10 @@ def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=F
     if mode == "nl":
         V.Acubic = out["Acubic"]
     if snap_t is not None:
-        hist = snap_t.cpu().numpy()
+        stage = dev.pinned_buffer(rows * L, tag="history").view(rows, L)
+        stage.copy_(snap_t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hist = stage.numpy()
         n_abs = np.arange(rows) * int(P.vidInterval)
         done = (n_abs > 0) & (n_abs >= n0) & (n_abs < n0 + nsteps)
         V.Ex_History[done] = hist[done]

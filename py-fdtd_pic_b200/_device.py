@@ -67,6 +67,20 @@ def probes_ok_for_tiles(probe_idx, cells_per_thread=8):
     return len(p) < 3 or bool(np.all(p[2:] - p[:-2] >= cells_per_thread))
 
 
+_PINNED = {}
+
+
+def pinned_buffer(n_doubles, tag="stage"):
+    """Grow-only cache of pinned host staging buffers (allocating pinned memory costs milliseconds and a
+    single run would otherwise do it every pass).  Callers must finish their copies before the next use."""
+    torch = nat.require_cuda()
+    buf = _PINNED.get(tag)
+    if buf is None or buf.numel() < n_doubles:
+        buf = torch.empty(int(n_doubles * 1.25) + 1024, dtype=torch.float64).pin_memory()
+        _PINNED[tag] = buf
+    return buf[:n_doubles]
+
+
 class DeviceGrid:
     """Device-resident copy of one grid + its PfGrid descriptor."""
 
@@ -96,8 +110,9 @@ class DeviceGrid:
         cur += max(n_probe, 1) * Tp
         self.n_doubles = cur
         self.Tp = Tp
-        self.host = torch.zeros(cur, dtype=torch.float64).pin_memory()
+        self.host = pinned_buffer(cur)
         hv = self.host.numpy()
+        hv[:] = 0.0
         for n in names:
             a = arrays.get(n)
             if a is not None:
@@ -106,6 +121,7 @@ class DeviceGrid:
         hv[self.off["srcH"]: self.off["srcH"] + len(srcH)] = srcH
         self.pool = torch.empty(cur, dtype=torch.float64, device=self.device)
         self.pool.copy_(self.host, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the staging buffer is shared: the copy must have left it
         self.h2d_bytes = cur * 8
         self.probe_idx_t = torch.tensor(list(probe_idx) or [0], dtype=torch.int32, device=self.device)
         self.h2d_bytes += 4 * max(n_probe, 1)
