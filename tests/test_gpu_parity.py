@@ -446,3 +446,50 @@ def test_broadband_reflection_spectrum_matches_fresnel(pk):
     want = fo.run_case(oracle_case(spec))
     fo_f, fo_R = TH.reflection_spectrum(want["x1ColBe"], want["x1ColAf"], P.delT, 6e9, 10e9)
     np.testing.assert_allclose(R, fo_R, rtol=1e-10)
+
+
+def test_full_size_batch_properties(pk):
+    """Size-independent properties on a batch at the benchmark's member geometry (default 0.7 m domain,
+    Nz ~ 13k, CPML 2394, 2048 steps): (i) determinism / placement independence -- members with identical
+    inputs give bit-identical outputs wherever they sit in the batch; (ii) linearity of the Lorentz path --
+    scaling the source scales every field (to rounding); (iii) the first member equals the CPU oracle."""
+    from pyfdtd_b200 import MasterController as MC, Environment_Setup as envDef
+    S = 2048
+    base = {}
+    members, amps = [], [1.0, 3.0, 1.0, 0.5, 3.0, 1.0, 7.25, 1.0]
+    freqs = [9e9, 9e9, 6.5e9, 9e9, 9e9, 6.5e9, 9e9, 9e9]
+    for f, amp in zip(freqs, amps):
+        if f not in base:
+            tup = envDef.envSetup(f, 0.7, 7000, 8000, LorMed=True)
+            P = MC.Params(*tup, False, 0.7, f, 20)
+            P.TFSF, P.SineCont, P.Periods, P.LorentzMed, P.FreeSpace = True, True, 1000, True, False
+            V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
+            C_P = MC.CPML_Params(P.dz)
+            C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
+            for _ in range(2):
+                C_V, Exs, Hys = pk.SE.prepare_pass(V, P, C_V, C_P, lorentz=True)
+            base[f] = (V, P, C_V, C_P, Exs, Hys)
+        V, P, C_V, C_P, Exs, Hys = base[f]
+        members.append(pk.sweep.Member(V, P, C_V, C_P, Exs * amp, Hys * amp, [P.x2Loc, P.x1Loc], nsteps=S))
+    batch = pk.sweep.MemberBatch(members, "lorentz")
+    batch.upload()
+    batch.reset_state()
+    batch.run(do_pol=True)
+    traces = batch.download_probes()
+    ex = [batch.state(i, "Ex") for i in range(len(members))]
+    # (i) identical inputs -> identical bits: members 0, 7 (9 GHz, amp 1) ; 1, 4 (amp 3) ; 2, 5 (6.5 GHz)
+    for a, b in ((0, 7), (1, 4), (2, 5)):
+        assert np.array_equal(ex[a], ex[b]) and np.array_equal(traces[a], traces[b])
+        assert np.array_equal(batch.state(a, "P"), batch.state(b, "P"))
+    assert np.max(np.abs(ex[0])) > 0.1
+    # (ii) linearity
+    scale = np.max(np.abs(ex[0]))
+    for i, amp in ((1, 3.0), (3, 0.5), (6, 7.25)):
+        assert np.max(np.abs(ex[i] - amp * ex[0])) / (amp * scale) < 1e-10
+        assert np.max(np.abs(traces[i] - amp * traces[0])) / (amp * np.max(np.abs(traces[0]))) < 1e-10
+    # (iii) oracle
+    V, P, C_V, C_P, Exs, Hys = base[9e9]
+    c = oracle_case(dict(mode="lorentz", freq=9e9, dom=0.7, win=[7000, 8000], periods=1000))
+    pa = fo.PassArrays(c, V.plasmaFreqE, Exs, Hys, [c.x2Loc, c.x1Loc], False)
+    fo.lib().orc_run(ctypes.byref(pa.g), 1, 1, 0, S, c.T)
+    assert np.array_equal(ex[0], pa.Ex) and np.array_equal(traces[0][:, :S], pa.probe_out[:, :S])
