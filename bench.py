@@ -465,8 +465,8 @@ def main():
             "note": "algorithmic fp64 instructions of the reference arithmetic (exact mode, no FMA contraction) / kernel time; "
                     "this, not HBM, is the pipe that bounds the temporally blocked kernel"}
     # DRAM bytes of one launch of this kernel from the committed ncu --set full capture of the DEFAULT workload
-    # (profiles/r1_final_k_tile_ncu.txt: dram__bytes_read.sum 537.6 MB + dram__bytes_write.sum 472.0 MB)
-    traffic = 537.582592e6 + 471.976704e6 if (args.members == 1024 and k_block == 64 and args.n_freq == 64) else None
+    # (profiles/r1_final_k_tile_ncu.txt: dram__bytes_read.sum 539.5 MB + dram__bytes_write.sum 469.8 MB)
+    traffic = 539.547392e6 + 469.796096e6 if (args.members == 1024 and k_block == 64 and args.n_freq == 64) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_tile<PF_LORENTZ,POL,8,Exact>", "peak_source": peak_src,
                 "kernel_ms_avg": avg_kernel_ms, "kernel_launches_timed": kn.value,
