@@ -214,10 +214,9 @@ def extras(torch, peak_gbs, quick=False):
     del batch
     torch.cuda.empty_cache()
     # --- config 4: PIC push + cell sort + deterministic deposit
-    import pic_oracle as po
     L, dz, dt = 13194, 8.3276e-5, 2.6389e-13
     n = 2_000_000 if quick else 20_000_000
-    z, ux, uz, w, cell = po.make_beam(n, L, dz, seed=1)
+    z, ux, uz, w = pic.make_beam(n, L, dz, seed=1)
     ps = pic.ParticleSet(z, ux, uz, w, L, dz, dt)
     Ex = (torch.rand(L, dtype=torch.float64, device="cuda") * 2 - 1) * 1e5
     Hy = (torch.rand(L, dtype=torch.float64, device="cuda") * 2 - 1) * 3e2

@@ -22,6 +22,19 @@ C0 = 299792458.0
 MU0 = 1.25663706127e-06
 
 
+def make_beam(n, L, dz, *, gamma=1.2, thermal=0.01, c=C0, seed=1234, zlo=0.05, zhi=0.95, weight=1.0e10):
+    """Synthetic electron beam of SURVEY 8(d) config 4: n macro-particles uniform in z over [zlo, zhi] of the grid,
+    drifting along z with Lorentz factor ``gamma`` and a relative thermal spread (normal) in both momenta.
+    Returns host arrays (z, ux, uz, w)."""
+    rng = np.random.default_rng(seed)
+    zmax = (L - 1) * dz
+    z = rng.uniform(zlo * zmax, zhi * zmax, n)
+    u0 = c * np.sqrt(gamma * gamma - 1.0)
+    uz = u0 * (1.0 + thermal * rng.standard_normal(n))
+    ux = u0 * thermal * rng.standard_normal(n)
+    return z, ux, uz, np.full(n, weight)
+
+
 class ParticleSet:
     """Device-resident SoA particle arrays (double-buffered for the sort) + the PfPic descriptor."""
 
