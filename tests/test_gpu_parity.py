@@ -493,3 +493,77 @@ def test_full_size_batch_properties(pk):
     pa = fo.PassArrays(c, V.plasmaFreqE, Exs, Hys, [c.x2Loc, c.x1Loc], False)
     fo.lib().orc_run(ctypes.byref(pa.g), 1, 1, 0, S, c.T)
     assert np.array_equal(ex[0], pa.Ex) and np.array_equal(traces[0][:, :S], pa.probe_out[:, :S])
+
+
+# ------------------------------------------------------------------------------------------------ fuzz
+@pytest.mark.parametrize("seed", range(18))
+def test_random_geometries_match_oracle(pk, seed):
+    """Fuzz at the C-ABI: random grid length, CPML width (down to 0), slab anywhere (incl. not reaching the
+    wall and empty), source cell, TF/SF on/off, one-sided CPML, probes anywhere, random split of the run into
+    two pf_run_pass calls, all three integrators, both engines -- against the CPU oracle on the same arrays.
+    Linear paths bit for bit; cubic path within the 1e-10 bar."""
+    from types import SimpleNamespace
+    from pyfdtd_b200 import _device as dev
+    nat, torch = pk.nat, pk.torch
+    rng = np.random.default_rng(4200 + seed)
+    mode = ["free", "lorentz", "nl"][seed % 3]
+    Nz = int(rng.integers(150, 5000))
+    T = int(rng.integers(40, 300))
+    pw = 0 if seed % 6 == 5 else int(rng.integers(2, max(3, Nz // 6)))
+    nzsrc = int(rng.integers(max(pw, 2) + 2, Nz // 2))
+    mf = int(rng.integers(nzsrc + 3, Nz - 30))
+    mr = Nz - 1 if seed % 4 else int(rng.integers(mf, Nz - 1))
+    tfsf = bool(seed % 2)
+    cp_m, cp_p = [(1, 1), (1, 1), (0, 1), (1, 0)][seed % 4] if pw else (0, 0)
+    base = fo.make_case(mode, 9e9, 0.15, 300, 320, source="sine", tfsf=tfsf, periods=1000.0,
+                        epsRe=2.25 if mode == "free" else 1.0, amplitude=30.0 if mode == "nl" else 1.0)
+    c = fo.Case(**{**base.__dict__, "Nz": Nz, "T": T, "pw": pw, "mf": mf, "mr": mr, "nzsrc": nzsrc,
+                   "x1Loc": mf - 2, "x2Loc": nzsrc - 1, "cpml": dict(cpml_m=bool(cp_m), cpml_p=bool(cp_p))})
+    wp = c.medium["wp"]
+    Exs, Hys = fo.sources(c)
+    probes = sorted(set(int(x) for x in rng.integers(0, Nz + 1, 4)))
+    probes = [p for i, p in enumerate(probes) if i == 0 or p - probes[i - 1] >= 8]
+    pa = fo.PassArrays(c, wp, Exs, Hys, probes, False)
+    pa.g.cpml_m, pa.g.cpml_p = cp_m, cp_p
+    coef = dict(UpExMat=pa.UpExMat, UpHySelf=pa.UpHySelf, UpHyMat=pa.UpHyMat,
+                **{k: pa.coef[k] for k in ("denE", "denH", "beX", "ceX", "Cb", "bmY", "cmY", "C2")})
+    coef = {k: v.copy() for k, v in coef.items()}
+    fo.lib().orc_run(ctypes.byref(pa.g), fo.MODE_ID[mode], 1, 0, T, T)
+
+    L = c.L
+    arrays = dict(coef, **{k: np.zeros(L) for k in dev.STATE})
+    P = SimpleNamespace(pmlWidth=pw, materialFrontEdge=mf, materialRearEdge=mr, CPMLXm=bool(cp_m), CPMLXp=bool(cp_p))
+    scal = dict(pw=pw, mf=mf, mr=mr, nzsrc=nzsrc,
+                **{k: getattr(pa.g, k) for k in ("dt_over_dz", "eps0", "polA", "polB", "polC", "cub_a", "cub_b",
+                                                 "cub_c", "nl_den0", "nl_den1")})
+    flags0 = (nat.PF_F_TFSF if tfsf else 0) | (nat.PF_F_CPML_M if cp_m else 0) | (nat.PF_F_CPML_P if cp_p else 0)
+    canon = dev.canonical_form(P, arrays)
+    assert canon is not None, "oracle-built coefficient arrays must be canonical"
+    split = int(rng.integers(1, T))
+    lib = nat.lib()
+    for engine in (nat.PF_ENGINE_TILE, nat.PF_ENGINE_OPS):
+        s = dict(scal)
+        flags = flags0
+        if engine == nat.PF_ENGINE_TILE:
+            s.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
+            flags |= nat.PF_F_CANONICAL
+        g = dev.DeviceGrid(L=L, T=T, arrays=arrays, scalars=s, srcE=pa.srcE, srcH=pa.srcH, probe_idx=probes, flags=flags)
+        sbytes = lib.pf_run_scratch_bytes(g.ref(), 1, engine)
+        scratch = torch.empty(max(sbytes, 8), dtype=torch.uint8, device="cuda")
+        for first, count in ((0, split), (split, T - split)):
+            nat.check(lib.pf_run_pass(g.ref(), dev.MODE_ID[mode], 1, first, count, engine, None, 0, 0,
+                                      scratch.data_ptr(), sbytes, nat.current_stream_ptr()), "pf_run_pass")
+        out = g.fetch(list(dev.STATE))
+        ctx = (seed, engine, dict(mode=mode, Nz=Nz, T=T, pw=pw, mf=mf, mr=mr, nzsrc=nzsrc, tfsf=tfsf, cp=(cp_m, cp_p),
+                                  split=split, probes=probes))
+        if mode == "nl":
+            for nm in ("Ex", "Hy", "Dx", "psiE", "psiH"):
+                assert rel_err(out[nm], getattr(pa, nm)) <= RTOL, (nm, ctx)
+            assert np.max(np.abs(out["Acubic"] - pa.Acubic)) <= 1e-10 * max(1.0, float(np.max(np.abs(pa.Acubic)))), ctx
+            assert rel_err(out["probe_out"], pa.probe_out) <= RTOL, ctx
+        else:
+            for nm in ("Ex", "Hy", "Dx", "P", "Pprev", "psiE", "psiH"):
+                if mode == "free" and nm in ("Dx", "P", "Pprev"):
+                    continue
+                assert np.array_equal(out[nm], getattr(pa, nm)), (nm, ctx)
+            assert np.array_equal(out["probe_out"], pa.probe_out), ctx
