@@ -28,6 +28,7 @@
 // bmY == beX, no Jx, UpExMat/UpHyMat two-valued (outside/inside the slab), Cb == UpExMat and
 // C2 == c2_pml on the CPML correction ranges, both 0 at the single cell Lg-pw
 // (the reference's exclusive range end, BaseFDTD11.py:312,326).
+#include <type_traits>
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -69,7 +70,7 @@ template <int MODE, int C>
 struct TileSmem {
     static constexpr int NT = TILE_CELLS / C;
     static constexpr int N_ARR = 7;
-    static constexpr size_t bytes = sizeof(double) * ((size_t)N_ARR * TILE_CELLS + 2 * NT + 2 * TILE_KMAX);
+    static constexpr size_t bytes = sizeof(double) * ((size_t)N_ARR * TILE_CELLS + 2 * NT + 2 + 2 * TILE_KMAX);
 };
 
 // Shared memory is addressed as pf_smem[offset + index] with plain integer offsets: going through
@@ -141,7 +142,7 @@ struct StepConsts {
 // One full time step (E half-step, barrier, H half-step) on the thread's C cells.
 //   pc = P^n (current polarisation), pq = P^{n-1}: the new P^{n+1} is written over pq, so the
 //   caller alternates (pc,pq) <-> (pq,pc) instead of shifting the history (no register moves).
-template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML>
+template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, bool SP>
 __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts &K, const CubicConsts *kcp, int tid, int s,
                                           double (&ex)[C], double (&hy)[C], double (&dx)[C], double (&pc)[C],
                                           double (&pq)[C], double (&pe)[C], double (&ph)[C], double (&acub)[C],
@@ -153,7 +154,7 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
     constexpr bool HAS_PML = GEN || PML;
     // ===== E half-step: history shift + polarisation, ADE_ExUpdate, CPML_Psi_e, source,
     //                    ADE_DxUpdate, ADE_ExCreate | AcubicFinder + NonLinExUpdate =====
-    double hl = (tid > 0) ? S.edgeH[tid - 1] : 0.0;
+    double hl = S.edgeH[tid - 1];
     unsigned divkey = 0;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
@@ -214,7 +215,7 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
             }
         }
     }
-    if (!ALL_MAT && K.wSrc) {
+    if (!ALL_MAT && SP && K.wSrc) {
         // soft source (Solver_Engine.py:307): the last E operation of a non-material cell; a source
         // inside a material-law cell is overwritten by ADE_ExCreate in the reference too
 #pragma unroll
@@ -223,7 +224,7 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
     }
     S.edgeE[tid] = ex[0];
     cta_sync();
-    if (K.wSrc) {   // one-point TF/SF correction (Solver_Engine.py:309-310), before ADE_HyUpdate
+    if (SP && K.wSrc) {   // one-point TF/SF correction (Solver_Engine.py:309-310), before ADE_HyUpdate
 #pragma unroll
         for (int j = 0; j < C; ++j)
             if (j == K.jtfsf) hy[j] = A::sub(hy[j], S.srcH[s]);
@@ -232,7 +233,7 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
     // ===== H half-step: TF/SF correction, ADE_HyUpdate, CPML_Psi_m =====
     // the neighbour's Ex is requested first and consumed last (cell C-1), behind the cells that only
     // need the thread's own Ex, so the shared-memory latency is covered
-    const double exr = (tid < NT - 1) ? S.edgeE[tid + 1] : 0.0;
+    const double exr = S.edgeE[tid + 1];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
         double h = hy[j];
@@ -359,23 +360,30 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
     S.edgeH[tid] = hy[C - 1];
     cta_sync();
     constexpr bool SWAP = MODE == PF_LORENTZ && HAS_MAT && POL;   // P history alternates between pa and pb
-    int s = 0;
-    for (; s + 1 < ks; s += 2) {
-        tile_step<MODE, POL, C, A, GEN, SLAB, PML>(S, K, kc, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
-        probes(s);
-        cta_sync();
-        if (SWAP) tile_step<MODE, POL, C, A, GEN, SLAB, PML>(S, K, kc, tid, s + 1, ex, hy, dx, pb, pa, pe, ph, acub, rbe, rce, rcm);
-        else tile_step<MODE, POL, C, A, GEN, SLAB, PML>(S, K, kc, tid, s + 1, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
-        probes(s + 1);
-        cta_sync();
-    }
     bool swapped = false;   // true: current P is in pb, previous in pa
-    if (s < ks) {
-        tile_step<MODE, POL, C, A, GEN, SLAB, PML>(S, K, kc, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
-        probes(s);
-        cta_sync();
-        swapped = SWAP;
-    }
+    // The time loop exists twice: warps that own a source cell or a probe run the version with those
+    // (warp-uniform) tests, every other warp a loop with nothing in it but the update itself.
+    auto time_loop = [&](auto sp) {
+        constexpr bool SP = decltype(sp)::value;
+        int s = 0;
+        for (; s + 1 < ks; s += 2) {
+            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            if (SP) probes(s);
+            cta_sync();
+            if (SWAP) tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, tid, s + 1, ex, hy, dx, pb, pa, pe, ph, acub, rbe, rce, rcm);
+            else tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, tid, s + 1, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            if (SP) probes(s + 1);
+            cta_sync();
+        }
+        if (s < ks) {
+            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            if (SP) probes(s);
+            cta_sync();
+            swapped = SWAP;
+        }
+    };
+    if (K.wSrc || wProbe) time_loop(std::true_type{});
+    else time_loop(std::false_type{});
 
     // ---- store interior ---------------------------------------------------------------------------
     const int dst = src ^ 1;
@@ -438,9 +446,11 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     S.cHu.base = S.cEu.base + 8u * TILE_CELLS;
     S.cb.base = S.cHu.base + 8u * TILE_CELLS;
     S.c2u.base = S.cb.base + 8u * TILE_CELLS;
-    S.edgeH.base = S.c2u.base + 8u * TILE_CELLS;
+    // edgeH[-1] and edgeE[NT] are zero pads: the first / last thread reads its missing neighbour
+    // without a per-step test
+    S.edgeH.base = S.c2u.base + 8u * TILE_CELLS + 8u;
     S.edgeE.base = S.edgeH.base + 8u * NT;
-    S.srcE.base = S.edgeE.base + 8u * NT;
+    S.srcE.base = S.edgeE.base + 8u * NT + 8u;
     S.srcH.base = S.srcE.base + 8u * TILE_KMAX;
 
     const TileDesc td = tiles[blockIdx.x];
@@ -490,6 +500,7 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
             else { M.pj1 = j; M.po1 = (size_t)p * g.probe_stride; }
         }
     }
+    if (tid == 0) { S.edgeH[-1] = 0.0; S.edgeE[NT] = 0.0; }
     // source tables of this launch's steps (CTA-uniform load)
     const int nabs0 = n0 + n_done;
     for (int s = tid; s < ks; s += NT) {
