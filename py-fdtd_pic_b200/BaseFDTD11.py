@@ -119,14 +119,35 @@ def CPML_FieldInit(V, P, C_V, C_P):
     return C_V
 
 
+_LIBM_CACHE = {}
+
+
+def _libm_map(fn, x, y=None):
+    """math.exp(x) / math.pow(x, y) element by element (glibc, not NumPy's SIMD kernels, which differ in the
+    last bit).  Results are memoised on the exact input bytes: the E and H profiles use the same arguments and
+    every pass / sweep member with the same geometry repeats them."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    key = (fn, y, x.tobytes())
+    hit = _LIBM_CACHE.get(key)
+    if hit is None:
+        if fn == "exp":
+            hit = np.fromiter((math.exp(v) for v in x), dtype=np.float64, count=len(x))
+        else:
+            hit = np.fromiter((math.pow(v, y) for v in x), dtype=np.float64, count=len(x))
+        if len(_LIBM_CACHE) >= 64:
+            _LIBM_CACHE.clear()
+        _LIBM_CACHE[key] = hit
+    return hit.copy()
+
+
 def CPML_ScalingCalc(V, P, C_V, C_P):
     """BaseFDTD11.py:222-272 -- polynomial grading of sigma/kappa/alpha, mirrored on the right.
     The Hy profiles alias the Ex profiles, as in the reference."""
     pw, L = int(P.pmlWidth), len(V.Ex)
     n = np.arange(pw)
     depth = (pw - n) / pw
-    graded = np.fromiter((math.pow(d, C_P.r_scale) for d in depth), dtype=np.float64, count=pw)       # libm pow, as numba calls it
-    ramp = np.fromiter((math.pow(d, C_P.r_a_scale) for d in (n + 1) / pw), dtype=np.float64, count=pw)
+    graded = _libm_map("pow", depth, float(C_P.r_scale))       # libm pow, as numba calls it
+    ramp = _libm_map("pow", (n + 1) / pw, float(C_P.r_a_scale))
     kap = 1 + (C_P.kappaMax - 1) * graded
     sig = C_P.sigmaOpt * graded
     alp = C_P.alphaMax * ramp
@@ -152,7 +173,7 @@ def _recursive_conv_coefs(P, sigma, kappa, alpha, cells, per_dz):
     cells = np.asarray(cells, dtype=np.int64)
     s, k, a = sigma[cells], kappa[cells], alpha[cells]
     arg = -((s * P.delT / (k * P.permit_0)) + ((a * P.delT) / P.permit_0))
-    bn = np.fromiter((math.exp(v) for v in arg), dtype=np.float64, count=len(arg))
+    bn = _libm_map("exp", arg)
     den = s * k + a * k * k
     if per_dz:
         den = den * P.dz

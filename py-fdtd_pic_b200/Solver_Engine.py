@@ -192,8 +192,9 @@ def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=F
         torch.cuda.current_stream().synchronize()
         hist = stage.numpy()
         n_abs = np.arange(rows) * int(P.vidInterval)
-        done = (n_abs > 0) & (n_abs >= n0) & (n_abs < n0 + nsteps)
-        V.Ex_History[done] = hist[done]
+        done = np.flatnonzero((n_abs > 0) & (n_abs >= n0) & (n_abs < n0 + nsteps))
+        if len(done):                               # a contiguous block of rows: one memcpy, no mask temporaries
+            V.Ex_History[done[0]:done[-1] + 1] = hist[done[0]:done[-1] + 1]
     LAST_RUN_INFO.update(engine="tile" if engine == nat.PF_ENGINE_TILE else "ops", h2d_bytes=g.h2d_bytes,
                          d2h_bytes=g.d2h_bytes, launches=lib.pf_launch_count() - launches0, cells=L, steps=nsteps)
     return out["probe_out"]

@@ -204,7 +204,11 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
     }
     // warp-uniform test: a per-lane branch here opens a divergent region, which costs the uniform
     // registers holding the shared-memory window (re-read with S2UR after every step)
+#ifdef PF_EXPERIMENT_NO_GUARD   // timing experiment only: cost of the division-range guard
+    if (false) {
+#else
     if (MODE == PF_LORENTZ && HAS_MAT && __any_sync(0xffffffffu, !div_const_in_range(divkey))) {
+#endif
         // some cell's (Dx - P) was zero, in the denormal range or non-finite: redo those divisions
         // exactly (rare once the wave has arrived; integer tests only for the zero case)
 #pragma unroll

@@ -190,6 +190,10 @@ class MemberBatch:
         self.host_probe.copy_(self.pool[self.n_state + self.n_in:], non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
         hv = self.host_probe.numpy()
+        shapes = {(max(len(m.probe_idx), 1), len(m.probe_idx), (m.T + 31) // 32 * 32, m.T) for m in self.members}
+        if len(shapes) == 1:        # uniform batch (the sweep case): one strided copy instead of one per member
+            rows, n_p, Tp, T = next(iter(shapes))
+            return list(hv.reshape(len(self.members), rows, Tp)[:, :n_p, :T].copy())
         out = []
         o0 = self.n_state + self.n_in
         for i, m in enumerate(self.members):
