@@ -465,7 +465,7 @@ def main():
                     "this, not HBM, is the pipe that bounds the temporally blocked kernel"}
     # DRAM bytes of one launch of this kernel from the committed ncu --set full capture of the DEFAULT workload
     # (profiles/r1_final_k_tile_ncu.txt: dram__bytes_read.sum 539.5 MB + dram__bytes_write.sum 469.8 MB)
-    traffic = 539.547392e6 + 469.796096e6 if (args.members == 1024 and k_block == 64 and args.n_freq == 64) else None
+    traffic = 537.556736e6 + 462.760448e6 if (args.members == 1024 and k_block == 64 and args.n_freq == 64) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "k_tile<PF_LORENTZ,POL,8,Exact>", "peak_source": peak_src,
                 "kernel_ms_avg": avg_kernel_ms, "kernel_launches_timed": kn.value,

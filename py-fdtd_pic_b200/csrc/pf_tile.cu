@@ -386,7 +386,8 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
             swapped = SWAP;
         }
     };
-    if (K.wSrc || wProbe) time_loop(std::true_type{});
+    // (the cubic material law dwarfs those tests and is large: one copy of its loop only)
+    if (MODE == PF_NL || K.wSrc || wProbe) time_loop(std::true_type{});
     else time_loop(std::false_type{});
 
     // ---- store interior ---------------------------------------------------------------------------
