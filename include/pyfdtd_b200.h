@@ -110,6 +110,12 @@ int pf_sync(void *stream);
 /* number of kernels this library has launched since load (bench.py's gpu_launches)             */
 unsigned long long pf_launch_count(void);
 
+/* Host-side helpers of the setup chain (no GPU involved): y[i] = exp(x[i]) / pow(x[i], e) through the C
+ * library, one element at a time.  The reference's numba-compiled setup loops (BaseFDTD11.py:237-240,
+ * 278-294) call libm per element; NumPy's SIMD exp/pow differ from it in the last bit.               */
+int pf_host_exp(const double *x, double *y, long long n);
+int pf_host_pow(const double *x, double e, double *y, long long n);
+
 /* ---- leaf ops: one call = one reference leaf function on one grid ---------------------- */
 int pf_ade_ex_update(const PfGrid *g, void *stream);        /* BaseFDTD11.py:663-669  ADE_ExUpdate               */
 int pf_ade_hy_update(const PfGrid *g, void *stream);        /* BaseFDTD11.py:640-656  ADE_HyUpdate               */

@@ -130,10 +130,19 @@ def _libm_map(fn, x, y=None):
     key = (fn, y, x.tobytes())
     hit = _LIBM_CACHE.get(key)
     if hit is None:
-        if fn == "exp":
-            hit = np.fromiter((math.exp(v) for v in x), dtype=np.float64, count=len(x))
+        hit = np.empty(len(x))
+        try:
+            L = nat.lib()
+        except nat.NativeError:
+            L = None                    # library not built: same libm through CPython, just slower
+        if L is not None and fn == "exp":
+            nat.check(L.pf_host_exp(x.ctypes.data, hit.ctypes.data, len(x)), "pf_host_exp")
+        elif L is not None:
+            nat.check(L.pf_host_pow(x.ctypes.data, float(y), hit.ctypes.data, len(x)), "pf_host_pow")
+        elif fn == "exp":
+            hit[:] = np.fromiter((math.exp(v) for v in x), dtype=np.float64, count=len(x))
         else:
-            hit = np.fromiter((math.pow(v, y) for v in x), dtype=np.float64, count=len(x))
+            hit[:] = np.fromiter((math.pow(v, y) for v in x), dtype=np.float64, count=len(x))
         if len(_LIBM_CACHE) >= 64:
             _LIBM_CACHE.clear()
         _LIBM_CACHE[key] = hit

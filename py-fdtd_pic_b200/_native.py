@@ -61,6 +61,8 @@ SYMBOLS = {
     "pf_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t)]),
     "pf_sync": (c_int, [c_void_p]),
     "pf_launch_count": (ctypes.c_ulonglong, []),
+    "pf_host_exp": (c_int, [c_void_p, c_void_p, ctypes.c_longlong]),
+    "pf_host_pow": (c_int, [c_void_p, c_double, c_void_p, ctypes.c_longlong]),
     "pf_ade_ex_update": (c_int, [_G, c_void_p]),
     "pf_ade_hy_update": (c_int, [_G, c_void_p]),
     "pf_cpml_psi_e_update": (c_int, [_G, c_void_p]),

@@ -58,6 +58,20 @@ int pf_abi_version(void) { return PF_ABI_VERSION; }
 const char *pf_last_error(void) { return pf::g_err; }
 unsigned long long pf_launch_count(void) { return pf::g_launches; }
 
+int pf_host_exp(const double *x, double *y, long long n)
+{
+    if (n < 0 || (n > 0 && (!x || !y))) return pf::set_err(PF_E_ARG, "pf_host_exp: bad arguments");
+    for (long long i = 0; i < n; ++i) y[i] = exp(x[i]);
+    return PF_OK;
+}
+
+int pf_host_pow(const double *x, double e, double *y, long long n)
+{
+    if (n < 0 || (n > 0 && (!x || !y))) return pf::set_err(PF_E_ARG, "pf_host_pow: bad arguments");
+    for (long long i = 0; i < n; ++i) y[i] = pow(x[i], e);
+    return PF_OK;
+}
+
 int pf_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *free_bytes, size_t *total_bytes)
 {
     int dev = 0;

@@ -172,3 +172,19 @@ def test_hot_path_fails_loudly_without_gpu():
     BaseFDTD11.FieldInit(V, P)
     with pytest.raises(nat.NativeError):
         BaseFDTD11.ADE_ExUpdate(V, P, C_V, C_P, 0)
+
+
+def test_native_libm_maps_equal_cpython_math():
+    """pf_host_exp / pf_host_pow (setup-chain helpers in the product library) are the same glibc calls as
+    math.exp / math.pow: bit-identical, including the memoised second call."""
+    import math
+    from pyfdtd_b200 import BaseFDTD11 as B
+    rng = np.random.default_rng(5)
+    x = -np.abs(rng.normal(size=3000)) * 30
+    B._LIBM_CACHE.clear()
+    for _ in range(2):
+        got = B._libm_map("exp", x)
+        assert np.array_equal(got, np.array([math.exp(v) for v in x]))
+    d = rng.uniform(0, 1, 3000)
+    for e in (4.0, 1.0, 2.5):
+        assert np.array_equal(B._libm_map("pow", d, e), np.array([math.pow(v, e) for v in d]))
