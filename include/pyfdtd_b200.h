@@ -209,7 +209,8 @@ int pf_pic_push(const PfPic *p, void *stream);
 int pf_pic_sort(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
 /* push + stable re-sort fused, for a set that IS sorted by cell on entry: exploits |v| dt < dz (a
  * particle changes cell by at most one per step) -- count pass, cell scan, move pass; reads the primary
- * arrays, writes the pushed AND sorted particles to the *_alt arrays (caller swaps).  Bit-identical to
+ * arrays, writes the pushed AND sorted particles to the *_alt arrays (caller swaps; the primary z/ux/uz
+ * are used as staging and hold the pushed particles in their old order afterwards).  Bit-identical to
  * pf_pic_push followed by pf_pic_sort.  pf_pic_check returns 1 if a particle crossed more than one cell. */
 int pf_pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
 int pf_pic_check(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);

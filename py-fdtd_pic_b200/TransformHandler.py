@@ -35,3 +35,32 @@ def reflection_spectrum(x1ColBe, x1ColAf, delT, fmin=None, fmax=None):
     if fmax is not None:
         sel &= f <= fmax
     return f[sel], Ya[sel] / Yb[sel]
+
+
+def ref_tester_batch(traces, time_steps, keep_from=None, keep_to=None):
+    """RefTester's scalar for a whole batch, on whatever device ``traces`` lives on (SURVEY section 8f row 1:
+    the sweep's probe traces never leave the GPU).
+
+    traces: torch tensor [members, >= time_steps] float64, one probe trace per row (only the first
+    ``time_steps`` samples are used -- no zero padding, the bins must be the reference's).  Samples with
+    index < keep_from[m] or > keep_to[m] are zeroed first (the reference's x1ColAf / x1ColBe read windows,
+    Solver_Engine.py:360-368).  Returns (val, idx): val[m] = 2|FFT(y_m)|/time_steps at the largest bin,
+    idx[m] that bin.  Raises ValueError like RefTester if the largest bin of any member is DC.
+    """
+    import torch
+    T = int(time_steps)
+    y = traces[:, :T]
+    if keep_from is not None or keep_to is not None:
+        n = torch.arange(T, device=y.device)[None, :]
+        keep = torch.ones(y.shape, dtype=torch.bool, device=y.device)
+        if keep_from is not None:
+            keep &= n >= torch.as_tensor(keep_from, device=y.device).reshape(-1, 1)
+        if keep_to is not None:
+            keep &= n <= torch.as_tensor(keep_to, device=y.device).reshape(-1, 1)
+        y = torch.where(keep, y, torch.zeros((), dtype=y.dtype, device=y.device))
+    mag = torch.fft.rfft(y, dim=1).abs()          # |Y[k]| = |Y[T-k]|: the first maximum is in the half spectrum
+    idx = torch.argmax(mag, dim=1)
+    if bool((idx == 0).any()):
+        raise ValueError("Could not find non-DC freq")
+    val = 2.0 * mag.gather(1, idx[:, None])[:, 0] / T
+    return val, idx

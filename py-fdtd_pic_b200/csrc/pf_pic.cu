@@ -109,10 +109,13 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_push(PfPic p, PicDerived D)
 // sorted up to exchanges between neighbouring cells.  The stable sort by new cell is then a counting
 // problem: the new population of cell c is [right-movers of c-1][stayers of c][left-movers of c+1], each
 // group in its old order.  Two passes, one warp per (old) cell, no radix sort, no gather:
-//   count : push the cell's particles in registers, count left / stay / right            (reads z,ux,uz)
+//   count : push the cell's particles, store them in place (old order), count left / stay / right
+//                                                                                      (reads 24 B, writes 24 B)
 //   scan  : new_start = exclusive scan of nR[c-1] + nS[c] + nL[c+1]
-//   move  : push again (bit-identical), rank by ballot in index order, write every particle straight to
-//           its final slot of the alternate arrays                                     (reads 32 B, writes 36 B)
+//   move  : re-derive each pushed particle's cell from its z, rank by ballot in index order, write it
+//           straight to its final slot of the alternate arrays                         (reads 32 B, writes 36 B)
+// (pushing twice instead of storing saves 24 B of traffic per particle but doubles the fp64 work of the
+//  push, ~190 instructions with its two square roots and three divisions: measured slower)
 __global__ void __launch_bounds__(PIC_THREADS) k_pic_cell_start(const int *__restrict__ cell, long long n, int L,
                                                                 long long *__restrict__ start)
 {
@@ -126,19 +129,40 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_cell_start(const int *__res
     start[c] = lo;
 }
 
-__global__ void __launch_bounds__(PIC_THREADS) k_pic_count(PfPic p, PicDerived D, const long long *__restrict__ start,
-                                                           int *__restrict__ counts, int *__restrict__ err)
+// particle range of sub-warp s (of S) of a cell holding [a, b): contiguous pieces, multiples of 32
+__device__ __forceinline__ void sub_range(long long a, long long b, int S, int s, long long &lo, long long &hi)
 {
-    const int c = (blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
+    const long long q = (((b - a) + S - 1) / S + 31) / 32 * 32;
+    lo = min(b, a + (long long)s * q);
+    hi = min(b, lo + q);
+}
+
+// sum of one of the three counters of cell c over its S sub-warps
+__device__ __forceinline__ int cell_count(const int *__restrict__ counts, int S, int c, int k)
+{
+    int t = 0;
+    for (int s = 0; s < S; ++s) t += counts[((size_t)c * S + s) * 3 + k];
+    return t;
+}
+
+__global__ void __launch_bounds__(PIC_THREADS) k_pic_count(PfPic p, PicDerived D, const long long *__restrict__ start,
+                                                           int *__restrict__ counts, int *__restrict__ err, int S)
+{
+    const long long wid = ((long long)blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    const int c = (int)(wid / S), sub = (int)(wid % S);
     if (c >= p.L) return;
-    const long long a = start[c], b = start[c + 1];
+    long long a, b;
+    sub_range(start[c], start[c + 1], S, sub, a, b);
     int nl = 0, ns = 0, nr = 0;
     for (long long i0 = a; i0 < b; i0 += 32) {
         const long long i = i0 + lane;
         int d = 2;                        // 2 = no particle in this lane
         if (i < b) {
             Pushed r = pic_push_one(p, D, p.z[i], p.ux[i], p.uz[i]);
+            p.z[i] = r.z;               // pushed state, still in the old order: the move pass only re-ranks it
+            p.ux[i] = r.ux;
+            p.uz[i] = r.uz;
             d = r.cell - c;
             if (d < -1 || d > 1) { atomicExch(err, 1); d = max(-1, min(1, d)); }
         }
@@ -147,13 +171,23 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_count(PfPic p, PicDerived D
         nr += __popc(__ballot_sync(0xffffffffu, d == 1));
     }
     if (lane == 0) {
-        counts[3 * c] = nl;
-        counts[3 * c + 1] = ns;
-        counts[3 * c + 2] = nr;
+        int *o = counts + ((size_t)c * S + sub) * 3;
+        o[0] = nl;
+        o[1] = ns;
+        o[2] = nr;
     }
 }
 
-// single CTA: new_start[c] = sum_{c' < c} (nR[c'-1] + nS[c'] + nL[c'+1])
+// per-cell totals of the sub-warp counters (tot[3c+k]); one thread per cell
+__global__ void __launch_bounds__(PIC_THREADS) k_pic_cell_totals(const int *__restrict__ counts, int L, int S,
+                                                                 int *__restrict__ tot)
+{
+    const int c = blockIdx.x * PIC_THREADS + threadIdx.x;
+    if (c >= L) return;
+    for (int k = 0; k < 3; ++k) tot[3 * c + k] = cell_count(counts, S, c, k);
+}
+
+// single CTA: new_start[c] = sum_{c' < c} (nR[c'-1] + nS[c'] + nL[c'+1])   (counts = per-cell totals)
 __global__ void __launch_bounds__(1024) k_pic_scan(const int *__restrict__ counts, int L, long long *__restrict__ new_start)
 {
     __shared__ long long part[1024];
@@ -180,28 +214,40 @@ __global__ void __launch_bounds__(1024) k_pic_scan(const int *__restrict__ count
 }
 
 __global__ void __launch_bounds__(PIC_THREADS) k_pic_move(PfPic p, PicDerived D, const long long *__restrict__ start,
-                                                          const int *__restrict__ counts, const long long *__restrict__ new_start)
+                                                          const int *__restrict__ counts, const int *__restrict__ tot,
+                                                          const long long *__restrict__ new_start, int S)
 {
-    const int c = (blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
+    const long long wid = ((long long)blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    const int c = (int)(wid / S), sub = (int)(wid % S);
     if (c >= p.L) return;
-    const long long a = start[c], b = start[c + 1];
+    long long a, b;
+    sub_range(start[c], start[c + 1], S, sub, a, b);
     if (a == b) return;
     const unsigned lt = (1u << lane) - 1u;
-    // first slot of each group in the new order
+    // first slot of each group in the new order (tot = per-cell totals), advanced past the cell's earlier sub-warps
     long long posL = 0, posS, posR = 0;
-    if (c > 0) posL = new_start[c - 1] + (c > 1 ? counts[3 * (c - 2) + 2] : 0) + counts[3 * (c - 1) + 1];
-    posS = new_start[c] + (c > 0 ? counts[3 * (c - 1) + 2] : 0);
+    if (c > 0) posL = new_start[c - 1] + (c > 1 ? tot[3 * (c - 2) + 2] : 0) + tot[3 * (c - 1) + 1];
+    posS = new_start[c] + (c > 0 ? tot[3 * (c - 1) + 2] : 0);
     if (c + 1 < p.L) posR = new_start[c + 1];
+    for (int s2 = 0; s2 < sub; ++s2) {
+        const int *o = counts + ((size_t)c * S + s2) * 3;
+        posL += o[0];
+        posS += o[1];
+        posR += o[2];
+    }
     for (long long i0 = a; i0 < b; i0 += 32) {
         const long long i = i0 + lane;
         int d = 2;
         Pushed r;
         double w = 0.0;
         if (i < b) {
-            r = pic_push_one(p, D, p.z[i], p.ux[i], p.uz[i]);
+            r.z = p.z[i];               // already pushed by the count pass
+            r.ux = p.ux[i];
+            r.uz = p.uz[i];
             w = p.w[i];
-            d = max(-1, min(1, r.cell - c));
+            const int cn = (int)floor(r.z * D.inv_dz);     // same expression as pic_push_one's cell
+            d = max(-1, min(1, max(0, min(cn, p.L - 2)) - c));
         }
         const unsigned bl = __ballot_sync(0xffffffffu, d == -1);
         const unsigned bs = __ballot_sync(0xffffffffu, d == 0);
@@ -238,6 +284,14 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_permute(PfPic p, const int 
     p.w_alt[i] = p.w[src];
 }
 
+// the fused push + re-sort runs up to this many warps per cell (each on a contiguous piece of the cell's particles)
+constexpr int PIC_SUB_MAX = 8;
+static inline int pic_sub_warps(const PfPic *p)
+{
+    long long per_cell = p->n / std::max(1, p->L);
+    return (int)std::min<long long>(PIC_SUB_MAX, std::max<long long>(1, (per_cell + 255) / 256));
+}
+
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
 static int key_bits(int L)
@@ -248,7 +302,7 @@ static int key_bits(int L)
 }
 
 struct PicPlan {
-    size_t off_idx_in, off_idx_out, off_cub, off_acc, off_start, off_new_start, off_counts, off_err, cub_bytes, total;
+    size_t off_idx_in, off_idx_out, off_cub, off_acc, off_start, off_new_start, off_counts, off_tot, off_err, cub_bytes, total;
 };
 
 static PicPlan pic_plan(const PfPic *p)
@@ -265,7 +319,8 @@ static PicPlan pic_plan(const PfPic *p)
     pl.off_start = pl.off_acc + al256(sizeof(double) * 2 * (size_t)p->L);
     pl.off_new_start = pl.off_start + al256(sizeof(long long) * ((size_t)p->L + 1));
     pl.off_counts = pl.off_new_start + al256(sizeof(long long) * ((size_t)p->L + 1));
-    pl.off_err = pl.off_counts + al256(sizeof(int) * 3 * (size_t)p->L);
+    pl.off_tot = pl.off_counts + al256(sizeof(int) * 3 * (size_t)p->L * PIC_SUB_MAX);
+    pl.off_err = pl.off_tot + al256(sizeof(int) * 3 * (size_t)p->L);
     pl.total = pl.off_err + 256;
     return pl;
 }
@@ -377,12 +432,16 @@ int pf_pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void
     PF_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
     k_pic_cell_start<<<(p->L + 1 + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(p->cell, p->n, p->L, start);
     PF_LAUNCH_CHECK("k_pic_cell_start");
-    unsigned wblocks = (unsigned)(((long long)p->L * 32 + PIC_THREADS - 1) / PIC_THREADS);
-    k_pic_count<<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, err);
+    const int S = pic_sub_warps(p);
+    int *tot = (int *)(s + pl.off_tot);
+    unsigned wblocks = (unsigned)(((long long)p->L * S * 32 + PIC_THREADS - 1) / PIC_THREADS);
+    k_pic_count<<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, err, S);
     PF_LAUNCH_CHECK("k_pic_count");
-    k_pic_scan<<<1, 1024, 0, st>>>(counts, p->L, new_start);
+    k_pic_cell_totals<<<(p->L + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(counts, p->L, S, tot);
+    PF_LAUNCH_CHECK("k_pic_cell_totals");
+    k_pic_scan<<<1, 1024, 0, st>>>(tot, p->L, new_start);
     PF_LAUNCH_CHECK("k_pic_scan");
-    k_pic_move<<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, new_start);
+    k_pic_move<<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S);
     PF_LAUNCH_CHECK("k_pic_move");
     return PF_OK;
 }

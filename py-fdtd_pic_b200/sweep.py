@@ -203,6 +203,34 @@ class MemberBatch:
             out.append(a.reshape(max(n_p, 1), Tp)[:n_p, : m.T].copy())
         return out
 
+    def download_probe(self, i):
+        """D2H of the probe traces of member i only -> array [n_probes, T]."""
+        m = self.members[i]
+        Tp = (m.T + 31) // 32 * 32
+        n_p = len(m.probe_idx)
+        a = self.pool[self.off_probe[i]: self.off_probe[i] + max(n_p, 1) * Tp].cpu().numpy()
+        return a.reshape(max(n_p, 1), Tp)[:n_p, : m.T].copy()
+
+    def probe_peaks(self, probe=0, keep_from=None, keep_to=None):
+        """RefTester's scalar of probe ``probe`` of every member, computed on the device (batched FFT per
+        distinct timeSteps; nothing but the result, one double per member, is copied to the host).
+        keep_from / keep_to: per-member first / last sample index of the read window (others are zeroed)."""
+        from . import TransformHandler as transH
+        torch = self.torch
+        M = len(self.members)
+        kf = None if keep_from is None else np.asarray(keep_from, dtype=np.int64)
+        kt = None if keep_to is None else np.asarray(keep_to, dtype=np.int64)
+        groups = {}
+        for i, m in enumerate(self.members):
+            groups.setdefault(m.T, []).append(i)
+        out = torch.empty(M, dtype=torch.float64, device=self.device)
+        for T, idxs in groups.items():
+            Tp = (T + 31) // 32 * 32
+            rows = torch.stack([self.pool[self.off_probe[i] + probe * Tp: self.off_probe[i] + probe * Tp + T] for i in idxs])
+            val, _ = transH.ref_tester_batch(rows, T, None if kf is None else kf[idxs], None if kt is None else kt[idxs])
+            out[torch.as_tensor(idxs, device=self.device)] = val
+        return out.cpu().numpy()
+
     def state(self, i, name):
         """Device -> host copy of one state array of member i (tests / final fields)."""
         m = self.members[i]
@@ -229,13 +257,19 @@ def new_member_objects(freq_in, domainSize, lowLimTim, highLimTim, prevV, prevP,
     return V, P, C_V, C_P
 
 
-def run_two_pass_batch(objs, lorentz=True, k_block=0, rank=0, world_size=1):
+def run_two_pass_batch(objs, lorentz=True, k_block=0, rank=0, world_size=1, device_reflection=False):
     """Run the two-pass (incident / with medium) integrator for every (V,P,C_V,C_P) in ``objs`` as a
     batch.  Fills V.x1ColBe / V.x1ColAf and the final fields of every member owned by this rank
-    (member % world_size == rank) and returns the indices of the owned members."""
+    (member % world_size == rank).  Returns (owned member indices, their source tables, reflection).
+
+    device_reflection=True: the reflection coefficient of every owned member (``results(RefCo=True)``:
+    RefTester peak of the windowed x1ColAf over that of x1ColBe) is computed on the device and returned as
+    an array; only the LAST owned member's traces are copied back into its V (the reference's sweep never
+    looks at the others again).  Otherwise reflection is None and every member's traces are downloaded."""
     mode = "lorentz" if lorentz else "free"
     mine = [i for i in range(len(objs)) if i % world_size == rank]
     srcs = {}
+    peaks = [None, None]
     for pass_idx in range(2):
         members = []
         for i in mine:
@@ -250,21 +284,34 @@ def run_two_pass_batch(objs, lorentz=True, k_block=0, rank=0, world_size=1):
         batch.upload()
         batch.reset_state()
         batch.run(do_pol=(lorentz and pass_idx == 1), k_block=k_block)
-        traces = batch.download_probes()
-        for j, i in enumerate(mine):
-            V, P, C_V, C_P = objs[i]
+        fin_be = [int(objs[i][1].timeSteps * 0.7) for i in mine]        # Solver_Engine.py:360-368 read windows
+        start_af = [int(objs[i][1].timeSteps * 0.05) for i in mine]
+        if device_reflection:
+            peaks[pass_idx] = (batch.probe_peaks(keep_to=fin_be) if pass_idx == 0
+                               else batch.probe_peaks(keep_from=start_af))
+            fetch = [len(mine) - 1]
+            traces = {fetch[0]: batch.download_probe(fetch[0])}
+        else:
+            fetch = range(len(mine))
+            traces = dict(enumerate(batch.download_probes()))
+        for j in fetch:
+            V, P, C_V, C_P = objs[mine[j]]
             n = np.arange(P.timeSteps)
             if pass_idx == 0:
-                V.x1ColBe = np.where(n <= int(P.timeSteps * 0.7), traces[j][0], 0.0)
+                V.x1ColBe = np.where(n <= fin_be[j], traces[j][0], 0.0)
             else:
-                V.x1ColAf = np.where(n >= int(P.timeSteps * 0.05), traces[j][0], 0.0)
+                V.x1ColAf = np.where(n >= start_af[j], traces[j][0], 0.0)
                 V.Ex, V.Hy = batch.state(j, "Ex"), batch.state(j, "Hy")
-    return mine, srcs
+    refl = peaks[1] / peaks[0] if device_reflection and mine else None
+    return mine, srcs, refl
 
 
-def frequency_sweep(V, P, domainSize, lowLimTim, highLimTim, Low=3e9, Interval=1e8, points=20, batched=True):
+def frequency_sweep(V, P, domainSize, lowLimTim, highLimTim, Low=3e9, Interval=1e8, points=20, batched=True,
+                    device_postproc=True):
     """MasterController.LoopedSim(loop=True) :533-569.  Returns (freqs, measured R, analytical R,
-    (V,P,C_V,C_P,Exs,Hys) of the last member)."""
+    (V,P,C_V,C_P,Exs,Hys) of the last member).  With ``batched`` and ``device_postproc`` the reflection
+    extraction (results(RefCo=True) -> RefTester) runs on the device too and only the last member's traces
+    come back to the host."""
     from . import MasterController as MC
     freqs = np.arange(Low, points * Interval + Low, Interval)[:points]
     # -- setup chain (sequential by construction: member i is sized from member i-1's corrected medium;
@@ -289,14 +336,15 @@ def frequency_sweep(V, P, domainSize, lowLimTim, highLimTim, Low=3e9, Interval=1
             MC.Controller(Vi, Pi, CVi, CPi)
             prevV, prevP = Vi, Pi
         freq = Pi.freq_in + Interval
-    srcs = {}
+    srcs, refl = {}, None
     if batched:
-        _, srcs = run_two_pass_batch(objs, lorentz=bool(P.LorentzMed), k_block=0)
+        _, srcs, refl = run_two_pass_batch(objs, lorentz=bool(P.LorentzMed), k_block=0,
+                                           device_reflection=bool(device_postproc))
     measured = np.zeros(points)
     analytical = np.zeros(points)
     for i, (Vi, Pi, CVi, CPi) in enumerate(objs):
         t = np.arange(0, len(Vi.x1ColBe)) * Pi.delT
-        measured[i] = MC.results(Vi, Pi, CVi, CPi, t, RefCo=True)
+        measured[i] = refl[i] if refl is not None else MC.results(Vi, Pi, CVi, CPi, t, RefCo=True)
         analytical[i] = MC.results(Vi, Pi, CVi, CPi, t, AnalRefCo=True)
     Vi, Pi, CVi, CPi = objs[-1]
     Pi.freq_in = Pi.freq_in + Interval          # the reference leaves the last P advanced (:559)

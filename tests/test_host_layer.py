@@ -188,3 +188,34 @@ def test_native_libm_maps_equal_cpython_math():
     d = rng.uniform(0, 1, 3000)
     for e in (4.0, 1.0, 2.5):
         assert np.array_equal(B._libm_map("pow", d, e), np.array([math.pow(v, e) for v in d]))
+
+
+def test_batched_ref_tester_matches_reference_ref_tester():
+    """TransformHandler.ref_tester_batch (the device-side post-processing of sweeps, run here on CPU tensors)
+    against the RefTester mirror on traces of the unmodified reference; read windows; DC-peak error."""
+    import torch
+    from types import SimpleNamespace
+    from pyfdtd_b200 import TransformHandler as TH
+    from conftest import load_golden
+    g = load_golden("lorentz_sine")
+    be, af = np.asarray(g["x1ColBe"]), np.asarray(g["x1ColAf"])
+    T = len(be)
+    P = SimpleNamespace(timeSteps=T, delT=1e-13)
+    want = [TH.RefTester(None, P, y, 1)[2] for y in (be, af)]
+    pad = np.zeros((2, T + 7))                       # rows are padded in the device pool: only [:T] may be used
+    pad[0, :T], pad[1, :T] = be, af
+    pad[:, T:] = 123.0
+    val, idx = TH.ref_tester_batch(torch.from_numpy(pad), T)
+    np.testing.assert_allclose(val.numpy(), want, rtol=1e-12)
+    assert (idx.numpy() > 0).all()
+    # windows: zero outside [keep_from, keep_to] exactly like the integrators do (Solver_Engine.py:360-368)
+    rng = np.random.default_rng(3)
+    raw = rng.normal(size=(3, T)) + np.sin(0.05 * np.arange(T))[None, :]
+    kf, kt = np.array([0, 10, 40]), np.array([T - 1, T - 30, int(T * 0.7)])
+    val, _ = TH.ref_tester_batch(torch.from_numpy(raw), T, keep_from=kf, keep_to=kt)
+    n = np.arange(T)
+    for m in range(3):
+        y = np.where((n >= kf[m]) & (n <= kt[m]), raw[m], 0.0)
+        assert val[m].item() == pytest.approx(TH.RefTester(None, P, y, 1)[2], rel=1e-12)
+    with pytest.raises(ValueError):
+        TH.ref_tester_batch(torch.ones((1, T), dtype=torch.float64), T)

@@ -19,4 +19,23 @@ for _ in range(2):
     ps.push(Ex, Hy)
     ps.deposit()
 torch.cuda.synchronize()
-print("ok")
+
+
+def timed(fn, reps=5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+ps.sort()
+t_ps = timed(lambda: ps.push_sorted(Ex, Hy))
+t_dep = timed(ps.deposit)
+t_push = timed(lambda: ps.push(Ex, Hy))
+ps.sort()
+print("n=%d  push_sorted %.3f ms  deposit %.3f ms  -> %.3e particle-steps/s;  plain push %.3f ms (%.3e /s)"
+      % (n, t_ps, t_dep, n / (t_ps + t_dep) * 1e3, t_push, n / t_push * 1e3))
