@@ -129,6 +129,39 @@ def _time_cuda(torch, fn, reps):
     return e0.elapsed_time(e1) * 1e-3 / reps
 
 
+def build_nl_batch(M, S):
+    """Config 3 workload: M members of the nonlinear (cubic) sweep, S time steps each (16 distinct grids)."""
+    import pyfdtd_b200  # noqa: F401
+    from pyfdtd_b200 import MasterController as MC, Environment_Setup as envDef, Solver_Engine as SE, sweep
+    freqs = np.linspace(6e9, 10.5e9, 16)
+    members, share, first = [], [], {}
+    for i in range(M):
+        f = float(freqs[i % 16])
+        if f in first:
+            b = members[first[f]]
+            m = sweep.Member(b.V, b.P, b.C_V, b.C_P, b._Exs * (1 + i / M), b._Hys * (1 + i / M), [b.P.materialFrontEdge], nsteps=S)
+            share.append(first[f])
+        else:
+            tup = envDef.envSetup(f, 0.7, 7000, 8000, nonLinMed=True)
+            P = MC.Params(*tup, False, 0.7, f, 20)
+            P.TFSF, P.SineCont, P.Periods, P.nonLinMed, P.FreeSpace, P.LorentzMed = True, True, 1000, True, False, False
+            V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
+            C_P = MC.CPML_Params(P.dz)
+            C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
+            C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=False, nonlinear=True)
+            m = sweep.Member(V, P, C_V, C_P, Exs, Hys, [P.materialFrontEdge], nsteps=S)
+            m._Exs, m._Hys = Exs, Hys
+            first[f] = i
+            share.append(i)
+        m.T = S
+        m.srcE, m.srcH = m.srcE[:S], m.srcH[:S]
+        members.append(m)
+    batch = sweep.MemberBatch(members, "nl", share_coef=share)
+    batch.upload()
+    batch.randomize_state()
+    return batch, members
+
+
 def extras(torch, peak_gbs, quick=False):
     """Short measurements of the other BASELINE.json configs (device-resident, synthetic non-zero state)."""
     import pyfdtd_b200  # noqa: F401
@@ -177,32 +210,7 @@ def extras(torch, peak_gbs, quick=False):
                              "unmodified reference on the build container CPU (tests/golden/*_default_full.npz: ref_wall_seconds)"}
     # --- config 3: nonlinear (cubic solve per slab cell per step) sweep batch
     M, S = (64, 64) if quick else (256, 128)
-    freqs = np.linspace(6e9, 10.5e9, 16)
-    members, share, first = [], [], {}
-    for i in range(M):
-        f = float(freqs[i % 16])
-        if f in first:
-            b = members[first[f]]
-            m = sweep.Member(b.V, b.P, b.C_V, b.C_P, b._Exs * (1 + i / M), b._Hys * (1 + i / M), [b.P.materialFrontEdge], nsteps=S)
-            share.append(first[f])
-        else:
-            tup = envDef.envSetup(f, 0.7, 7000, 8000, nonLinMed=True)
-            P = MC.Params(*tup, False, 0.7, f, 20)
-            P.TFSF, P.SineCont, P.Periods, P.nonLinMed, P.FreeSpace, P.LorentzMed = True, True, 1000, True, False, False
-            V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
-            C_P = MC.CPML_Params(P.dz)
-            C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
-            C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=False, nonlinear=True)
-            m = sweep.Member(V, P, C_V, C_P, Exs, Hys, [P.materialFrontEdge], nsteps=S)
-            m._Exs, m._Hys = Exs, Hys
-            first[f] = i
-            share.append(i)
-        m.T = S
-        m.srcE, m.srcH = m.srcE[:S], m.srcH[:S]
-        members.append(m)
-    batch = sweep.MemberBatch(members, "nl", share_coef=share)
-    batch.upload()
-    batch.randomize_state()
+    batch, members = build_nl_batch(M, S)
 
     def nl_step():
         batch.reset_state(template=True)

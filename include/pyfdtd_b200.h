@@ -57,8 +57,18 @@ enum {
                            Cb[nz] == UpExMat[nz] and C2[nz] == c2_pml on the CPML correction
                            ranges and 0 at nz = L-pw (BaseFDTD11.py:306-330).  Set by the host
                            layer after checking the arrays bit for bit.                          */
-    PF_F_FMA = 16       /* allow fused multiply-add contraction (faster, not bit-identical to the
+    PF_F_FMA = 16,      /* allow fused multiply-add contraction (faster, not bit-identical to the
                            reference's un-contracted fp64 arithmetic; <= 1e-10 relative)         */
+    PF_F_NEWTON = 64,   /* nonlinear mode: find the positive root of the per-cell cubic by Newton iteration
+                           instead of the reference's closed form (CubicEquationSolver.py:29-105) when
+                           cub, qua >= 0 and one > 0 (otherwise the closed form is used).  ~3x fewer
+                           instructions; differs from the closed form by its own cancellation error
+                           (<= 1e-10 absolute on Acubic, <= 1e-10 relative on the fields).          */
+    PF_F_FP32 = 32      /* optional single-precision mode of the tile engine: the on-chip state is
+                           advanced in fp32 (contracted; Lorentz ADE in difference form, cubic root by
+                           Newton iteration); the arrays in device memory stay fp64 and are converted at
+                           tile load / store.  Not a parity mode: stated tolerance 1e-5 of the trace
+                           peak.  PF_ENGINE_OPS rejects it (PF_E_UNSUPPORTED).                    */
 };
 
 /* One 1-D grid: a single simulation, one sweep member, or one rank's slab of a long grid.
@@ -131,6 +141,9 @@ int pf_probe_record(const PfGrid *g, int n, void *stream);  /* Solver_Engine.py:
 /* CubicEquationSolver.solve root[0] (CubicEquationSolver.py:29-105) for n polynomials,
  * coeffs = [n][4] (a,b,c,d) device, root0 = [n] device                                          */
 int pf_cubic_root0(const double *coeffs, double *root0, int n, void *stream);
+/* same contract, PF_F_NEWTON arithmetic: Newton iteration where a, b >= 0, c > 0, d < 0 (one positive
+ * root, monotone convergence from -d/c), the closed form elsewhere                                */
+int pf_cubic_root0_newton(const double *coeffs, double *root0, int n, void *stream);
 /* every root, as CubicEquationSolver.solve returns them: roots = [n][3][2] (re, im) device,
  * nroots = [n] device (1 linear, 2 quadratic, 3 cubic)                                          */
 int pf_cubic_solve(const double *coeffs, double *roots, int *nroots, int n, void *stream);

@@ -288,9 +288,10 @@ def grid_scalars(V, P):
                 nl_den0=P.permit_0 * float(np.sqrt(1.2)), nl_den1=P.permit_0 * V.chi3Stat)
 
 
-def grid_flags(P, fma=False):
+def grid_flags(P, fma=False, fp32=False, newton=False):
     return ((nat.PF_F_TFSF if P.TFSF else 0) | (nat.PF_F_CPML_M if P.CPMLXm else 0) |
-            (nat.PF_F_CPML_P if P.CPMLXp else 0) | (nat.PF_F_FMA if fma else 0))
+            (nat.PF_F_CPML_P if P.CPMLXp else 0) | (nat.PF_F_FMA if fma else 0) | (nat.PF_F_FP32 if fp32 else 0) |
+            (nat.PF_F_NEWTON if newton else 0))
 
 
 def _host_arrays(V, C_V, pprev):

@@ -35,6 +35,17 @@ def solve_many(coeffs):
     return out, nr
 
 
+def root0_many(coeffs, newton=False):
+    """root[0] of every polynomial of coeffs [n, 4] (what the nonlinear path consumes).  newton=True: the
+    PF_F_NEWTON variant (Newton iteration where a, b >= 0, c > 0, d < 0; the closed form elsewhere)."""
+    torch = nat.require_cuda()
+    co = torch.as_tensor(np.ascontiguousarray(coeffs, dtype=np.float64), device="cuda").reshape(-1, 4)
+    out = torch.zeros(co.shape[0], dtype=torch.float64, device="cuda")
+    fn = nat.lib().pf_cubic_root0_newton if newton else nat.lib().pf_cubic_root0
+    nat.check(fn(co.data_ptr(), out.data_ptr(), co.shape[0], nat.current_stream_ptr()), "pf_cubic_root0")
+    return out.cpu().numpy()
+
+
 def solve(a, b=None, c=None, d=None):
     """``solve(a, b, c, d)`` like the reference; ``solve(CS)`` with CS = CubicSolver(...) also works."""
     if b is None:

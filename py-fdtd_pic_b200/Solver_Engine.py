@@ -25,6 +25,11 @@ from . import genericStability as gStab
 
 ENGINE = "auto"      # "auto" | "tile" | "ops"
 USE_FMA = False      # True: allow FMA contraction in the kernels (PF_F_FMA; not bit-identical)
+CUBIC = "closed"     # "closed": the reference's closed-form cubic root (CubicEquationSolver.solve);
+                     # "newton": PF_F_NEWTON, the same root by Newton iteration (~3x fewer instructions; differs by the
+                     # closed form's cancellation error, <= 1e-10 absolute on Acubic)
+USE_FP32 = False     # True: optional single-precision mode of the tile engine (PF_F_FP32; stated tolerance 1e-5
+                     # of the trace peak -- not a parity mode; arrays stay fp64 at the boundary)
 LAST_RUN_INFO = {}   # engine used, bytes moved, kernel launches of the last pass (for tests / bench)
 
 
@@ -143,7 +148,9 @@ def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=F
     Jx = V.Jx if np.any(V.Jx != 0.0) else None
     engine, canon = _pick_engine(P, arrs, Jx, probe_idx)
     scal = BaseFDTD11.grid_scalars(V, P)
-    flags = BaseFDTD11.grid_flags(P, USE_FMA)
+    flags = BaseFDTD11.grid_flags(P, USE_FMA, USE_FP32, CUBIC == "newton")
+    if USE_FP32 and engine != nat.PF_ENGINE_TILE:
+        raise ValueError("USE_FP32 is a mode of the tile engine; this grid needs the general per-op engine")
     if canon is not None:
         scal.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
         flags |= nat.PF_F_CANONICAL

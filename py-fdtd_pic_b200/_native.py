@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("PYFDTD_B200_LIB") or os.path.join(HERE, "libpyfdtd_b2
 
 PF_FREE, PF_LORENTZ, PF_NL = 0, 1, 2
 PF_ENGINE_OPS, PF_ENGINE_TILE = 0, 1
-PF_F_TFSF, PF_F_CPML_M, PF_F_CPML_P, PF_F_CANONICAL, PF_F_FMA = 1, 2, 4, 8, 16
+PF_F_TFSF, PF_F_CPML_M, PF_F_CPML_P, PF_F_CANONICAL, PF_F_FMA, PF_F_FP32, PF_F_NEWTON = 1, 2, 4, 8, 16, 32, 64
 
 _dp = c_void_p  # device pointers travel as integers
 
@@ -75,6 +75,7 @@ SYMBOLS = {
     "pf_nonlin_ex_update": (c_int, [_G, c_void_p]),
     "pf_probe_record": (c_int, [_G, c_int, c_void_p]),
     "pf_cubic_root0": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "pf_cubic_root0_newton": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "pf_cubic_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pf_run_pass": (c_int, [_G, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_batch": (c_int, [_G, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_size_t, c_void_p]),

@@ -36,6 +36,7 @@ int check_cuda(cudaError_t e, const char *what);
 // intrinsics, which nvcc never fuses.  Fused lets a*b+c become one DFMA (PF_F_FMA).
 // ---------------------------------------------------------------------------------------------
 struct Exact {
+    using real = double;
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
@@ -45,11 +46,23 @@ struct Exact {
     static __device__ __forceinline__ double nmad(double a, double b, double c) { return __dsub_rn(c, __dmul_rn(a, b)); }
 };
 struct Fused {
+    using real = double;
     static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
     static __device__ __forceinline__ double add(double a, double b) { return a + b; }
     static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
     static __device__ __forceinline__ double mad(double a, double b, double c) { return fma(a, b, c); }
     static __device__ __forceinline__ double nmad(double a, double b, double c) { return fma(-a, b, c); }
+};
+
+// PF_F_FP32: the on-chip state is advanced in single precision with contraction.  Not a parity mode:
+// reported against a stated 1e-5 tolerance (fields relative to the peak of the trace).
+struct Fast32 {
+    using real = float;
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float mad(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ float nmad(float a, float b, float c) { return fmaf(-a, b, c); }
 };
 
 // Correctly rounded x / d for a loop-invariant divisor d with r = RN(1/d) precomputed
@@ -112,6 +125,9 @@ struct CubicConsts {
     double g_ab;         // (2 b^3)/a^3 - (9 b c)/a^2   (first two terms of findG)
     double f3_27;        // f^3/27
     double b_3a;         // b/(3a)
+    double inv_c;        // RN(1/c): starting slope of the Newton variant
+    int newton;          // PF_F_NEWTON requested and a, b >= 0, c > 0 (see cubic_root0_newton)
+    int pad;
 };
 
 // Device-side constants (generic pf_cubic_root0 entry, where every polynomial has its own a,b,c).
@@ -134,6 +150,9 @@ __device__ __forceinline__ CubicConsts cubic_consts_dev(double a, double b, doub
     double f3 = __fma_rn(f2, k.f, f2lo * k.f);
     k.f3_27 = __ddiv_rn(f3, 27.0);
     k.b_3a = __ddiv_rn(b, __dmul_rn(3.0, a));
+    k.inv_c = 1.0 / c;
+    k.newton = 0;
+    k.pad = 0;
     return k;
 }
 
@@ -185,13 +204,38 @@ __device__ __forceinline__ double cubic_root0(const CubicConsts &k, double d)
     return __dsub_rn(__dmul_rn(__dmul_rn(2.0, j), cos(__ddiv_rn(kk, 3.0))), k.b_3a);
 }
 
+// PF_F_NEWTON: the same root by Newton iteration.  For a, b >= 0, c > 0 and d = -q^2 < 0 the polynomial
+// p(x) = a x^3 + b x^2 + c x - q^2 is increasing and convex on x > 0 with exactly one positive root -- the
+// root[0] the closed form returns in every branch (largest real root) -- and x0 = q^2/c >= root, so the
+// iteration descends monotonically.  1/p'(x) is carried along by its own Newton step (no division).
+// The result is the correctly converged root (|p| at rounding level); the reference's closed form loses
+// ~4 digits to cancellation in (S+U) - b/3a, so the two differ by up to ~1e-11 absolute, inside the
+// 1e-10 absolute tolerance Acubic is held to (its effect on Ex is below 1e-14 relative).
+__device__ __forceinline__ double cubic_root0_newton(const CubicConsts &k, double q2)
+{
+    const double a3 = 3.0 * k.a, b2 = 2.0 * k.b;
+    double x = q2 * k.inv_c, r = k.inv_c, step;
+    int it = 0;
+    do {
+        const double p = fma(fma(fma(k.a, x, k.b), x, k.c), x, -q2);
+        const double dp = fma(fma(a3, x, b2), x, k.c);
+        r = fma(r, fma(-dp, r, 1.0), r);
+        step = p * r;
+        x -= step;
+        ++it;
+        // superlinear: once a step is below 1e-10 x the error left after it is far below one ulp
+    } while (it < 3 || (it < 24 && fabs(step) > 1e-10 * x));
+    return x;
+}
+
 // Acubic of one cell: root0 of [cub, qua, one, -|Dx/eps0|^2] if |d| > 1e-8 else 0
 // (BaseFDTD11.py:793-853).
 __device__ __forceinline__ double acubic_cell(const CubicConsts &k, double dx, double eps0, double inv_eps0)
 {
     double q = fabs(div_const(dx, eps0, inv_eps0));
     double d = -__dmul_rn(q, q);
-    return (fabs(d) > 1e-8) ? cubic_root0(k, d) : 0.0;
+    if (!(fabs(d) > 1e-8)) return 0.0;
+    return k.newton ? cubic_root0_newton(k, -d) : cubic_root0(k, d);
 }
 
 // The whole nonlinear material law of one cell (AcubicFinder + NonLinExUpdate, BaseFDTD11.py:793-877),

@@ -38,6 +38,7 @@ CubicConsts cubic_consts_host(double a, double b, double c)
     k.g_ab = ((2.0 * std::pow(b, 3.0)) / std::pow(a, 3.0)) - ((9.0 * b * c) / std::pow(a, 2.0));
     k.f3_27 = std::pow(k.f, 3.0) / 27.0;
     k.b_3a = b / (3.0 * a);
+    k.inv_c = (c != 0.0) ? 1.0 / c : 0.0;
     return k;
 }
 
@@ -46,6 +47,7 @@ GridDev make_grid_dev(const PfGrid &g)
     GridDev d;
     d.g = g;
     d.k = cubic_consts_host(g.cub_a, g.cub_b, g.cub_c);
+    d.k.newton = (g.flags & PF_F_NEWTON) && g.cub_a >= 0.0 && g.cub_b >= 0.0 && g.cub_c > 0.0;
     d.inv_eps0 = 1.0 / g.eps0;
     return d;
 }

@@ -147,13 +147,16 @@ __global__ void k_probe(PfGrid g, int n)
     if (lp >= 0 && lp < g.L) g.probe_out[(size_t)p * g.probe_stride + n] = g.Ex[lp];
 }
 
-__global__ void __launch_bounds__(OPS_THREADS) k_cubic_root0(const double *__restrict__ co, double *__restrict__ out, int n)
+__global__ void __launch_bounds__(OPS_THREADS) k_cubic_root0(const double *__restrict__ co, double *__restrict__ out, int n,
+                                                            int newton)
 {
     int i = blockIdx.x * OPS_THREADS + threadIdx.x;
     if (i >= n) return;
     double a = co[4 * i], b = co[4 * i + 1], c = co[4 * i + 2], d = co[4 * i + 3];
     CubicConsts k = cubic_consts_dev(a, b, c);
-    out[i] = cubic_root0(k, d);
+    // PF_F_NEWTON only where its monotone-convergence conditions hold; the closed form otherwise
+    if (newton && a >= 0.0 && b >= 0.0 && c > 0.0 && d < 0.0) out[i] = cubic_root0_newton(k, -d);
+    else out[i] = cubic_root0(k, d);
 }
 
 // All roots of a x^3 + b x^2 + c x + d as CubicEquationSolver.solve returns them
@@ -355,7 +358,16 @@ int pf_cubic_root0(const double *coeffs, double *root0, int n, void *stream)
 {
     if (!coeffs || !root0 || n < 0) return set_err(PF_E_ARG, "pf_cubic_root0: bad arguments");
     if (n == 0) return PF_OK;
-    k_cubic_root0<<<ops_blocks(n), OPS_THREADS, 0, (cudaStream_t)stream>>>(coeffs, root0, n);
+    k_cubic_root0<<<ops_blocks(n), OPS_THREADS, 0, (cudaStream_t)stream>>>(coeffs, root0, n, 0);
+    PF_LAUNCH_CHECK("k_cubic_root0");
+    return PF_OK;
+}
+
+int pf_cubic_root0_newton(const double *coeffs, double *root0, int n, void *stream)
+{
+    if (!coeffs || !root0 || n < 0) return set_err(PF_E_ARG, "pf_cubic_root0_newton: bad arguments");
+    if (n == 0) return PF_OK;
+    k_cubic_root0<<<ops_blocks(n), OPS_THREADS, 0, (cudaStream_t)stream>>>(coeffs, root0, n, 1);
     PF_LAUNCH_CHECK("k_cubic_root0");
     return PF_OK;
 }

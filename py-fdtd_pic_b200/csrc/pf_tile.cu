@@ -66,11 +66,11 @@ struct TileDesc {
 };
 
 // shared memory carve-up (doubles): 7 per-cell coefficient arrays + edge exchange + source tables
-template <int MODE, int C>
+template <int MODE, int C, class R>
 struct TileSmem {
     static constexpr int NT = TILE_CELLS / C;
     static constexpr int N_ARR = 7;
-    static constexpr size_t bytes = sizeof(double) * ((size_t)N_ARR * TILE_CELLS + 2 * NT + 2 + 2 * TILE_KMAX);
+    static constexpr size_t bytes = sizeof(R) * ((size_t)N_ARR * TILE_CELLS + 2 * NT + 2 + 2 * TILE_KMAX);
 };
 
 // Shared memory is addressed as pf_smem[offset + index] with plain integer offsets: going through
@@ -78,9 +78,12 @@ struct TileSmem {
 // every barrier, on the critical path (ncu r1_final: ~10 % of the hot loop's stall samples).
 extern __shared__ double pf_smem[];
 
-// One 8-byte shared-memory slot addressed in the shared state space (ld.shared / st.shared with a
-// 32-bit address): reads and writes look like array accesses at the call sites.
-struct SmemSlot {
+// One shared-memory slot of the working precision R addressed in the shared state space (ld.shared /
+// st.shared with a 32-bit address): reads and writes look like array accesses at the call sites.
+template <class R>
+struct SmemSlot;
+template <>
+struct SmemSlot<double> {
     unsigned addr;
     __device__ __forceinline__ operator double() const
     {
@@ -93,17 +96,33 @@ struct SmemSlot {
         asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
     }
 };
+template <>
+struct SmemSlot<float> {
+    unsigned addr;
+    __device__ __forceinline__ operator float() const
+    {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void operator=(float v) const
+    {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+    }
+};
+template <class R>
 struct SmemArray {
     unsigned base;   // byte address in the shared window
-    __device__ __forceinline__ SmemSlot operator[](int i) const { return SmemSlot{base + 8u * (unsigned)i}; }
+    __device__ __forceinline__ SmemSlot<R> operator[](int i) const { return SmemSlot<R>{base + (unsigned)sizeof(R) * (unsigned)i}; }
 };
 
+template <class R>
 struct TileShared {
     // per-cell coefficient slots, [j][thread] order (each thread touches only its own slots)
-    SmemArray be, ce, cm;      // CPML recursive-convolution profiles (0 outside the CPML)
-    SmemArray cEu, cHu;        // update coefficient of the cell, 0 where the field is never updated
-    SmemArray cb, c2u;         // CPML field-correction coefficients, 0 outside / at the quirk cell
-    SmemArray edgeH, edgeE, srcE, srcH;
+    SmemArray<R> be, ce, cm;      // CPML recursive-convolution profiles (0 outside the CPML)
+    SmemArray<R> cEu, cHu;        // update coefficient of the cell, 0 where the field is never updated
+    SmemArray<R> cb, c2u;         // CPML field-correction coefficients, 0 outside / at the quirk cell
+    SmemArray<R> edgeH, edgeE, srcE, srcH;
 };
 
 // CTA-wide barrier usable from warp-uniform divergent code: every warp executes exactly two of
@@ -132,61 +151,124 @@ struct CellMasks {
 //                 is needed; only the material law is selected per cell.
 // -------------------------------------------------------------------------------------------------
 // Everything a time step needs besides the per-cell register arrays.
+template <class R>
 struct StepConsts {
-    double cEs, cHs, c2s, dtdz, eps0, inv_eps0, pA, pB, pC, den0, den1;
+    R cEs, cHs, c2s, dtdz, eps0, inv_eps0, pA, pB, pC, den0, den1;
+    // fp32 mode works in scaled variables (H/cH0, psi_E/cH0, D/eps0, P/eps0: everything O(E), the H update
+    // coefficient exactly 1) and carries the two coefficients that set the numerical wave speed as
+    // hi + lo pairs, so that no coefficient rounding accumulates as a phase drift.
+    R cEs_lo, dtdz_lo;
+    R pG, pK;            // fp32 mode: Lorentz ADE in difference form, G = 1 + B, K = 1 - A - B
+    R ca, cb, cc;        // fp32 mode: cubic coefficients
     int jsrc, jtfsf;
     bool wSrc;
     unsigned mSlab;
 };
 
+// PF_F_FP32 material law of one nonlinear cell.  The closed form the reference uses
+// (CubicEquationSolver.py:29-105) cancels ~4 digits in (S+U) - b/3a, which single precision cannot
+// afford, so the positive root of a x^3 + b x^2 + c x - q^2 (a, b >= 0, c > 0: increasing and convex
+// for x > 0) is found by Newton iteration from x0 = q^2/c >= root, which converges monotonically.
+struct NlResultF {
+    float a, e;
+};
+__device__ __forceinline__ NlResultF nl_material_law_f32(float ca, float cb, float cc, float dx, float inv_eps0,
+                                                        float den0, float den1)
+{
+    NlResultF r;
+    const float q = dx * inv_eps0;   // inv_eps0 = 1 in the scaled variables of the fp32 mode
+    const float d = q * q;
+    float x = 0.f;
+    if (d > 1e-8f) {
+        x = __fdividef(d, cc);
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const float p = fmaf(fmaf(fmaf(ca, x, cb), x, cc), x, -d);
+            const float dp = fmaf(fmaf(3.f * ca, x, 2.f * cb), x, cc);
+            x -= __fdividef(p, dp);
+        }
+    }
+    r.a = x;
+    r.e = __fdividef(dx, fmaf(den1, x, den0));
+    return r;
+}
+
 // One full time step (E half-step, barrier, H half-step) on the thread's C cells.
 //   pc = P^n (current polarisation), pq = P^{n-1}: the new P^{n+1} is written over pq, so the
 //   caller alternates (pc,pq) <-> (pq,pc) instead of shifting the history (no register moves).
-template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, bool SP>
-__device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts &K, const CubicConsts *kcp, int tid, int s,
-                                          double (&ex)[C], double (&hy)[C], double (&dx)[C], double (&pc)[C],
-                                          double (&pq)[C], double (&pe)[C], double (&ph)[C], double (&acub)[C],
-                                          double (&rbe)[C], double (&rce)[C], double (&rcm)[C])
+template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, bool SP, class R = typename A::real>
+__device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepConsts<R> &K, const CubicConsts *kcp, int tid, int s,
+                                          R (&ex)[C], R (&hy)[C], R (&dx)[C], R (&pc)[C],
+                                          R (&pq)[C], R (&pe)[C], R (&ph)[C], R (&acub)[C],
+                                          R (&rbe)[C], R (&rce)[C], R (&rcm)[C])
 {
     constexpr int NT = TILE_CELLS / C;
+    constexpr bool F32 = std::is_same<R, float>::value;
     constexpr bool HAS_MAT = (GEN || SLAB) && MODE != PF_FREE;
     constexpr bool ALL_MAT = !GEN && SLAB && MODE != PF_FREE;
     constexpr bool HAS_PML = GEN || PML;
     // ===== E half-step: history shift + polarisation, ADE_ExUpdate, CPML_Psi_e, source,
     //                    ADE_DxUpdate, ADE_ExCreate | AcubicFinder + NonLinExUpdate =====
-    double hl = S.edgeH[tid - 1];
+    R hl = S.edgeH[tid - 1];
     unsigned divkey = 0;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
-        const double dH = A::sub(hy[j], hl);
+        const R dH = A::sub(hy[j], hl);
         hl = hy[j];
-        double e = ex[j];
-        double pnow = 0.0;
+        R e = ex[j];
+        R pnow = R(0);
         if (MODE == PF_LORENTZ && HAS_MAT) {
             if (POL) {
-                pq[j] = A::add(A::add(A::mul(K.pA, pc[j]), A::mul(K.pB, pq[j])), A::mul(K.pC, e));
-                pnow = pq[j];
+                if constexpr (F32) {
+                    // difference form: pq holds v = P^n - P^{n-1};  v' = v - G v - K P + C E,  P' = P + v'
+                    R v = pq[j];
+                    v = A::nmad(K.pG, v, v);
+                    v = A::nmad(K.pK, pc[j], v);
+                    v = A::mad(K.pC, e, v);
+                    pq[j] = v;
+                    pc[j] = A::add(pc[j], v);
+                    pnow = pc[j];
+                } else {
+                    pq[j] = A::add(A::add(A::mul(K.pA, pc[j]), A::mul(K.pB, pq[j])), A::mul(K.pC, e));
+                    pnow = pq[j];
+                }
             } else {
                 pnow = pc[j];
             }
         }
-        if (!ALL_MAT) e = A::add(e, A::mul(dH, GEN ? S.cEu[j * NT + tid] : K.cEs));
+        if (!ALL_MAT) {
+            if constexpr (F32 && !GEN) e = A::add(e, A::mad(dH, K.cEs, A::mul(dH, K.cEs_lo)));
+            else e = A::mad(dH, GEN ? (R)S.cEu[j * NT + tid] : K.cEs, e);
+        }
         if (HAS_PML) {
-            const double b = GEN ? S.be[j * NT + tid] : rbe[j];
-            const double c = GEN ? S.ce[j * NT + tid] : rce[j];
-            const double psi = A::add(A::mul(b, pe[j]), A::mul(c, dH));
+            const R b = GEN ? (R)S.be[j * NT + tid] : rbe[j];
+            const R c = GEN ? (R)S.ce[j * NT + tid] : rce[j];
+            const R psi = A::mad(b, pe[j], A::mul(c, dH));
             pe[j] = psi;
-            if (!ALL_MAT) e = A::sub(e, A::mul(GEN ? S.cb[j * NT + tid] : K.cEs, psi));
+            if (!ALL_MAT) e = A::nmad(GEN ? (R)S.cb[j * NT + tid] : K.cEs, psi, e);
         }
         if (HAS_MAT) {
             if (MODE == PF_LORENTZ) {
-                dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));
-                const double em = div_const_fast(A::sub(dx[j], pnow), K.eps0, K.inv_eps0, divkey);
+                R em;
+                if constexpr (F32) {
+                    dx[j] = A::add(dx[j], A::mad(dH, K.dtdz, A::mul(dH, K.dtdz_lo)));
+                    em = A::sub(dx[j], pnow);
+                } else {
+                    dx[j] = A::mad(dH, K.dtdz, dx[j]);
+                    em = div_const_fast(A::sub(dx[j], pnow), K.eps0, K.inv_eps0, divkey);
+                }
                 e = (!GEN || ((K.mSlab >> j) & 1)) ? em : e;
+            } else if constexpr (F32) {
+                if (!GEN || ((K.mSlab >> j) & 1)) {
+                    dx[j] = A::add(dx[j], A::mad(dH, K.dtdz, A::mul(dH, K.dtdz_lo)));
+                    const NlResultF nl = nl_material_law_f32(K.ca, K.cb, K.cc, dx[j], K.inv_eps0, K.den0, K.den1);
+                    acub[j] = nl.a;
+                    e = nl.e;
+                }
             } else if (!GEN) {
-                dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));      // the material law of all C cells follows the loop
+                dx[j] = A::mad(dH, K.dtdz, dx[j]);      // the material law of all C cells follows the loop
             } else if ((K.mSlab >> j) & 1) {
-                dx[j] = A::add(dx[j], A::mul(dH, K.dtdz));
+                dx[j] = A::mad(dH, K.dtdz, dx[j]);
                 const NlResult nl = nl_material_law(kcp, dx[j], K.eps0, K.inv_eps0, K.den0, K.den1);
                 acub[j] = nl.a;
                 e = nl.e;
@@ -194,7 +276,7 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
         }
         ex[j] = e;
     }
-    if (MODE == PF_NL && ALL_MAT) {
+    if constexpr (MODE == PF_NL && ALL_MAT && !F32) {
         NlVec<C> dv;
 #pragma unroll
         for (int j = 0; j < C; ++j) dv.v[j] = dx[j];
@@ -207,15 +289,17 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
 #ifdef PF_EXPERIMENT_NO_GUARD   // timing experiment only: cost of the division-range guard
     if (false) {
 #else
-    if (MODE == PF_LORENTZ && HAS_MAT && __any_sync(0xffffffffu, !div_const_in_range(divkey))) {
+    if (!F32 && MODE == PF_LORENTZ && HAS_MAT && __any_sync(0xffffffffu, !div_const_in_range(divkey))) {
 #endif
         // some cell's (Dx - P) was zero, in the denormal range or non-finite: redo those divisions
         // exactly (rare once the wave has arrived; integer tests only for the zero case)
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            if (!GEN || ((K.mSlab >> j) & 1)) {
-                const double x = A::sub(dx[j], POL ? pq[j] : pc[j]);
-                ex[j] = div_const_fix(x, K.eps0, K.inv_eps0, ex[j]);
+            if constexpr (!F32) {
+                if (!GEN || ((K.mSlab >> j) & 1)) {
+                    const double x = A::sub(dx[j], POL ? pq[j] : pc[j]);
+                    ex[j] = div_const_fix(x, K.eps0, K.inv_eps0, ex[j]);
+                }
             }
         }
     }
@@ -237,18 +321,18 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
     // ===== H half-step: TF/SF correction, ADE_HyUpdate, CPML_Psi_m =====
     // the neighbour's Ex is requested first and consumed last (cell C-1), behind the cells that only
     // need the thread's own Ex, so the shared-memory latency is covered
-    const double exr = S.edgeE[tid + 1];
+    const R exr = S.edgeE[tid + 1];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
-        double h = hy[j];
-        const double dE = A::sub((j == C - 1) ? exr : ex[(j + 1) % C], ex[j]);
-        h = A::add(h, A::mul(dE, GEN ? S.cHu[j * NT + tid] : K.cHs));
+        R h = hy[j];
+        const R dE = A::sub((j == C - 1) ? exr : ex[(j + 1) % C], ex[j]);
+        h = A::mad(dE, GEN ? (R)S.cHu[j * NT + tid] : K.cHs, h);
         if (HAS_PML) {
-            const double b = GEN ? S.be[j * NT + tid] : rbe[j];
-            const double c = GEN ? S.cm[j * NT + tid] : rcm[j];
-            const double psi = A::add(A::mul(b, ph[j]), A::mul(c, dE));
+            const R b = GEN ? (R)S.be[j * NT + tid] : rbe[j];
+            const R c = GEN ? (R)S.cm[j * NT + tid] : rcm[j];
+            const R psi = A::mad(b, ph[j], A::mul(c, dE));
             ph[j] = psi;
-            h = A::add(h, A::mul(GEN ? S.c2u[j * NT + tid] : K.c2s, psi));
+            h = A::mad(GEN ? (R)S.c2u[j * NT + tid] : K.c2s, psi, h);
         }
         hy[j] = h;
     }
@@ -266,16 +350,20 @@ __device__ __forceinline__ void tile_step(const TileShared &S, const StepConsts 
 //                 exactly 0 turns its term into an exact no-op (x + y*0 == x), so no per-cell branch
 //                 is needed; only the material law is selected per cell.
 // -------------------------------------------------------------------------------------------------
-template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML>
-__device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &S, const CellMasks &M,
+template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, class R = typename A::real>
+__device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R> &S, const CellMasks &M,
                                           int tid, int lz0, int ks, int src, int nabs0)
 {
     constexpr int NT = TILE_CELLS / C;
+    constexpr bool F32 = std::is_same<R, float>::value;
     constexpr bool HAS_MAT = (GEN || SLAB) && MODE != PF_FREE;   // material arrays present
     constexpr bool HAS_PML = GEN || PML;
     const PfGrid &g = TG.d.g;
     const unsigned mSlab = M.slab;
-    double ex[C], hy[C], dx[C], pa[C], pb[C], pe[C], ph[C], acub[C], rbe[C], rce[C], rcm[C];
+    // scaled variables of the fp32 mode (identity scales otherwise): H' = H sH, psi_E' = psi_E sH, D' = D sD, P' = P sD
+    const double sH = F32 ? 1.0 / g.cH0 : 1.0, uH = F32 ? g.cH0 : 1.0;
+    const double sD = F32 ? TG.d.inv_eps0 : 1.0, uD = F32 ? g.eps0 : 1.0;
+    R ex[C], hy[C], dx[C], pa[C], pb[C], pe[C], ph[C], acub[C], rbe[C], rce[C], rcm[C];
 
     // ---- load ---------------------------------------------------------------------------------
     {
@@ -285,7 +373,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
         for (int j = 0; j < C; ++j) {
             bool v = !GEN || ((M.valid >> j) & 1);
             ex[j] = v ? inEx[lz0 + j] : 0.0;
-            hy[j] = v ? inHy[lz0 + j] : 0.0;
+            hy[j] = F32 ? (v ? inHy[lz0 + j] * sH : 0.0) : (v ? inHy[lz0 + j] : 0.0);
         }
         if (HAS_PML) {
             const double *__restrict__ inPe = TG.buf[src][S_PSIE];
@@ -294,13 +382,13 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
             for (int j = 0; j < C; ++j) {
                 bool e_ = !GEN || ((M.pmlE >> j) & 1), h_ = !GEN || ((M.pmlH >> j) & 1);
                 int lz = lz0 + j;
-                pe[j] = e_ ? inPe[lz] : 0.0;
+                pe[j] = F32 ? (e_ ? inPe[lz] * sH : 0.0) : (e_ ? inPe[lz] : 0.0);
                 ph[j] = h_ ? inPh[lz] : 0.0;
                 const double b = (e_ || h_) ? g.beX[lz] : 0.0, c1 = e_ ? g.ceX[lz] : 0.0, c2 = h_ ? g.cmY[lz] : 0.0;
                 if (GEN) {
-                    S.be[j * NT + tid] = b;
-                    S.ce[j * NT + tid] = c1;
-                    S.cm[j * NT + tid] = c2;
+                    S.be[j * NT + tid] = (R)b;
+                    S.ce[j * NT + tid] = (R)c1;
+                    S.cm[j * NT + tid] = (R)c2;
                 } else {
                     rbe[j] = b; rce[j] = c1; rcm[j] = c2;
                 }
@@ -309,15 +397,19 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
         if (HAS_MAT) {
             const double *__restrict__ inDx = TG.buf[src][S_DX];
 #pragma unroll
-            for (int j = 0; j < C; ++j) dx[j] = (!GEN || ((mSlab >> j) & 1)) ? inDx[lz0 + j] : 0.0;
+            for (int j = 0; j < C; ++j) {
+                const double d0 = (!GEN || ((mSlab >> j) & 1)) ? inDx[lz0 + j] : 0.0;
+                dx[j] = F32 ? d0 * sD : d0;
+            }
             if (MODE == PF_LORENTZ) {
                 const double *__restrict__ inP = TG.buf[src][S_P];
                 const double *__restrict__ inPp = TG.buf[src][S_PP];
 #pragma unroll
                 for (int j = 0; j < C; ++j) {
                     bool sl = !GEN || ((mSlab >> j) & 1);
-                    pa[j] = sl ? inP[lz0 + j] : 0.0;
-                    pb[j] = sl ? inPp[lz0 + j] : 0.0;
+                    const double p0 = sl ? inP[lz0 + j] : 0.0, p1 = sl ? inPp[lz0 + j] : 0.0;
+                    pa[j] = F32 ? p0 * sD : p0;
+                    pb[j] = F32 ? (p0 - p1) * sD : p1;   // fp32 mode carries P^n - P^{n-1} (difference form)
                 }
             }
         }
@@ -325,22 +417,28 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
 #pragma unroll
             for (int j = 0; j < C; ++j) {
                 const bool sl = (mSlab >> j) & 1, q = (M.quirk >> j) & 1;
-                const double cE = sl ? g.cE1 : g.cE0, cH = sl ? g.cH1 : g.cH0;
-                S.cEu[j * NT + tid] = ((M.updE >> j) & 1) ? cE : 0.0;
-                S.cHu[j * NT + tid] = ((M.updH >> j) & 1) ? cH : 0.0;
-                S.cb[j * NT + tid] = (((M.pmlE >> j) & 1) && !q) ? cE : 0.0;
-                S.c2u[j * NT + tid] = (((M.pmlH >> j) & 1) && !q) ? g.c2_pml : 0.0;
+                const double cE = (sl ? g.cE1 : g.cE0) * uH, cH = (sl ? g.cH1 : g.cH0) * sH;
+                S.cEu[j * NT + tid] = (R)(((M.updE >> j) & 1) ? cE : 0.0);
+                S.cHu[j * NT + tid] = (R)(((M.updH >> j) & 1) ? cH : 0.0);
+                S.cb[j * NT + tid] = (R)((((M.pmlE >> j) & 1) && !q) ? cE : 0.0);
+                S.c2u[j * NT + tid] = (R)((((M.pmlH >> j) & 1) && !q) ? g.c2_pml * sH : 0.0);
             }
         }
         if (MODE == PF_NL) {
 #pragma unroll
-            for (int j = 0; j < C; ++j) acub[j] = 0.0;
+            for (int j = 0; j < C; ++j) acub[j] = R(0);
         }
     }
-    StepConsts K;
-    K.cEs = SLAB ? g.cE1 : g.cE0; K.cHs = SLAB ? g.cH1 : g.cH0; K.c2s = g.c2_pml;
-    K.dtdz = g.dt_over_dz; K.eps0 = g.eps0; K.inv_eps0 = TG.d.inv_eps0;
-    K.pA = g.polA; K.pB = g.polB; K.pC = g.polC; K.den0 = g.nl_den0; K.den1 = g.nl_den1;
+    StepConsts<R> K;
+    {
+        const double cE = (SLAB ? g.cE1 : g.cE0) * uH, dd = g.dt_over_dz * uH * sD;
+        K.cEs = cE; K.cHs = (SLAB ? g.cH1 : g.cH0) * sH; K.c2s = g.c2_pml * sH;
+        K.dtdz = dd; K.eps0 = g.eps0; K.inv_eps0 = F32 ? 1.0 : TG.d.inv_eps0;
+        K.cEs_lo = (R)(cE - (double)K.cEs); K.dtdz_lo = (R)(dd - (double)K.dtdz);
+        K.pA = g.polA; K.pB = g.polB; K.pC = g.polC * sD; K.den0 = g.nl_den0 * sD; K.den1 = g.nl_den1 * sD;
+    }
+    K.pG = (R)(1.0 + g.polB); K.pK = (R)((1.0 - g.polA) - g.polB);
+    K.ca = (R)g.cub_a; K.cb = (R)g.cub_b; K.cc = (R)g.cub_c;
     K.jsrc = M.jsrc; K.jtfsf = M.jtfsf; K.mSlab = mSlab;
     K.wSrc = __any_sync(0xffffffffu, M.jsrc >= 0 || M.jtfsf >= 0);
     const CubicConsts *kc = &TG.d.k;
@@ -349,7 +447,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
 
     auto probes = [&](int s) {   // Solver_Engine.probeSim: Ex after the step
         if (wProbe && pj0 >= 0) {
-            double v = 0.0;
+            R v = R(0);
 #pragma unroll
             for (int j = 0; j < C; ++j) v = (j == pj0) ? ex[j] : v;
             g.probe_out[M.po0 + nabs0 + s] = v;
@@ -363,7 +461,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
 
     S.edgeH[tid] = hy[C - 1];
     cta_sync();
-    constexpr bool SWAP = MODE == PF_LORENTZ && HAS_MAT && POL;   // P history alternates between pa and pb
+    constexpr bool SWAP = MODE == PF_LORENTZ && HAS_MAT && POL && !F32;   // P history alternates between pa and pb
     bool swapped = false;   // true: current P is in pb, previous in pa
     // The time loop exists twice: warps that own a source cell or a probe run the version with those
     // (warp-uniform) tests, every other warp a loop with nothing in it but the update itself.
@@ -397,14 +495,14 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
     double *__restrict__ outHy = TG.buf[dst][S_HY];
 #pragma unroll
     for (int j = 0; j < C; ++j)
-        if ((st >> j) & 1) { outEx[lz0 + j] = ex[j]; outHy[lz0 + j] = hy[j]; }
+        if ((st >> j) & 1) { outEx[lz0 + j] = ex[j]; outHy[lz0 + j] = F32 ? hy[j] * uH : hy[j]; }
     if (HAS_PML) {
         double *__restrict__ outPe = TG.buf[dst][S_PSIE];
         double *__restrict__ outPh = TG.buf[dst][S_PSIH];
         const unsigned se = GEN ? (st & M.pmlE) : st, sh = GEN ? (st & M.pmlH) : st;
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            if ((se >> j) & 1) outPe[lz0 + j] = pe[j];
+            if ((se >> j) & 1) outPe[lz0 + j] = F32 ? pe[j] * uH : pe[j];
             if ((sh >> j) & 1) outPh[lz0 + j] = ph[j];
         }
     }
@@ -413,15 +511,20 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
         double *__restrict__ outDx = TG.buf[dst][S_DX];
 #pragma unroll
         for (int j = 0; j < C; ++j)
-            if ((sm >> j) & 1) outDx[lz0 + j] = dx[j];
+            if ((sm >> j) & 1) outDx[lz0 + j] = F32 ? dx[j] * uD : dx[j];
         if (MODE == PF_LORENTZ) {
             double *__restrict__ outP = TG.buf[dst][S_P];
             double *__restrict__ outPp = TG.buf[dst][S_PP];
 #pragma unroll
             for (int j = 0; j < C; ++j)
                 if ((sm >> j) & 1) {
-                    outP[lz0 + j] = swapped ? pb[j] : pa[j];
-                    outPp[lz0 + j] = swapped ? pa[j] : pb[j];
+                    if (F32) {
+                        outP[lz0 + j] = pa[j] * uD;
+                        outPp[lz0 + j] = ((double)pa[j] - (double)pb[j]) * uD;
+                    } else {
+                        outP[lz0 + j] = swapped ? pb[j] : pa[j];
+                        outPp[lz0 + j] = swapped ? pa[j] : pb[j];
+                    }
                 }
         }
         if (MODE == PF_NL && g.Acubic) {
@@ -432,31 +535,39 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared &
     }
 }
 
+#ifndef PF_TILE_MINBLOCKS_F32
+#define PF_TILE_MINBLOCKS_F32 2
+#endif
+template <class A>
+constexpr int tile_minblocks() { return std::is_same<typename A::real, float>::value ? PF_TILE_MINBLOCKS_F32 : PF_TILE_MINBLOCKS; }
+
 template <int MODE, bool POL, int C, class A>
-__global__ void __launch_bounds__(TILE_CELLS / C, PF_TILE_MINBLOCKS)
+__global__ void __launch_bounds__(TILE_CELLS / C, tile_minblocks<A>())
 k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, int src, int n_done,
        int n0, int ksteps, int halo)
 {
+    using R = typename A::real;
+    constexpr unsigned RB = (unsigned)sizeof(R);
     constexpr int NT = TILE_CELLS / C;
     constexpr unsigned ALL = (1u << C) - 1u;
-    TileShared S;
+    TileShared<R> S;
     unsigned sbase = (unsigned)__cvta_generic_to_shared(pf_smem);
     // keep the window address in an ordinary (per-thread) register: as a uniform value it is
     // re-derived from SR_CgaCtaId after every potentially divergent region of the time loop
     asm volatile("xor.b32 %0, %0, %1;" : "+r"(sbase) : "r"(threadIdx.x & 0u));
     S.be.base = sbase;
-    S.ce.base = S.be.base + 8u * TILE_CELLS;
-    S.cm.base = S.ce.base + 8u * TILE_CELLS;
-    S.cEu.base = S.cm.base + 8u * TILE_CELLS;
-    S.cHu.base = S.cEu.base + 8u * TILE_CELLS;
-    S.cb.base = S.cHu.base + 8u * TILE_CELLS;
-    S.c2u.base = S.cb.base + 8u * TILE_CELLS;
+    S.ce.base = S.be.base + RB * TILE_CELLS;
+    S.cm.base = S.ce.base + RB * TILE_CELLS;
+    S.cEu.base = S.cm.base + RB * TILE_CELLS;
+    S.cHu.base = S.cEu.base + RB * TILE_CELLS;
+    S.cb.base = S.cHu.base + RB * TILE_CELLS;
+    S.c2u.base = S.cb.base + RB * TILE_CELLS;
     // edgeH[-1] and edgeE[NT] are zero pads: the first / last thread reads its missing neighbour
     // without a per-step test
-    S.edgeH.base = S.c2u.base + 8u * TILE_CELLS + 8u;
-    S.edgeE.base = S.edgeH.base + 8u * NT;
-    S.srcE.base = S.edgeE.base + 8u * NT + 8u;
-    S.srcH.base = S.srcE.base + 8u * TILE_KMAX;
+    S.edgeH.base = S.c2u.base + RB * TILE_CELLS + RB;
+    S.edgeE.base = S.edgeH.base + RB * NT;
+    S.srcE.base = S.edgeE.base + RB * NT + RB;
+    S.srcH.base = S.srcE.base + RB * TILE_KMAX;
 
     const TileDesc td = tiles[blockIdx.x];
     const TileGrid &TG = grids[td.grid];
@@ -505,12 +616,12 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
             else { M.pj1 = j; M.po1 = (size_t)p * g.probe_stride; }
         }
     }
-    if (tid == 0) { S.edgeH[-1] = 0.0; S.edgeE[NT] = 0.0; }
+    if (tid == 0) { S.edgeH[-1] = R(0); S.edgeE[NT] = R(0); }
     // source tables of this launch's steps (CTA-uniform load)
     const int nabs0 = n0 + n_done;
     for (int s = tid; s < ks; s += NT) {
-        S.srcE[s] = g.srcE[nabs0 + s];
-        S.srcH[s] = (flags & PF_F_TFSF) ? g.srcH[nabs0 + s] : 0.0;
+        S.srcE[s] = (R)g.srcE[nabs0 + s];
+        S.srcH[s] = (R)((flags & PF_F_TFSF) ? g.srcH[nabs0 + s] * (std::is_same<R, float>::value ? 1.0 / g.cH0 : 1.0) : 0.0);
     }
 
     // ---- warp class: 0 vacuum, 1 slab, 2 CPML, 3 slab+CPML, 4 mixed, 5 dead ------------------
@@ -532,8 +643,8 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     case 3: tile_body<MODE, POL, C, A, false, true, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
     case 5:
         // nothing to compute: publish zero edges once, then only keep the CTA's barrier count
-        S.edgeH[tid] = 0.0;
-        S.edgeE[tid] = 0.0;
+        S.edgeH[tid] = R(0);
+        S.edgeE[tid] = R(0);
         cta_sync();
         for (int s = 0; s < ks; ++s) { cta_sync(); cta_sync(); }
         break;
@@ -646,23 +757,27 @@ struct ProfScope {
     }
 };
 
-template <int MODE, bool POL, int C>
-static int launch_tile(bool fma, int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
-                       int n0, int ks, int halo, cudaStream_t st)
+enum { ARITH_EXACT = 0, ARITH_FUSED = 1, ARITH_FP32 = 2 };
+
+template <int MODE, bool POL, int C, class A>
+static int launch_tile_a(int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
+                         int n0, int ks, int halo, cudaStream_t st)
 {
-    size_t sm = TileSmem<MODE, C>::bytes;
+    const size_t sm = TileSmem<MODE, C, typename A::real>::bytes;
     ProfScope prof(st);
-    if (fma) {
-        static bool set = false;
-        if (!set) { PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, Fused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); set = true; }
-        k_tile<MODE, POL, C, Fused><<<n_tiles, TILE_CELLS / C, sm, st>>>(dg, dt, src, n_done, n0, ks, halo);
-    } else {
-        static bool set = false;
-        if (!set) { PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, Exact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); set = true; }
-        k_tile<MODE, POL, C, Exact><<<n_tiles, TILE_CELLS / C, sm, st>>>(dg, dt, src, n_done, n0, ks, halo);
-    }
+    static bool set = false;
+    if (!set) { PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); set = true; }
+    k_tile<MODE, POL, C, A><<<n_tiles, TILE_CELLS / C, sm, st>>>(dg, dt, src, n_done, n0, ks, halo);
     PF_LAUNCH_CHECK("k_tile");
     return 0;
+}
+
+template <int MODE, bool POL, int C>
+static int launch_tile(int arith, int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
+                       int n0, int ks, int halo, cudaStream_t st)
+{
+    if (arith == ARITH_FUSED) return launch_tile_a<MODE, POL, C, Fused>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    return launch_tile_a<MODE, POL, C, Exact>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
 }
 
 constexpr int TILE_C = PF_TILE_C;            // cells per thread, Lorentz and nonlinear modes
@@ -676,9 +791,23 @@ constexpr int TILE_C_FREE = PF_TILE_C_FREE;
 
 // wide = true: grids with (almost) no CPML cells, e.g. the pieces of a long grid -- 4 cells per thread
 // (measured 733 vs 684 Gcell-updates/s on a 1e8-cell Lorentz grid; the CPML-heavy sweep members prefer 2).
-static int launch_tile_mode(int mode, int do_pol, bool fma, bool wide, int n_tiles, const TileGrid *dg, const TileDesc *dt,
+#ifndef PF_TILE_C_F32
+#define PF_TILE_C_F32 4
+#endif
+#ifndef PF_TILE_C_F32_FREE
+#define PF_TILE_C_F32_FREE 8
+#endif
+static int launch_tile_mode(int mode, int do_pol, int fma, bool wide, int n_tiles, const TileGrid *dg, const TileDesc *dt,
                             int src, int n_done, int n0, int ks, int halo, cudaStream_t st)
 {
+    if (fma == ARITH_FP32) {   // PF_F_FP32: one geometry per mode
+        if (mode == PF_FREE) return launch_tile_a<PF_FREE, false, PF_TILE_C_F32_FREE, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        if (mode == PF_LORENTZ)
+            return do_pol ? launch_tile_a<PF_LORENTZ, true, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
+                          : launch_tile_a<PF_LORENTZ, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        if (mode == PF_NL) return launch_tile_a<PF_NL, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        return set_err(PF_E_ARG, "bad mode %d", mode);
+    }
     if (mode == PF_FREE) return launch_tile<PF_FREE, false, TILE_C_FREE>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
     if (mode == PF_LORENTZ) {
         if (wide)
@@ -689,6 +818,25 @@ static int launch_tile_mode(int mode, int do_pol, bool fma, bool wide, int n_til
     }
     if (mode == PF_NL) return launch_tile<PF_NL, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
     return set_err(PF_E_ARG, "bad mode %d", mode);
+}
+
+// arithmetic class of a launch: PF_F_FP32 on any grid selects single precision, else PF_F_FMA contraction
+static int arith_of(const PfGrid *grids, int n, int mode, int *arith)
+{
+    int a = ARITH_EXACT;
+    for (int m = 0; m < n; ++m) {
+        const PfGrid &g = grids[m];
+        if (g.flags & PF_F_FP32) {
+            // the fp32 cubic root is a Newton iteration that needs an increasing, convex polynomial
+            if (mode == PF_NL && !(g.cub_a >= 0.0 && g.cub_b >= 0.0 && g.cub_c > 0.0))
+                return set_err(PF_E_UNSUPPORTED, "PF_F_FP32: nonlinear mode needs cub >= 0, qua >= 0, one > 0");
+            a = ARITH_FP32;
+        } else if ((g.flags & PF_F_FMA) && a == ARITH_EXACT) {
+            a = ARITH_FUSED;
+        }
+    }
+    *arith = a;
+    return 0;
 }
 
 // fraction of CPML cells over a set of grids < 1/8 ?
@@ -748,7 +896,11 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
     char *sbase = (char *)scratch;
     size_t off = plan.off_state;
     int max_steps = 0;
-    bool fma = false;
+    int fma = ARITH_EXACT;
+    {
+        int rc = arith_of(grids, n, mode, &fma);
+        if (rc) return rc;
+    }
     const int na = n_state_arrays(mode);
     for (int m = 0; m < n; ++m) {
         const PfGrid &g = grids[m];
@@ -766,7 +918,6 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
         t.nsteps = nsteps[m];
         t.pad = 0;
         max_steps = std::max(max_steps, nsteps[m]);
-        fma = fma || (g.flags & PF_F_FMA);
         int ntile = (g.L + W - 1) / W;
         for (int i = 0; i < ntile; ++i) ht.push_back(TileDesc{m, i * W - halo});
     }
@@ -834,8 +985,11 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
     const size_t off_tiles = align_up(sizeof(TileGrid) * (size_t)n, 256);
     TileGrid *dg = (TileGrid *)scratch;
     TileDesc *dt = (TileDesc *)((char *)scratch + off_tiles);
-    bool fma = false;
-    for (int m = 0; m < n; ++m) fma = fma || (src[m].flags & PF_F_FMA);
+    int fma = ARITH_EXACT;
+    {
+        int rc = arith_of(src, n, mode, &fma);
+        if (rc) return rc;
+    }
     if (bc.scratch == scratch && bc.n == n && bc.mode == mode && bc.halo == halo) {
         if (same_grids(bc.a, src, n) && same_grids(bc.b, dst, n))
             return launch_tile_mode(mode, do_pol, fma, bc.wide, bc.n_tiles, dg, dt, 0, 0, n0, ks, halo, st);
@@ -949,6 +1103,8 @@ int pf_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, int e
     if (!g || nsteps < 0) return set_err(PF_E_ARG, "pf_run_pass: bad arguments");
     if (mode < PF_FREE || mode > PF_NL) return set_err(PF_E_ARG, "pf_run_pass: bad mode %d", mode);
     cudaStream_t st = (cudaStream_t)stream;
+    if (engine == PF_ENGINE_OPS && (g->flags & PF_F_FP32))
+        return set_err(PF_E_UNSUPPORTED, "PF_F_FP32 is a mode of the tile engine only");
     if (engine == PF_ENGINE_OPS) return ops_run_pass(g, mode, do_pol, n0, nsteps, snap_out, snap_interval, snap_rows, st);
     if (engine == PF_ENGINE_TILE)
         return tile_run(g, 1, mode, do_pol, n0, &nsteps, 0, snap_out, snap_interval, snap_rows, scratch, scratch_bytes, st);

@@ -141,7 +141,8 @@ class LongGrid:
     """A long Lorentz / dielectric / nonlinear grid decomposed into pieces on this rank's GPU."""
 
     def __init__(self, Lg, *, mode, pw, mf, mr, nzsrc, dz, dt, courantNo, scalars, pml_profiles, srcE, srcH,
-                 probes=(), tfsf=True, k=64, rank=0, world_size=1, fma=False, max_piece=1 << 27, device=None):
+                 probes=(), tfsf=True, k=64, rank=0, world_size=1, fma=False, fp32=False, newton=False, max_piece=1 << 27,
+                 device=None):
         torch = nat.require_cuda()
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
@@ -160,7 +161,7 @@ class LongGrid:
         self.probe_out = torch.zeros((max(len(probes), 1), T), **f64)
         self.probes = probes
         flags = ((nat.PF_F_TFSF if tfsf else 0) | nat.PF_F_CPML_M | nat.PF_F_CPML_P | nat.PF_F_CANONICAL |
-                 (nat.PF_F_FMA if fma else 0))
+                 (nat.PF_F_FMA if fma else 0) | (nat.PF_F_FP32 if fp32 else 0) | (nat.PF_F_NEWTON if newton else 0))
         n_arr = 7 if mode == "lorentz" else (5 if mode == "nl" else 4)
         self.names = STATE_ALL[:n_arr]
         self.bufs = [[], []]          # [which][piece] -> dict name -> tensor
@@ -291,7 +292,7 @@ class LongGrid:
 
 
 def lorentz_long_grid(Lg, freq=9e9, *, T=1024, slab_fraction=0.7, k=64, rank=0, world_size=1, mode="lorentz", fma=False,
-                      probes=None, max_piece=1 << 27):
+                      probes=None, max_piece=1 << 27, fp32=False, newton=False):
     """Config 5 of BASELINE.json: a grid of Lg cells with the reference's default cell size / CPML, the
     slab filling the right ``slab_fraction`` of the domain.  Returns (LongGrid, info dict)."""
     from . import BaseFDTD11, Environment_Setup as envDef, MasterController as MC, Solver_Engine as SE
@@ -331,7 +332,7 @@ def lorentz_long_grid(Lg, freq=9e9, *, T=1024, slab_fraction=0.7, k=64, rank=0, 
     lg = LongGrid(Lg, mode=mode, pw=pw, mf=mf, mr=mr, nzsrc=nzsrc, dz=Pp.dz, dt=Pp.delT, courantNo=Pp.courantNo,
                   scalars=scal, pml_profiles=prof, srcE=np.asarray(Exs) / Pp.courantNo, srcH=np.asarray(Hys) / Pp.courantNo,
                   probes=probes if probes is not None else [nzsrc - 100], k=k, rank=rank, world_size=world_size, fma=fma,
-                  max_piece=max_piece)
+                  fp32=fp32, newton=newton, max_piece=max_piece)
     info = dict(pw=pw, mf=mf, mr=mr, nzsrc=nzsrc, dz=Pp.dz, dt=Pp.delT, courantNo=Pp.courantNo, scalars=scal, profiles=prof,
                 Exs=Exs, Hys=Hys, P=Pp, V=V)
     return lg, info

@@ -42,7 +42,7 @@ class Member:
             raise ValueError("sweep member is not in the tile engine's canonical form; run it through Controller")
         self.scalars = BaseFDTD11.grid_scalars(V, P)
         self.scalars.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
-        self.flags = BaseFDTD11.grid_flags(P, SE.USE_FMA) | nat.PF_F_CANONICAL
+        self.flags = BaseFDTD11.grid_flags(P, SE.USE_FMA, SE.USE_FP32, SE.CUBIC == "newton") | nat.PF_F_CANONICAL
         self.coef = {"beX": C_V.beX, "ceX": C_V.ceX, "cmY": C_V.cmY}
 
 

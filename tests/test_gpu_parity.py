@@ -567,3 +567,77 @@ def test_random_geometries_match_oracle(pk, seed):
                     continue
                 assert np.array_equal(out[nm], getattr(pa, nm)), (nm, ctx)
             assert np.array_equal(out["probe_out"], pa.probe_out), ctx
+
+
+FP32_TOL = 1e-5   # BASELINE north_star: optional fp32 mode against a stated 1e-5 tolerance (of the array's peak)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_fp32_mode_within_stated_tolerance(pk, name):
+    """PF_F_FP32: on-chip state advanced in single precision (Lorentz ADE in difference form, cubic root by
+    Newton iteration), fp64 arrays at the boundary.  Not a parity mode: max error <= 1e-5 of the peak of the
+    reference's array, against the reference goldens."""
+    g = load_golden(name)
+    pk.SE.USE_FP32 = True
+    try:
+        V, P, C_V, C_P = pk.build_objects(g["spec"])
+        V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    finally:
+        pk.SE.USE_FP32 = False
+    assert pk.SE.LAST_RUN_INFO["engine"] == "tile"
+    pairs = [("Ex", V.Ex), ("Hy", V.Hy)]
+    pairs += [("Port1", V.Port1), ("Port2", V.Port2)] if g["spec"]["mode"] == "nl" else [("x1ColBe", V.x1ColBe), ("x1ColAf", V.x1ColAf)]
+    for nm, got in pairs:
+        assert rel_err(got, g[nm]) <= FP32_TOL, (name, nm, rel_err(got, g[nm]))
+    assert not np.array_equal(V.Ex, g["Ex"])      # it really is a different arithmetic
+
+
+def test_fp32_mode_is_rejected_by_the_per_op_engine(pk):
+    g = load_golden("lorentz_sine")
+    pk.SE.USE_FP32, pk.SE.ENGINE = True, "ops"
+    try:
+        V, P, C_V, C_P = pk.build_objects(g["spec"])
+        with pytest.raises(ValueError):
+            pk.MC.Controller(V, P, C_V, C_P)
+    finally:
+        pk.SE.USE_FP32, pk.SE.ENGINE = False, "auto"
+
+
+@pytest.mark.parametrize("engine", ["tile", "ops"])
+@pytest.mark.parametrize("name", ["nl_sine", "nl_sine_amp"])
+def test_newton_cubic_option_within_tolerance(pk, name, engine):
+    """PF_F_NEWTON (Solver_Engine.CUBIC = "newton"): the positive root of the per-cell cubic by Newton
+    iteration instead of the closed form -- same tolerances as the closed form is held to."""
+    g = load_golden(name)
+    pk.SE.CUBIC, pk.SE.ENGINE = "newton", engine
+    try:
+        V, P, C_V, C_P = pk.build_objects(g["spec"])
+        V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    finally:
+        pk.SE.CUBIC, pk.SE.ENGINE = "closed", "auto"
+    for nm, got in (("Ex", V.Ex), ("Hy", V.Hy), ("Dx", V.Dx), ("Port1", V.Port1), ("Port2", V.Port2)):
+        assert rel_err(got, g[nm]) <= RTOL, (name, nm)
+    assert np.max(np.abs(V.Acubic - g["Acubic"])) <= 1e-10
+    # the Newton root satisfies the polynomial to rounding level (the closed form does not: cancellation)
+    sc = pk.B.grid_scalars(V, P)
+    A = V.Acubic[P.materialFrontEdge:P.materialRearEdge]
+    q2 = (V.Dx[P.materialFrontEdge:P.materialRearEdge] / P.permit_0) ** 2
+    live = A > 0
+    resid = ((sc["cub_a"] * A + sc["cub_b"]) * A + sc["cub_c"]) * A - q2
+    assert np.max(np.abs(resid[live]) / q2[live]) <= 1e-14
+
+
+def test_newton_cubic_root0_random_polynomials(pk):
+    """Newton root against numpy.roots on random admissible polynomials (a, b >= 0, c > 0, d < 0)."""
+    rng = np.random.default_rng(7)
+    n = 2000
+    co = np.stack([10.0 ** rng.uniform(-8, -2, n), 10.0 ** rng.uniform(-5, -1, n), 10.0 ** rng.uniform(-1, 1, n),
+                   -(10.0 ** rng.uniform(-7, 3, n))], axis=1)
+    from pyfdtd_b200 import CubicEquationSolver as CES
+    got = CES.root0_many(co, newton=True)
+    for i in range(0, n, 37):
+        r = np.roots(co[i])
+        want = float(np.max(r[np.abs(r.imag) < 1e-9 * np.abs(r.real).max()].real))
+        assert got[i] == pytest.approx(want, rel=1e-11)
+    a, b, c, d = co.T
+    assert np.max(np.abs(((a * got + b) * got + c) * got + d) / -d) <= 1e-14

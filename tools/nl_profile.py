@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""A few launches of the nonlinear (cubic) sweep batch (config 3), for ncu captures of k_tile<PF_NL,...>.
+Usage: python tools/nl_profile.py [members] [steps]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import bench  # noqa: E402
+
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+batch, members = bench.build_nl_batch(M, S)
+
+
+def step():
+    batch.reset_state(template=True)
+    batch.run(do_pol=False)
+
+
+sec = bench._time_cuda(torch, step, 2)
+slab = sum(m.scalars["mr"] - m.scalars["mf"] for m in members)
+print({"members": M, "steps": S, "Gcell_updates_per_s": batch.cell_steps / sec / 1e9, "cubic_solves_per_s": slab * S / sec})
