@@ -168,10 +168,16 @@ def extras(torch, peak_gbs, quick=False):
     from pyfdtd_b200 import MasterController as MC, Environment_Setup as envDef, Solver_Engine as SE, longgrid, pic, sweep
     out = {}
     # --- config 1 / 5: one long grid, streaming with k-step temporal blocking
-    for name, mode, cells, alg in (("free_long_grid", "free", 1 << 24, 32.0),
-                                   ("lorentz_long_grid", "lorentz", (1 << 24) if quick else 100_000_000, 32.0 + 0.7 * 40.0)):
+    big = (1 << 24) if quick else 100_000_000
+    for name, mode, cells, alg, kw in (("free_long_grid", "free", 1 << 24, 32.0, {}),
+                                       ("lorentz_long_grid", "lorentz", big, 32.0 + 0.7 * 40.0, {}),
+                                       # config 5 as BASELINE words it: dispersive AND nonlinear (PF_LORENTZ_NL, the
+                                       # Lorentz ADE + the cubic Kerr law on Dx - P); closed-form and Newton root
+                                       ("kerr_lorentz_long_grid", "lorentz_nl", big, 32.0 + 0.7 * 40.0, {}),
+                                       ("kerr_lorentz_long_grid_newton", "lorentz_nl", big, 32.0 + 0.7 * 40.0, {"newton": True}),
+                                       ("lorentz_long_grid_fp32", "lorentz", big, 32.0 + 0.7 * 40.0, {"fp32": True})):
         steps = 128
-        grid, info = longgrid.lorentz_long_grid(cells, T=steps + 64, k=64, mode=mode)
+        grid, info = longgrid.lorentz_long_grid(cells, T=steps + 64, k=64, mode=mode, **kw)
         for which in (0, 1):
             for arrs in grid.bufs[which]:
                 for n, t in arrs.items():
@@ -181,7 +187,7 @@ def extras(torch, peak_gbs, quick=False):
             for n in arrs0:
                 if arrs0[n] is not None:
                     arrs1[n].copy_(arrs0[n])
-        sec = _time_cuda(torch, lambda: grid.run(steps, do_pol=(mode == "lorentz")), 2)
+        sec = _time_cuda(torch, lambda: grid.run(steps, do_pol=(mode != "free")), 2)
         rate = cells * steps / sec / 1e9
         out[name] = {"cells": cells, "steps": steps, "pieces": len(grid.pieces), "Gcell_updates_per_s": rate,
                      "algorithmic_GBps_k1": rate * alg, "frac_of_hbm_peak_k1": rate * alg / peak_gbs, "temporal_block_k": 64}
@@ -218,9 +224,21 @@ def extras(torch, peak_gbs, quick=False):
     sec = _time_cuda(torch, nl_step, 2)
     slab_cells = sum(m.scalars["mr"] - m.scalars["mf"] for m in members)
     out["nl_cubic_sweep"] = {"members": M, "steps": S, "Gcell_updates_per_s": batch.cell_steps / sec / 1e9,
-                             "cubic_solves_per_s": slab_cells * S / sec}
+                             "cubic_solves_per_s": slab_cells * S / sec, "cubic": "closed form (reference algorithm)"}
     del batch
     torch.cuda.empty_cache()
+    # the same sweep with the optional arithmetic modes (not parity modes; tolerances in tests/test_gpu_parity.py)
+    for label, fp32, cubic in (("nl_cubic_sweep_newton", False, "newton"), ("nl_cubic_sweep_fp32", True, "closed")):
+        SE.USE_FP32, SE.CUBIC = fp32, cubic
+        try:
+            batch, members = build_nl_batch(M, S)
+            sec = _time_cuda(torch, nl_step, 2)
+            out[label] = {"members": M, "steps": S, "Gcell_updates_per_s": batch.cell_steps / sec / 1e9,
+                          "cubic_solves_per_s": slab_cells * S / sec}
+        finally:
+            SE.USE_FP32, SE.CUBIC = False, "closed"
+        del batch
+        torch.cuda.empty_cache()
     # --- config 4: PIC push + cell sort + deterministic deposit
     L, dz, dt = 13194, 8.3276e-5, 2.6389e-13
     n = 2_000_000 if quick else 20_000_000
@@ -359,6 +377,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--fma", action="store_true", help="PF_F_FMA kernels (not bit-identical; reported in config)")
+    ap.add_argument("--fp32", action="store_true", help="PF_F_FP32 kernels (optional single-precision mode; reported as dtype f32)")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--quick-extras", action="store_true", help="smaller extras (smoke)")
     args = ap.parse_args()
@@ -382,6 +401,7 @@ def main():
     import pyfdtd_b200  # noqa: F401
     from pyfdtd_b200 import Solver_Engine as SE, _native as nat
     SE.USE_FMA = bool(args.fma)
+    SE.USE_FP32 = bool(args.fp32)
     lib = nat.lib()
     wl = ProductWorkload(args.members, args.pass_steps, args.n_freq)
     batch = wl.batch
@@ -505,12 +525,13 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
             "config": {"workload": f"batched Lorentz-ADE+CPML 1D FDTD sweep, {args.members} members/GPU x "
                                    f"{args.pass_steps} time steps per step, Nz~10-15k cells/member "
                                    f"({cfg_cells/1e9:.2f} Gcell-updates/step/GPU), probes recorded every step",
                        "members_per_gpu": args.members, "time_steps_per_step": args.pass_steps,
-                       "k_block": k_block, "arithmetic": "fma-contracted" if args.fma else "exact (bit-identical to reference order)",
+                       "k_block": k_block, "arithmetic": ("fp32 on chip (PF_F_FP32, stated tolerance 1e-5; not a parity mode)" if args.fp32 else
+                                      "fma-contracted" if args.fma else "exact (bit-identical to reference order)"),
                        "l2_policy": f"state {cfg_state_mb:.0f} MB per GPU > 126 MB L2, restored from a random template every step",
                        "parallelism": f"members sharded over {world} GPU(s), no collectives"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,

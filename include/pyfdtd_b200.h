@@ -36,7 +36,14 @@ enum { PF_OK = 0, PF_E_ARG = -1, PF_E_CUDA = -2, PF_E_UNSUPPORTED = -3, PF_E_SCR
 enum {
     PF_FREE = 0,    /* Solver_Engine.py:167-183  IntegratorFreeSpace1D */
     PF_LORENTZ = 1, /* Solver_Engine.py:294-316  IntegratorLinLor1D    */
-    PF_NL = 2       /* Solver_Engine.py:236-261  IntegratorNL1D        */
+    PF_NL = 2,      /* Solver_Engine.py:236-261  IntegratorNL1D        */
+    PF_LORENTZ_NL = 3 /* BASELINE config 5's "dispersive and nonlinear" material.  NOT a reference
+                         integrator (its nonlinear loop has no dispersion ADE): the IntegratorLinLor1D
+                         loop with ADE_ExCreate (BaseFDTD11.py:712-725) replaced by the reference's cubic
+                         chain (BaseFDTD11.py:793-877) applied to Dn = Dx - P:
+                           Acubic = root0([cub_a, cub_b, cub_c, -|Dn/eps0|^2]) (0 where |d| <= 1e-8),
+                           Ex = Dn / (nl_den0 + nl_den1*Acubic).
+                         Builder-defined composition; parity is against oracle/fdtd_oracle.c only.  */
 };
 
 /* engine selector for pf_run_pass / pf_run_batch */

@@ -181,6 +181,32 @@ void orc_nl_ex(OrcGrid *g)
         g->Ex[nz] = g->Dx[nz] / (g->nl_den0 + g->nl_den1 * g->Acubic[nz]);
 }
 
+/* Mode LORENTZ_NL (config 5's "dispersive and nonlinear" material; NOT in the reference, whose nonlinear
+ * integrator has no dispersion ADE -- builder-defined composition, parity unpinned): the Lorentz ADE
+ * carries the dispersive polarisation P (orc_pol_update), and the instantaneous Kerr response is solved
+ * on what is left of D, Dn = Dx - P (the numerator of ADE_ExCreate, BaseFDTD11.py:712-725), with the
+ * reference's own cubic chain (BaseFDTD11.py:793-877):
+ *   Acubic = root0([cub, qua, one, -|Dn/eps0|^2]) if that |d| > 1e-8 else 0;  Ex = Dn/(den0 + den1*Acubic)
+ * With cub = chi3^2, qua = 2*eps_inf*chi3, one = eps_inf^2, den0 = eps0*eps_inf, den1 = eps0*chi3 this is
+ * Dn = eps0*(eps_inf + chi3*|E|^2)*E. */
+void orc_acubic_dn(OrcGrid *g)
+{
+    for (int nz = g->mf; nz < g->mr; ++nz) {
+        double q = fabs((g->Dx[nz] - g->P[nz]) / g->eps0);
+        double d = -pow(q, 2.0);
+        double out = 0.0;
+        if (fabs(d) > 1e-8)
+            out = orc_cubic_root0(g->cub_a, g->cub_b, g->cub_c, d);
+        g->Acubic[nz] = out;
+    }
+}
+
+void orc_nl_ex_dn(OrcGrid *g)
+{
+    for (int nz = g->mf; nz < g->mr; ++nz)
+        g->Ex[nz] = (g->Dx[nz] - g->P[nz]) / (g->nl_den0 + g->nl_den1 * g->Acubic[nz]);
+}
+
 static void orc_record(OrcGrid *g, int n, int T)
 {
     for (int p = 0; p < g->n_probes; ++p)
@@ -192,17 +218,18 @@ static void orc_record(OrcGrid *g, int n, int T)
     }
 }
 
-enum { ORC_FREE = 0, ORC_LORENTZ = 1, ORC_NL = 2 };
+enum { ORC_FREE = 0, ORC_LORENTZ = 1, ORC_NL = 2, ORC_LORENTZ_NL = 3 };
 
 /* One pass of T steps starting at step n0 (sources indexed by absolute step).
  * mode FREE    : Solver_Engine.py:167-183
  * mode LORENTZ : Solver_Engine.py:294-316 (do_pol = pass index == 1)
- * mode NL      : Solver_Engine.py:236-261                                               */
+ * mode NL      : Solver_Engine.py:236-261
+ * mode LORENTZ_NL : the Lorentz loop with ADE_ExCreate replaced by the cubic chain on Dx - P (see above) */
 int orc_run(OrcGrid *g, int mode, int do_pol, int n0, int nsteps, int T_total)
 {
     int cpml = g->cpml_m || g->cpml_p;
     for (int n = n0; n < n0 + nsteps; ++n) {
-        if (mode == ORC_LORENTZ && do_pol)
+        if ((mode == ORC_LORENTZ || mode == ORC_LORENTZ_NL) && do_pol)
             orc_pol_update(g);
         orc_ex_update(g);
         if (cpml)
@@ -215,6 +242,10 @@ int orc_run(OrcGrid *g, int mode, int do_pol, int n0, int nsteps, int T_total)
             orc_dx_update(g);
             orc_acubic(g);
             orc_nl_ex(g);
+        } else if (mode == ORC_LORENTZ_NL) {
+            orc_dx_update(g);
+            orc_acubic_dn(g);
+            orc_nl_ex_dn(g);
         }
         orc_hy_update(g);
         if (cpml)

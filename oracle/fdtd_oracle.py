@@ -234,7 +234,7 @@ def sources(c):
 # ----------------------------------------------------------------------------- case container
 @dataclass
 class Case:
-    mode: str                 # "free" | "lorentz" | "nl"
+    mode: str                 # "free" | "lorentz" | "nl" | "lorentz_nl" (builder-defined composition)
     freq: float
     Nz: int
     T: int
@@ -318,7 +318,8 @@ def lib():
     return _lib
 
 
-MODE_ID = {"free": 0, "lorentz": 1, "nl": 2}
+MODE_ID = {"free": 0, "lorentz": 1, "nl": 2, "lorentz_nl": 3}
+KERR_EPS_INF = 1.0   # Kerr-Lorentz composition (mode "lorentz_nl", see fdtd_oracle.c): Dx - P = eps0 (eps_inf + chi3 |E|^2) E
 
 
 def _dp(a):
@@ -379,6 +380,10 @@ class PassArrays:
         g.cub_a, g.cub_b, g.cub_c = cubic_abc(c.freq, wp, m["w0"], m["gam"], m["alpha3"], m["chi3"])
         g.nl_den0 = EPS0 * float(np.sqrt(1.2))
         g.nl_den1 = EPS0 * m["chi3"]
+        if c.mode == "lorentz_nl":
+            chi3 = float(m["chi3"])
+            g.cub_a, g.cub_b, g.cub_c = chi3 ** 2, 2 * KERR_EPS_INF * chi3, KERR_EPS_INF ** 2
+            g.nl_den0 = EPS0 * KERR_EPS_INF
         for n in ("Ex", "Hy", "Dx", "P", "Pprev", "psiE", "psiH", "Acubic", "Jx", "UpExMat",
                   "UpHySelf", "UpHyMat", "srcE", "srcH"):
             setattr(g, n, _dp(getattr(self, n)))
@@ -401,9 +406,9 @@ def run_case(c: Case, snapshots=False, nsteps=None):
     wp = c.medium["wp"]
     out = {}
     x1ColBe = np.zeros(c.T); x1ColAf = np.zeros(c.T)
-    if c.mode in ("free", "lorentz"):
+    if c.mode in ("free", "lorentz", "lorentz_nl"):
         for i in range(2):
-            if c.mode == "lorentz":      # Solver_Engine.py:286 -- cumulative over the two passes
+            if c.mode != "free":         # Solver_Engine.py:286 -- cumulative over the two passes
                 wp, _ = spatial_stab(c.Nz, c.dz, c.freq, c.dt, wp, c.medium["w0"], c.medium["gam"])
             Exs, Hys = sources(c)
             pa = PassArrays(c, wp, Exs, Hys, [c.x1Loc if i == 0 else c.x2Loc], snapshots and i == 1)
@@ -413,7 +418,7 @@ def run_case(c: Case, snapshots=False, nsteps=None):
                 x1ColBe = np.where(n <= fin_be, pa.probe_out[0], 0.0)      # :360-363
             else:
                 x1ColAf = np.where(n >= start_af, pa.probe_out[0], 0.0)    # :365-368
-        out.update(P=pa.P, Pprev=pa.Pprev, Dx=pa.Dx)
+        out.update(P=pa.P, Pprev=pa.Pprev, Dx=pa.Dx, Acubic=pa.Acubic)
     else:
         wp, _ = spatial_stab(c.Nz, c.dz, c.freq, c.dt, wp, c.medium["w0"], c.medium["gam"])  # :231
         Exs, Hys = sources(c)

@@ -280,9 +280,21 @@ def _cubic_abc(V, P):
     return float(cub), float(qua), float(one)
 
 
-def grid_scalars(V, P):
+KERR_EPS_INF = 1.0   # instantaneous relative permittivity of the Kerr-Lorentz composition (the reference's
+                     # Lorentz medium has eps_inf = 1: Ex = (Dx - P)/eps0, BaseFDTD11.py:712-725)
+
+
+def grid_scalars(V, P, kerr_lorentz=False):
+    """Scalars of one PfGrid.  kerr_lorentz=True: the PF_LORENTZ_NL composition (not in the reference),
+    Dx - P = eps0 (eps_inf + chi3 |E|^2) E, i.e. cubic coefficients (chi3^2, 2 eps_inf chi3, eps_inf^2) in
+    A = |E|^2 and Ex = (Dx - P)/(eps0 eps_inf + eps0 chi3 A)."""
     A, B, C = _lorentz_abc(V, P)
     ca, cb, cc = _cubic_abc(V, P)
+    if kerr_lorentz:
+        chi3, einf = float(V.chi3Stat), KERR_EPS_INF
+        return dict(pw=int(P.pmlWidth), mf=int(P.materialFrontEdge), mr=int(P.materialRearEdge), nzsrc=int(P.nzsrc),
+                    dt_over_dz=P.delT / P.dz, eps0=P.permit_0, polA=A, polB=B, polC=C, cub_a=chi3 ** 2,
+                    cub_b=2 * einf * chi3, cub_c=einf ** 2, nl_den0=P.permit_0 * einf, nl_den1=P.permit_0 * chi3)
     return dict(pw=int(P.pmlWidth), mf=int(P.materialFrontEdge), mr=int(P.materialRearEdge), nzsrc=int(P.nzsrc),
                 dt_over_dz=P.delT / P.dz, eps0=P.permit_0, polA=A, polB=B, polC=C, cub_a=ca, cub_b=cb, cub_c=cc,
                 nl_den0=P.permit_0 * float(np.sqrt(1.2)), nl_den1=P.permit_0 * V.chi3Stat)

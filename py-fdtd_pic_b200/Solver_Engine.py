@@ -28,6 +28,8 @@ USE_FMA = False      # True: allow FMA contraction in the kernels (PF_F_FMA; not
 CUBIC = "closed"     # "closed": the reference's closed-form cubic root (CubicEquationSolver.solve);
                      # "newton": PF_F_NEWTON, the same root by Newton iteration (~3x fewer instructions; differs by the
                      # closed form's cancellation error, <= 1e-10 absolute on Acubic)
+KERR_LORENTZ = False  # True: IntegratorLinLor1D runs the Kerr-Lorentz composition (PF_LORENTZ_NL, BASELINE config 5's
+                      # "dispersive and nonlinear" material; not a reference integrator -- see include/pyfdtd_b200.h)
 USE_FP32 = False     # True: optional single-precision mode of the tile engine (PF_F_FP32; stated tolerance 1e-5
                      # of the trace peak -- not a parity mode; arrays stay fp64 at the boundary)
 LAST_RUN_INFO = {}   # engine used, bytes moved, kernel launches of the last pass (for tests / bench)
@@ -147,7 +149,7 @@ def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=F
     arrs = BaseFDTD11._host_arrays(V, C_V, V.tempVarPol)
     Jx = V.Jx if np.any(V.Jx != 0.0) else None
     engine, canon = _pick_engine(P, arrs, Jx, probe_idx)
-    scal = BaseFDTD11.grid_scalars(V, P)
+    scal = BaseFDTD11.grid_scalars(V, P, kerr_lorentz=(mode == "lorentz_nl"))
     flags = BaseFDTD11.grid_flags(P, USE_FMA, USE_FP32, CUBIC == "newton")
     if USE_FP32 and engine != nat.PF_ENGINE_TILE:
         raise ValueError("USE_FP32 is a mode of the tile engine; this grid needs the general per-op engine")
@@ -175,7 +177,7 @@ def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=F
                                   int(P.vidInterval) if snap_t is not None else 0, rows if snap_t is not None else 0,
                                   scratch.data_ptr() if scratch is not None else None, sbytes, stream), "pf_run_pass")
 
-    if mode == "lorentz" and do_pol and nsteps >= 1:
+    if mode in ("lorentz", "lorentz_nl") and do_pol and nsteps >= 1:
         # keep P^{N-2} as well so V.tempTempVarPol / V.tempVarPol end up as the reference leaves them
         if nsteps > 1:
             call(n0, nsteps - 1)
@@ -186,12 +188,12 @@ def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=F
     out = g.fetch(["Ex", "Hy", "Dx", "P", "Pprev", "psiE", "psiH", "Acubic"])
     V.Ex, V.Hy, V.Dx = out["Ex"], out["Hy"], out["Dx"]
     C_V.psi_Ex, C_V.psi_Hy = out["psiE"], out["psiH"]
-    if mode == "lorentz":
+    if mode in ("lorentz", "lorentz_nl"):
         V.polarisationCurr = out["P"]
         V.tempVarPol = out["Pprev"]
         if pprev2 is not None:
             V.tempTempVarPol = pprev2.cpu().numpy()
-    if mode == "nl":
+    if mode in ("nl", "lorentz_nl"):
         V.Acubic = out["Acubic"]
     if snap_t is not None:
         stage = dev.pinned_buffer(rows * L, tag="history").view(rows, L)
@@ -236,7 +238,7 @@ def _two_pass(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf, lorentz):
     """Shared body of IntegratorFreeSpace1D / IntegratorLinLor1D: pass 0 = incident run (probe x1Loc),
     pass 1 = run with the medium's polarisation (probe x2Loc, history, attenuation probes)."""
     n = np.arange(P.timeSteps)
-    mode = "lorentz" if lorentz else "free"
+    mode = ("lorentz_nl" if KERR_LORENTZ else "lorentz") if lorentz else "free"
     for i in range(2):
         C_V, Exs, Hys = prepare_pass(V, P, C_V, C_P, lorentz)
         V.test = 0

@@ -16,7 +16,7 @@ from . import _native as nat
 
 STATE = ("Ex", "Hy", "Dx", "P", "Pprev", "psiE", "psiH", "Acubic")
 COEF = ("UpExMat", "denE", "UpHySelf", "UpHyMat", "denH", "beX", "ceX", "Cb", "bmY", "cmY", "C2")
-MODE_ID = {"free": nat.PF_FREE, "lorentz": nat.PF_LORENTZ, "nl": nat.PF_NL}
+MODE_ID = {"free": nat.PF_FREE, "lorentz": nat.PF_LORENTZ, "nl": nat.PF_NL, "lorentz_nl": nat.PF_LORENTZ_NL}
 
 
 def canonical_form(P, arrs, Jx=None):

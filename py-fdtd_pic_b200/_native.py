@@ -13,7 +13,7 @@ from ctypes import POINTER, c_double, c_int, c_int32, c_int64, c_size_t, c_void_
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYFDTD_B200_LIB") or os.path.join(HERE, "libpyfdtd_b200.so")  # env override: kernel tuning builds
 
-PF_FREE, PF_LORENTZ, PF_NL = 0, 1, 2
+PF_FREE, PF_LORENTZ, PF_NL, PF_LORENTZ_NL = 0, 1, 2, 3
 PF_ENGINE_OPS, PF_ENGINE_TILE = 0, 1
 PF_F_TFSF, PF_F_CPML_M, PF_F_CPML_P, PF_F_CANONICAL, PF_F_FMA, PF_F_FP32, PF_F_NEWTON = 1, 2, 4, 8, 16, 32, 64
 

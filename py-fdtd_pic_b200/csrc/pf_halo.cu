@@ -16,7 +16,7 @@ static HaloPtrs halo_arrays(const PfGrid *g, int mode)
 {
     HaloPtrs h;
     double *all[7] = {g->Ex, g->Hy, g->psiE, g->psiH, g->Dx, g->P, g->Pprev};
-    h.n = (mode == PF_LORENTZ) ? 7 : (mode == PF_NL ? 5 : 4);
+    h.n = (mode == PF_LORENTZ || mode == PF_LORENTZ_NL) ? 7 : (mode == PF_NL ? 5 : 4);
     for (int i = 0; i < 7; ++i) h.a[i] = all[i];
     return h;
 }

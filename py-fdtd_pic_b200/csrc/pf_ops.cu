@@ -128,6 +128,24 @@ __global__ void __launch_bounds__(OPS_THREADS) k_acubic(PfGrid g, CubicConsts k,
     g.Acubic[nz] = acubic_cell(k, g.Dx[nz], g.eps0, inv_eps0);
 }
 
+// PF_LORENTZ_NL: the same two leaf ops on Dn = Dx - P (see include/pyfdtd_b200.h)
+__global__ void __launch_bounds__(OPS_THREADS) k_acubic_dn(PfGrid g, CubicConsts k, double inv_eps0)
+{
+    int nz = blockIdx.x * OPS_THREADS + threadIdx.x;
+    if (nz >= g.L) return;
+    if (!in_slab(g, PF_GZ(g, nz))) return;
+    g.Acubic[nz] = acubic_cell(k, __dsub_rn(g.Dx[nz], g.P[nz]), g.eps0, inv_eps0);
+}
+
+template <class A>
+__global__ void __launch_bounds__(OPS_THREADS) k_nl_ex_dn(PfGrid g)
+{
+    int nz = blockIdx.x * OPS_THREADS + threadIdx.x;
+    if (nz >= g.L) return;
+    if (!in_slab(g, PF_GZ(g, nz))) return;
+    g.Ex[nz] = __ddiv_rn(A::sub(g.Dx[nz], g.P[nz]), A::add(g.nl_den0, A::mul(g.nl_den1, g.Acubic[nz])));
+}
+
 // BaseFDTD11.py:858-877  NonLinExUpdate
 template <class A>
 __global__ void __launch_bounds__(OPS_THREADS) k_nl_ex(PfGrid g)
@@ -243,7 +261,7 @@ static int validate(const PfGrid *g)
 int ops_step(const PfGrid *g, const GridDev &gd, int mode, int do_pol, int n, cudaStream_t st)
 {
     bool cpml = g->flags & (PF_F_CPML_M | PF_F_CPML_P);
-    if (mode == PF_LORENTZ && do_pol) PF_DISPATCH(k_pol_update, g, st, *g);
+    if ((mode == PF_LORENTZ || mode == PF_LORENTZ_NL) && do_pol) PF_DISPATCH(k_pol_update, g, st, *g);
     PF_DISPATCH(k_ex_update, g, st, *g);
     if (cpml) PF_DISPATCH(k_psi_e, g, st, *g);
     k_source<<<1, 32, 0, st>>>(*g, n);
@@ -256,6 +274,11 @@ int ops_step(const PfGrid *g, const GridDev &gd, int mode, int do_pol, int n, cu
         k_acubic<<<ops_blocks(g->L), OPS_THREADS, 0, st>>>(*g, gd.k, gd.inv_eps0);
         PF_LAUNCH_CHECK("k_acubic");
         PF_DISPATCH(k_nl_ex, g, st, *g);
+    } else if (mode == PF_LORENTZ_NL) {
+        PF_DISPATCH(k_dx_update, g, st, *g);
+        k_acubic_dn<<<ops_blocks(g->L), OPS_THREADS, 0, st>>>(*g, gd.k, gd.inv_eps0);
+        PF_LAUNCH_CHECK("k_acubic_dn");
+        PF_DISPATCH(k_nl_ex_dn, g, st, *g);
     }
     PF_DISPATCH(k_hy_update, g, st, *g);
     if (cpml) PF_DISPATCH(k_psi_m, g, st, *g);

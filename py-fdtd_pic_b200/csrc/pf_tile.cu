@@ -204,6 +204,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
 {
     constexpr int NT = TILE_CELLS / C;
     constexpr bool F32 = std::is_same<R, float>::value;
+    constexpr bool LOR = MODE == PF_LORENTZ || MODE == PF_LORENTZ_NL;   // Lorentz ADE polarisation
     constexpr bool HAS_MAT = (GEN || SLAB) && MODE != PF_FREE;
     constexpr bool ALL_MAT = !GEN && SLAB && MODE != PF_FREE;
     constexpr bool HAS_PML = GEN || PML;
@@ -217,7 +218,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
         hl = hy[j];
         R e = ex[j];
         R pnow = R(0);
-        if (MODE == PF_LORENTZ && HAS_MAT) {
+        if (LOR && HAS_MAT) {
             if (POL) {
                 if constexpr (F32) {
                     // difference form: pq holds v = P^n - P^{n-1};  v' = v - G v - K P + C E,  P' = P + v'
@@ -258,10 +259,11 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                     em = div_const_fast(A::sub(dx[j], pnow), K.eps0, K.inv_eps0, divkey);
                 }
                 e = (!GEN || ((K.mSlab >> j) & 1)) ? em : e;
-            } else if constexpr (F32) {
+            } else if constexpr (F32) {   // cubic law on Dx (PF_NL) or on Dx - P (PF_LORENTZ_NL)
                 if (!GEN || ((K.mSlab >> j) & 1)) {
                     dx[j] = A::add(dx[j], A::mad(dH, K.dtdz, A::mul(dH, K.dtdz_lo)));
-                    const NlResultF nl = nl_material_law_f32(K.ca, K.cb, K.cc, dx[j], K.inv_eps0, K.den0, K.den1);
+                    const R dn = LOR ? A::sub(dx[j], pnow) : dx[j];
+                    const NlResultF nl = nl_material_law_f32(K.ca, K.cb, K.cc, dn, K.inv_eps0, K.den0, K.den1);
                     acub[j] = nl.a;
                     e = nl.e;
                 }
@@ -269,17 +271,17 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                 dx[j] = A::mad(dH, K.dtdz, dx[j]);      // the material law of all C cells follows the loop
             } else if ((K.mSlab >> j) & 1) {
                 dx[j] = A::mad(dH, K.dtdz, dx[j]);
-                const NlResult nl = nl_material_law(kcp, dx[j], K.eps0, K.inv_eps0, K.den0, K.den1);
+                const NlResult nl = nl_material_law(kcp, LOR ? A::sub(dx[j], pnow) : dx[j], K.eps0, K.inv_eps0, K.den0, K.den1);
                 acub[j] = nl.a;
                 e = nl.e;
             }
         }
         ex[j] = e;
     }
-    if constexpr (MODE == PF_NL && ALL_MAT && !F32) {
+    if constexpr ((MODE == PF_NL || MODE == PF_LORENTZ_NL) && ALL_MAT && !F32) {
         NlVec<C> dv;
 #pragma unroll
-        for (int j = 0; j < C; ++j) dv.v[j] = dx[j];
+        for (int j = 0; j < C; ++j) dv.v[j] = LOR ? A::sub(dx[j], POL ? pq[j] : pc[j]) : dx[j];
         const NlResultVec<C> nl = nl_material_law_vec<C>(kcp, dv, K.eps0, K.inv_eps0, K.den0, K.den1);
 #pragma unroll
         for (int j = 0; j < C; ++j) { acub[j] = nl.a[j]; ex[j] = nl.e[j]; }
@@ -356,6 +358,8 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 {
     constexpr int NT = TILE_CELLS / C;
     constexpr bool F32 = std::is_same<R, float>::value;
+    constexpr bool LOR = MODE == PF_LORENTZ || MODE == PF_LORENTZ_NL;
+    constexpr bool CUB = MODE == PF_NL || MODE == PF_LORENTZ_NL;
     constexpr bool HAS_MAT = (GEN || SLAB) && MODE != PF_FREE;   // material arrays present
     constexpr bool HAS_PML = GEN || PML;
     const PfGrid &g = TG.d.g;
@@ -401,7 +405,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
                 const double d0 = (!GEN || ((mSlab >> j) & 1)) ? inDx[lz0 + j] : 0.0;
                 dx[j] = F32 ? d0 * sD : d0;
             }
-            if (MODE == PF_LORENTZ) {
+            if (LOR) {
                 const double *__restrict__ inP = TG.buf[src][S_P];
                 const double *__restrict__ inPp = TG.buf[src][S_PP];
 #pragma unroll
@@ -424,7 +428,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
                 S.c2u[j * NT + tid] = (R)((((M.pmlH >> j) & 1) && !q) ? g.c2_pml * sH : 0.0);
             }
         }
-        if (MODE == PF_NL) {
+        if (CUB) {
 #pragma unroll
             for (int j = 0; j < C; ++j) acub[j] = R(0);
         }
@@ -461,7 +465,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 
     S.edgeH[tid] = hy[C - 1];
     cta_sync();
-    constexpr bool SWAP = MODE == PF_LORENTZ && HAS_MAT && POL && !F32;   // P history alternates between pa and pb
+    constexpr bool SWAP = LOR && HAS_MAT && POL && !F32;   // P history alternates between pa and pb
     bool swapped = false;   // true: current P is in pb, previous in pa
     // The time loop exists twice: warps that own a source cell or a probe run the version with those
     // (warp-uniform) tests, every other warp a loop with nothing in it but the update itself.
@@ -485,7 +489,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
         }
     };
     // (the cubic material law dwarfs those tests and is large: one copy of its loop only)
-    if (MODE == PF_NL || K.wSrc || wProbe) time_loop(std::true_type{});
+    if (CUB || K.wSrc || wProbe) time_loop(std::true_type{});
     else time_loop(std::false_type{});
 
     // ---- store interior ---------------------------------------------------------------------------
@@ -512,7 +516,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 #pragma unroll
         for (int j = 0; j < C; ++j)
             if ((sm >> j) & 1) outDx[lz0 + j] = F32 ? dx[j] * uD : dx[j];
-        if (MODE == PF_LORENTZ) {
+        if (LOR) {
             double *__restrict__ outP = TG.buf[dst][S_P];
             double *__restrict__ outPp = TG.buf[dst][S_PP];
 #pragma unroll
@@ -527,7 +531,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
                     }
                 }
         }
-        if (MODE == PF_NL && g.Acubic) {
+        if (CUB && g.Acubic) {
 #pragma unroll
             for (int j = 0; j < C; ++j)
                 if ((sm >> j) & 1) g.Acubic[lz0 + j] = acub[j];
@@ -665,7 +669,7 @@ __global__ void __launch_bounds__(256) k_tile_copy(const TileGrid *__restrict__ 
         if ((launches & 1) == 0) return;
     }
     int W = TILE_CELLS - 2 * halo;
-    int narr = (mode == PF_LORENTZ) ? 7 : (mode == PF_NL ? 5 : 4);
+    int narr = (mode == PF_LORENTZ || mode == PF_LORENTZ_NL) ? 7 : (mode == PF_NL ? 5 : 4);
     for (int a = 0; a < narr; ++a) {
         const double *__restrict__ s = TG.buf[from][a];
         double *__restrict__ d = TG.buf[to][a];
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(256) k_tile_copy(const TileGrid *__restrict__ 
 // host side
 // ------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-static inline int n_state_arrays(int mode) { return mode == PF_LORENTZ ? 7 : (mode == PF_NL ? 5 : 4); }
+static inline int n_state_arrays(int mode) { return (mode == PF_LORENTZ || mode == PF_LORENTZ_NL) ? 7 : (mode == PF_NL ? 5 : 4); }
 
 // does the piece [z0, z0+L) of the global grid contain CPML / slab cells?
 static inline bool piece_has_pml(const PfGrid &g)
@@ -706,7 +710,7 @@ static int tile_supported(const PfGrid &g, int mode)
     if (piece_has_pml(g) && (!g.psiE || !g.psiH || !g.beX || !g.ceX || !g.cmY)) return set_err(PF_E_ARG, "CPML arrays missing");
     if (mode != PF_FREE && piece_has_slab(g)) {
         if (!g.Dx) return set_err(PF_E_ARG, "Dx missing");
-        if (mode == PF_LORENTZ && (!g.P || !g.Pprev)) return set_err(PF_E_ARG, "P/Pprev missing");
+        if ((mode == PF_LORENTZ || mode == PF_LORENTZ_NL) && (!g.P || !g.Pprev)) return set_err(PF_E_ARG, "P/Pprev missing");
     }
     return 0;
 }
@@ -806,6 +810,9 @@ static int launch_tile_mode(int mode, int do_pol, int fma, bool wide, int n_tile
             return do_pol ? launch_tile_a<PF_LORENTZ, true, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
                           : launch_tile_a<PF_LORENTZ, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
         if (mode == PF_NL) return launch_tile_a<PF_NL, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        if (mode == PF_LORENTZ_NL)
+            return do_pol ? launch_tile_a<PF_LORENTZ_NL, true, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
+                          : launch_tile_a<PF_LORENTZ_NL, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
         return set_err(PF_E_ARG, "bad mode %d", mode);
     }
     if (mode == PF_FREE) return launch_tile<PF_FREE, false, TILE_C_FREE>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
@@ -817,6 +824,9 @@ static int launch_tile_mode(int mode, int do_pol, int fma, bool wide, int n_tile
                       : launch_tile<PF_LORENTZ, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
     }
     if (mode == PF_NL) return launch_tile<PF_NL, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    if (mode == PF_LORENTZ_NL)
+        return do_pol ? launch_tile<PF_LORENTZ_NL, true, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
+                      : launch_tile<PF_LORENTZ_NL, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
     return set_err(PF_E_ARG, "bad mode %d", mode);
 }
 
@@ -828,7 +838,7 @@ static int arith_of(const PfGrid *grids, int n, int mode, int *arith)
         const PfGrid &g = grids[m];
         if (g.flags & PF_F_FP32) {
             // the fp32 cubic root is a Newton iteration that needs an increasing, convex polynomial
-            if (mode == PF_NL && !(g.cub_a >= 0.0 && g.cub_b >= 0.0 && g.cub_c > 0.0))
+            if ((mode == PF_NL || mode == PF_LORENTZ_NL) && !(g.cub_a >= 0.0 && g.cub_b >= 0.0 && g.cub_c > 0.0))
                 return set_err(PF_E_UNSUPPORTED, "PF_F_FP32: nonlinear mode needs cub >= 0, qua >= 0, one > 0");
             a = ARITH_FP32;
         } else if ((g.flags & PF_F_FMA) && a == ARITH_EXACT) {
@@ -1075,7 +1085,7 @@ int pf_run_block(const PfGrid *src, const PfGrid *dst, int n_grids, int mode, in
                  void *scratch, size_t scratch_bytes, void *stream)
 {
     if (!src || !dst || n_grids < 0) return set_err(PF_E_ARG, "pf_run_block: bad arguments");
-    if (mode < PF_FREE || mode > PF_NL) return set_err(PF_E_ARG, "pf_run_block: bad mode %d", mode);
+    if (mode < PF_FREE || mode > PF_LORENTZ_NL) return set_err(PF_E_ARG, "pf_run_block: bad mode %d", mode);
     return tile_block(src, dst, n_grids, mode, do_pol, n0, ksteps, halo, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
@@ -1101,7 +1111,7 @@ int pf_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, int e
                 int snap_interval, int snap_rows, void *scratch, size_t scratch_bytes, void *stream)
 {
     if (!g || nsteps < 0) return set_err(PF_E_ARG, "pf_run_pass: bad arguments");
-    if (mode < PF_FREE || mode > PF_NL) return set_err(PF_E_ARG, "pf_run_pass: bad mode %d", mode);
+    if (mode < PF_FREE || mode > PF_LORENTZ_NL) return set_err(PF_E_ARG, "pf_run_pass: bad mode %d", mode);
     cudaStream_t st = (cudaStream_t)stream;
     if (engine == PF_ENGINE_OPS && (g->flags & PF_F_FP32))
         return set_err(PF_E_UNSUPPORTED, "PF_F_FP32 is a mode of the tile engine only");
@@ -1115,7 +1125,7 @@ int pf_run_batch(const PfGrid *grids, int n_grids, int mode, int do_pol, int n0,
                  void *scratch, size_t scratch_bytes, void *stream)
 {
     if (!grids || n_grids < 0 || !nsteps) return set_err(PF_E_ARG, "pf_run_batch: bad arguments");
-    if (mode < PF_FREE || mode > PF_NL) return set_err(PF_E_ARG, "pf_run_batch: bad mode %d", mode);
+    if (mode < PF_FREE || mode > PF_LORENTZ_NL) return set_err(PF_E_ARG, "pf_run_batch: bad mode %d", mode);
     return tile_run(grids, n_grids, mode, do_pol, n0, nsteps, k_block, nullptr, 0, 0, scratch, scratch_bytes,
                     (cudaStream_t)stream);
 }

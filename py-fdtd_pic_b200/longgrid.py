@@ -162,7 +162,7 @@ class LongGrid:
         self.probes = probes
         flags = ((nat.PF_F_TFSF if tfsf else 0) | nat.PF_F_CPML_M | nat.PF_F_CPML_P | nat.PF_F_CANONICAL |
                  (nat.PF_F_FMA if fma else 0) | (nat.PF_F_FP32 if fp32 else 0) | (nat.PF_F_NEWTON if newton else 0))
-        n_arr = 7 if mode == "lorentz" else (5 if mode == "nl" else 4)
+        n_arr = 7 if mode in ("lorentz", "lorentz_nl") else (5 if mode == "nl" else 4)
         self.names = STATE_ALL[:n_arr]
         self.bufs = [[], []]          # [which][piece] -> dict name -> tensor
         self.grids = [(nat.PfGrid * len(self.mine))(), (nat.PfGrid * len(self.mine))()]
@@ -296,7 +296,7 @@ def lorentz_long_grid(Lg, freq=9e9, *, T=1024, slab_fraction=0.7, k=64, rank=0, 
     """Config 5 of BASELINE.json: a grid of Lg cells with the reference's default cell size / CPML, the
     slab filling the right ``slab_fraction`` of the domain.  Returns (LongGrid, info dict)."""
     from . import BaseFDTD11, Environment_Setup as envDef, MasterController as MC, Solver_Engine as SE
-    tup = envDef.envSetup(freq, 0.7, 7000, 8000, LorMed=(mode == "lorentz"), nonLinMed=(mode == "nl"))
+    tup = envDef.envSetup(freq, 0.7, 7000, 8000, LorMed=(mode in ("lorentz", "lorentz_nl")), nonLinMed=(mode == "nl"))
     Pp = MC.Params(*tup, False, 0.7, freq, 20)
     pw = int(Pp.pmlWidth)
     # proxy grid: the CPML profiles and update scalars do not depend on the grid length
@@ -304,7 +304,7 @@ def lorentz_long_grid(Lg, freq=9e9, *, T=1024, slab_fraction=0.7, k=64, rank=0, 
     Pp.timeSteps = int(T)
     Pp.materialFrontEdge, Pp.materialRearEdge = pw + 50, Pp.Nz - 1
     Pp.TFSF, Pp.SineCont, Pp.Periods = True, True, 1000
-    Pp.LorentzMed, Pp.nonLinMed, Pp.FreeSpace = mode == "lorentz", mode == "nl", mode == "free"
+    Pp.LorentzMed, Pp.nonLinMed, Pp.FreeSpace = mode in ("lorentz", "lorentz_nl"), mode == "nl", mode == "free"
     V = MC.Variables(Pp.Nz, Pp.timeSteps, Pp.vidInterval, 1)
     C_P = MC.CPML_Params(Pp.dz)
     C_V = MC.CPML_Variables(Pp.Nz, Pp.timeSteps)
@@ -326,7 +326,7 @@ def lorentz_long_grid(Lg, freq=9e9, *, T=1024, slab_fraction=0.7, k=64, rank=0, 
     mr = Lg - 2
     nzsrc = pw + int(0.05 / Pp.dz)
     Pp.materialFrontEdge, Pp.materialRearEdge, Pp.nzsrc = mf, mr, nzsrc
-    scal = BaseFDTD11.grid_scalars(V, Pp)
+    scal = BaseFDTD11.grid_scalars(V, Pp, kerr_lorentz=(mode == "lorentz_nl"))
     scal.update(cE0=float(V.UpExMat[0]), cE1=float(V.UpExMat[0]), cH0=float(V.UpHyMat[0]), cH1=float(V.UpHyMat[0]),
                 c2_pml=float(C_V.C2[1]))
     lg = LongGrid(Lg, mode=mode, pw=pw, mf=mf, mr=mr, nzsrc=nzsrc, dz=Pp.dz, dt=Pp.delT, courantNo=Pp.courantNo,

@@ -40,7 +40,7 @@ class Member:
         canon = dev.canonical_form(P, arrs, None)
         if canon is None or not dev.probes_ok_for_tiles(self.probe_idx):
             raise ValueError("sweep member is not in the tile engine's canonical form; run it through Controller")
-        self.scalars = BaseFDTD11.grid_scalars(V, P)
+        self.scalars = BaseFDTD11.grid_scalars(V, P, kerr_lorentz=SE.KERR_LORENTZ)
         self.scalars.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
         self.flags = BaseFDTD11.grid_flags(P, SE.USE_FMA, SE.USE_FP32, SE.CUBIC == "newton") | nat.PF_F_CANONICAL
         self.coef = {"beX": C_V.beX, "ceX": C_V.ceX, "cmY": C_V.cmY}
@@ -266,7 +266,7 @@ def run_two_pass_batch(objs, lorentz=True, k_block=0, rank=0, world_size=1, devi
     RefTester peak of the windowed x1ColAf over that of x1ColBe) is computed on the device and returned as
     an array; only the LAST owned member's traces are copied back into its V (the reference's sweep never
     looks at the others again).  Otherwise reflection is None and every member's traces are downloaded."""
-    mode = "lorentz" if lorentz else "free"
+    mode = ("lorentz_nl" if SE.KERR_LORENTZ else "lorentz") if lorentz else "free"
     mine = [i for i in range(len(objs)) if i % world_size == rank]
     srcs = {}
     peaks = [None, None]

@@ -54,6 +54,23 @@ def test_decomposed_long_grid_is_bit_identical_to_oracle(lg, k, max_piece):
     assert np.array_equal(probe, pa.probe_out[0, :nsteps])
 
 
+def test_decomposed_kerr_lorentz_grid_matches_oracle(lg):
+    """Config 5's material (PF_LORENTZ_NL: Lorentz ADE + cubic Kerr law) on a decomposed grid."""
+    Lg, T, nsteps = 40_000, 512, 300
+    grid, info = lg.lorentz_long_grid(Lg, T=T, k=64, max_piece=9000, mode="lorentz_nl")
+    assert len(grid.pieces) >= 4
+    grid.run(nsteps, do_pol=True)
+    pa = oracle_long(info, Lg, T, nsteps, mode="lorentz_nl")
+    sl = slice(info["mf"], info["mr"])
+    scale = np.max(np.abs(pa.Ex))
+    assert scale > 0
+    for name, want in (("Ex", pa.Ex), ("Hy", pa.Hy), ("Dx", pa.Dx), ("P", pa.P)):
+        got = grid.gather_owned(name)
+        if name in ("Dx", "P"):
+            got, want = got[sl], want[sl]
+        assert np.max(np.abs(got - want)) <= 1e-10 * np.max(np.abs(want)), name
+
+
 def test_long_free_space_grid(lg):
     Lg, T, nsteps = 30_000, 256, 200
     grid, info = lg.lorentz_long_grid(Lg, T=T, k=32, max_piece=8000, mode="free")

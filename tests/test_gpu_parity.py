@@ -641,3 +641,56 @@ def test_newton_cubic_root0_random_polynomials(pk):
         assert got[i] == pytest.approx(want, rel=1e-11)
     a, b, c, d = co.T
     assert np.max(np.abs(((a * got + b) * got + c) * got + d) / -d) <= 1e-14
+
+
+# ---- PF_LORENTZ_NL: Kerr-Lorentz composition (BASELINE config 5's "dispersive and nonlinear" material) ----------
+KERR_SPEC = dict(mode="lorentz", freq=9e9, dom=0.15, win=[300, 320], source="gauss", amplitude=4.0)
+
+
+@pytest.mark.parametrize("engine", ["tile", "ops"])
+def test_kerr_lorentz_composition_matches_oracle(pk, engine):
+    """Not a reference integrator (the reference's NL loop has no dispersion ADE): both engines against the
+    C oracle's statement of the composition; everything but the cubic root is bit-identical."""
+    want = fo.run_case(oracle_case(dict(KERR_SPEC, mode="lorentz_nl")))
+    pk.SE.KERR_LORENTZ, pk.SE.ENGINE = True, engine
+    try:
+        V, P, C_V, C_P = pk.build_objects(KERR_SPEC)
+        V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    finally:
+        pk.SE.KERR_LORENTZ, pk.SE.ENGINE = False, "auto"
+    assert pk.SE.LAST_RUN_INFO["engine"] == engine
+    assert np.max(want["Acubic"]) > 1.0            # the Kerr term matters: |E|^2 > 1 somewhere in the slab
+    for nm, got in (("Ex", V.Ex), ("Hy", V.Hy), ("Dx", V.Dx), ("P", V.polarisationCurr), ("x1ColBe", V.x1ColBe),
+                    ("x1ColAf", V.x1ColAf), ("Acubic", V.Acubic)):
+        assert rel_err(got, want[nm]) <= RTOL, (nm, rel_err(got, want[nm]))
+    assert np.array_equal(V.x1ColBe, want["x1ColBe"])   # pass 0 never reaches a polarised cell differently
+
+
+def test_kerr_lorentz_with_zero_chi3_is_the_reference_lorentz_integrator(pk):
+    """chi3 = 0: the cubic degenerates to A = |Dn/eps0|^2 and Ex = Dn/eps0 -- bit-identical to IntegratorLinLor1D,
+    which pins the composition to the reference's Lorentz golden in its linear limit."""
+    g = load_golden("lorentz_gauss")
+    pk.SE.KERR_LORENTZ = True
+    try:
+        V, P, C_V, C_P = pk.build_objects(g["spec"])
+        V.chi3Stat = 0.0
+        V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    finally:
+        pk.SE.KERR_LORENTZ = False
+    want = fo.run_case(oracle_case(g["spec"]))
+    for nm, got in (("Ex", V.Ex), ("Hy", V.Hy), ("Dx", V.Dx), ("P", V.polarisationCurr), ("x1ColAf", V.x1ColAf)):
+        assert np.array_equal(got, want[nm]), nm
+        assert rel_err(got, g["polarisationCurr" if nm == "P" else nm]) <= RTOL
+
+
+def test_kerr_lorentz_fp32_and_newton_variants(pk):
+    want = fo.run_case(oracle_case(dict(KERR_SPEC, mode="lorentz_nl")))
+    for fp32, cubic, tol in ((False, "newton", RTOL), (True, "closed", FP32_TOL)):
+        pk.SE.KERR_LORENTZ, pk.SE.USE_FP32, pk.SE.CUBIC = True, fp32, cubic
+        try:
+            V, P, C_V, C_P = pk.build_objects(KERR_SPEC)
+            V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+        finally:
+            pk.SE.KERR_LORENTZ, pk.SE.USE_FP32, pk.SE.CUBIC = False, False, "closed"
+        for nm, got in (("Ex", V.Ex), ("Hy", V.Hy), ("x1ColAf", V.x1ColAf)):
+            assert rel_err(got, want[nm]) <= tol, (fp32, cubic, nm, rel_err(got, want[nm]))

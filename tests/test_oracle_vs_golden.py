@@ -111,3 +111,26 @@ def test_sweep_reflection_matches_reference():
         assert fo.analytical_reflection(freq, wp_prev, med["w0"], med["gam"]) == pytest.approx(
             float(g["analytical"][i]), rel=1e-12)
         freq = freq + s["interval"]
+
+
+def test_kerr_lorentz_composition_reduces_to_the_reference_lorentz_path():
+    """Mode "lorentz_nl" is builder-defined (the reference's nonlinear loop has no dispersion ADE).  Its
+    linear limit chi3 = 0 must be the reference's Lorentz integrator bit for bit (golden), and a non-zero chi3
+    must change the result at the expected order (chi3 |E|^2)."""
+    import fdtd_oracle as fo
+    from conftest import load_golden
+    g = load_golden("lorentz_gauss")
+    s = g["spec"]
+    kw = dict(source=s.get("source", "sine"), tfsf=s.get("tfsf", True), periods=s.get("periods", 1000.0),
+              epsRe=s.get("epsRe", 1.0), amplitude=s.get("amplitude", 1.0))
+    c = fo.make_case("lorentz_nl", s["freq"], s["dom"], *s["win"], **kw)
+    c.medium = dict(c.medium, chi3=0.0)
+    out = fo.run_case(c)
+    for nm, gold in (("Ex", "Ex"), ("Hy", "Hy"), ("P", "polarisationCurr"), ("x1ColAf", "x1ColAf")):
+        assert np.array_equal(out[nm], g[gold]), nm
+    c = fo.make_case("lorentz_nl", s["freq"], s["dom"], *s["win"], **kw)
+    out = fo.run_case(c)
+    peak = np.max(np.abs(g["x1ColAf"]))
+    diff = np.max(np.abs(out["x1ColAf"] - g["x1ColAf"])) / peak
+    a2 = float(np.max(out["Acubic"]))
+    assert a2 > 0 and 1e-3 * c.medium["chi3"] * a2 < diff < 10 * c.medium["chi3"] * a2
