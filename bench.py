@@ -172,9 +172,8 @@ def extras(torch, peak_gbs, quick=False):
     for name, mode, cells, alg, kw in (("free_long_grid", "free", 1 << 24, 32.0, {}),
                                        ("lorentz_long_grid", "lorentz", big, 32.0 + 0.7 * 40.0, {}),
                                        # config 5 as BASELINE words it: dispersive AND nonlinear (PF_LORENTZ_NL, the
-                                       # Lorentz ADE + the cubic Kerr law on Dx - P); closed-form and Newton root
+                                       # Lorentz ADE + the cubic Kerr law on Dx - P, converged Newton root)
                                        ("kerr_lorentz_long_grid", "lorentz_nl", big, 32.0 + 0.7 * 40.0, {}),
-                                       ("kerr_lorentz_long_grid_newton", "lorentz_nl", big, 32.0 + 0.7 * 40.0, {"newton": True}),
                                        ("lorentz_long_grid_fp32", "lorentz", big, 32.0 + 0.7 * 40.0, {"fp32": True})):
         steps = 128
         grid, info = longgrid.lorentz_long_grid(cells, T=steps + 64, k=64, mode=mode, **kw)

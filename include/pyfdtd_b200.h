@@ -41,8 +41,11 @@ enum {
                          integrator (its nonlinear loop has no dispersion ADE): the IntegratorLinLor1D
                          loop with ADE_ExCreate (BaseFDTD11.py:712-725) replaced by the reference's cubic
                          chain (BaseFDTD11.py:793-877) applied to Dn = Dx - P:
-                           Acubic = root0([cub_a, cub_b, cub_c, -|Dn/eps0|^2]) (0 where |d| <= 1e-8),
+                           Acubic = positive root of [cub_a, cub_b, cub_c, -|Dn/eps0|^2] (0 where |d| <= 1e-8),
                            Ex = Dn / (nl_den0 + nl_den1*Acubic).
+                         The root is the converged (Newton) one whenever cub_a, cub_b >= 0, cub_c > 0: with
+                         Kerr coefficients the reference's closed form runs in its ill-conditioned
+                         three-real-root branch (acos near +-1), where libm implementations differ at 1e-8.
                          Builder-defined composition; parity is against oracle/fdtd_oracle.c only.  */
 };
 

@@ -186,9 +186,33 @@ void orc_nl_ex(OrcGrid *g)
  * carries the dispersive polarisation P (orc_pol_update), and the instantaneous Kerr response is solved
  * on what is left of D, Dn = Dx - P (the numerator of ADE_ExCreate, BaseFDTD11.py:712-725), with the
  * reference's own cubic chain (BaseFDTD11.py:793-877):
- *   Acubic = root0([cub, qua, one, -|Dn/eps0|^2]) if that |d| > 1e-8 else 0;  Ex = Dn/(den0 + den1*Acubic)
+ *   Acubic = positive root of [cub, qua, one, -|Dn/eps0|^2] if that |d| > 1e-8 else 0;  Ex = Dn/(den0 + den1*Acubic)
  * With cub = chi3^2, qua = 2*eps_inf*chi3, one = eps_inf^2, den0 = eps0*eps_inf, den1 = eps0*chi3 this is
  * Dn = eps0*(eps_inf + chi3*|E|^2)*E. */
+/* The composition's Acubic is DEFINED as the positive root of the cubic, converged to rounding level.  The
+ * reference's closed form is not used here: with Kerr coefficients (cub = chi3^2, qua = 2 chi3, one = 1) it runs
+ * in its three-real-root branch, x = 2 j cos(acos(.)/3) - b/3a, which is ill-conditioned (acos near +-1
+ * amplifies one ulp of its argument to ~1e-8 of the root), so two libm implementations disagree at 1e-8.
+ * For a, b >= 0, c > 0, q2 > 0 the polynomial is increasing and convex on x > 0 and every single term bounds
+ * the root from above, so Newton from x0 = min(q2/c, sqrt(q2/b), cbrt(q2/a)) descends monotonically. */
+double orc_cubic_root_newton(double a, double b, double c, double q2)
+{
+    if (!(a >= 0 && b >= 0 && c > 0))
+        return orc_cubic_root0(a, b, c, -q2);
+    double x = q2 / c;
+    if (b > 0 && sqrt(q2 / b) < x) x = sqrt(q2 / b);
+    if (a > 0 && cbrt(q2 / a) < x) x = cbrt(q2 / a);
+    for (int it = 0; it < 200; ++it) {
+        double p = ((a * x + b) * x + c) * x - q2;
+        double dp = (3.0 * a * x + 2.0 * b) * x + c;
+        double step = p / dp;
+        x -= step;
+        if (fabs(step) <= 1e-13 * x)
+            break;
+    }
+    return x;
+}
+
 void orc_acubic_dn(OrcGrid *g)
 {
     for (int nz = g->mf; nz < g->mr; ++nz) {
@@ -196,7 +220,7 @@ void orc_acubic_dn(OrcGrid *g)
         double d = -pow(q, 2.0);
         double out = 0.0;
         if (fabs(d) > 1e-8)
-            out = orc_cubic_root0(g->cub_a, g->cub_b, g->cub_c, d);
+            out = orc_cubic_root_newton(g->cub_a, g->cub_b, g->cub_c, -d);
         g->Acubic[nz] = out;
     }
 }

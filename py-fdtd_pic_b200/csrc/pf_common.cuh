@@ -37,6 +37,7 @@ int check_cuda(cudaError_t e, const char *what);
 // ---------------------------------------------------------------------------------------------
 struct Exact {
     using real = double;
+    static constexpr bool newton = false;
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
@@ -47,6 +48,7 @@ struct Exact {
 };
 struct Fused {
     using real = double;
+    static constexpr bool newton = false;
     static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
     static __device__ __forceinline__ double add(double a, double b) { return a + b; }
     static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
@@ -56,8 +58,14 @@ struct Fused {
 
 // PF_F_FP32: the on-chip state is advanced in single precision with contraction.  Not a parity mode:
 // reported against a stated 1e-5 tolerance (fields relative to the peak of the trace).
+// PF_F_NEWTON in the tile engine: Exact arithmetic everywhere except the cubic material law, which is the
+// inlined Newton iteration (cubic_root0_newton) with reciprocal-multiply divisions.
+struct ExactNewton : Exact {
+    static constexpr bool newton = true;
+};
 struct Fast32 {
     using real = float;
+    static constexpr bool newton = false;
     static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
     static __device__ __forceinline__ float add(float a, float b) { return a + b; }
     static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
@@ -211,21 +219,83 @@ __device__ __forceinline__ double cubic_root0(const CubicConsts &k, double d)
 // The result is the correctly converged root (|p| at rounding level); the reference's closed form loses
 // ~4 digits to cancellation in (S+U) - b/3a, so the two differ by up to ~1e-11 absolute, inside the
 // 1e-10 absolute tolerance Acubic is held to (its effect on Ex is below 1e-14 relative).
-__device__ __forceinline__ double cubic_root0_newton(const CubicConsts &k, double q2)
+// General starting point and true divisions: used when x0 = q^2/c is far from the root (p'(x0) > 1.5 c), where the
+// carried reciprocal of the fast path would lag behind.  Out of line: rare on the grid path.
+static __device__ __noinline__ double cubic_root0_newton_far(double a, double b, double c, double q2)
 {
-    const double a3 = 3.0 * k.a, b2 = 2.0 * k.b;
-    double x = q2 * k.inv_c, r = k.inv_c, step;
+    double x = q2 / c;                                   // each single term bounds the root from above
+    if (b > 0.0) x = fmin(x, sqrt(q2 / b));
+    if (a > 0.0) x = fmin(x, cbrt(q2 / a));
+    const double a3 = 3.0 * a, b2 = 2.0 * b;
+    for (int it = 0; it < 100; ++it) {
+        const double p = fma(fma(fma(a, x, b), x, c), x, -q2);
+        const double dp = fma(fma(a3, x, b2), x, c);
+        const double step = p / dp;
+        x -= step;
+        if (fabs(step) <= 1e-10 * x) {                   // one more step from here is converged to rounding
+            const double p2 = fma(fma(fma(a, x, b), x, c), x, -q2);
+            x -= p2 / fma(fma(a3, x, b2), x, c);
+            break;
+        }
+    }
+    return x;
+}
+
+__device__ __forceinline__ double cubic_root0_newton(double a, double b, double c, double inv_c, double q2)
+{
+    const double a3 = 3.0 * a, b2 = 2.0 * b;
+    double x = q2 * inv_c, r = inv_c, step;
+    if (fma(fma(a3, x, b2), x, c) * inv_c > 1.5) return cubic_root0_newton_far(a, b, c, q2);
     int it = 0;
     do {
-        const double p = fma(fma(fma(k.a, x, k.b), x, k.c), x, -q2);
-        const double dp = fma(fma(a3, x, b2), x, k.c);
-        r = fma(r, fma(-dp, r, 1.0), r);
+        const double p = fma(fma(fma(a, x, b), x, c), x, -q2);
+        const double dp = fma(fma(a3, x, b2), x, c);
+        r = fma(r, fma(-dp, r, 1.0), r);                 // 0 < r dp < 2 always: dp only decreases from p'(x0) <= 1.5 c
         step = p * r;
         x -= step;
         ++it;
         // superlinear: once a step is below 1e-10 x the error left after it is far below one ulp
     } while (it < 3 || (it < 24 && fabs(step) > 1e-10 * x));
     return x;
+}
+__device__ __forceinline__ double cubic_root0_newton(const CubicConsts &k, double q2)
+{
+    return cubic_root0_newton(k.a, k.b, k.c, k.inv_c, q2);
+}
+
+// 1/x to ~1 ulp for normal positive x (MUFU seed + two Newton steps); PF_F_NEWTON's material law only.
+__device__ __forceinline__ double rcp_newton(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+// The nonlinear material law of one cell under PF_F_NEWTON, small enough to be inlined: Acubic by Newton
+// iteration, |Dn/eps0| and Dn/(den0 + den1 A) by reciprocal multiplication (each within ~1 ulp of the
+// reference's divisions; the mode's tolerance is 1e-10).
+struct NlNewtonConsts {
+    double a, b, c, inv_c;
+};
+#ifdef PF_NEWTON_NOINLINE   // tuning experiment: the law as a call
+#define PF_NEWTON_LAW_QUAL static __device__ __noinline__
+#else
+#define PF_NEWTON_LAW_QUAL __device__ __forceinline__
+#endif
+PF_NEWTON_LAW_QUAL void nl_material_law_newton(const NlNewtonConsts &k, double dn, double inv_eps0, double den0,
+                                                       double den1, double &acub, double &e)
+{
+    const double q = dn * inv_eps0;
+    const double q2 = q * q;
+    double x = 0.0;
+    if (q2 > 1e-8) x = cubic_root0_newton(k.a, k.b, k.c, k.inv_c, q2);
+    const double den = fma(den1, x, den0);
+    const double r = rcp_newton(den);
+    const double e0 = dn * r;
+    acub = x;
+    e = fma(fma(-den, e0, dn), r, e0);
 }
 
 // Acubic of one cell: root0 of [cub, qua, one, -|Dx/eps0|^2] if |d| > 1e-8 else 0

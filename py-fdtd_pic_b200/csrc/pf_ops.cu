@@ -293,6 +293,8 @@ int ops_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, doub
                  int snap_interval, int snap_rows, cudaStream_t st)
 {
     GridDev gd = make_grid_dev(*g);
+    // PF_LORENTZ_NL is specified with the converged (Newton) root wherever the coefficients admit it
+    if (mode == PF_LORENTZ_NL && g->cub_a >= 0.0 && g->cub_b >= 0.0 && g->cub_c > 0.0) gd.k.newton = 1;
     for (int n = n0; n < n0 + nsteps; ++n) {
         int rc = ops_step(g, gd, mode, do_pol, n, st);
         if (rc) return rc;

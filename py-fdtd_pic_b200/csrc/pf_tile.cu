@@ -159,7 +159,7 @@ struct StepConsts {
     // hi + lo pairs, so that no coefficient rounding accumulates as a phase drift.
     R cEs_lo, dtdz_lo;
     R pG, pK;            // fp32 mode: Lorentz ADE in difference form, G = 1 + B, K = 1 - A - B
-    R ca, cb, cc;        // fp32 mode: cubic coefficients
+    R ca, cb, cc, inv_cc;   // fp32 / Newton modes: cubic coefficients (and 1/c) in registers
     int jsrc, jtfsf;
     bool wSrc;
     unsigned mSlab;
@@ -267,6 +267,12 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                     acub[j] = nl.a;
                     e = nl.e;
                 }
+            } else if constexpr (A::newton) {   // PF_F_NEWTON: small enough to be inlined per cell
+                if (!GEN || ((K.mSlab >> j) & 1)) {
+                    dx[j] = A::mad(dH, K.dtdz, dx[j]);
+                    const R dn = LOR ? A::sub(dx[j], pnow) : dx[j];
+                    nl_material_law_newton(NlNewtonConsts{K.ca, K.cb, K.cc, K.inv_cc}, dn, K.inv_eps0, K.den0, K.den1, acub[j], e);
+                }
             } else if (!GEN) {
                 dx[j] = A::mad(dH, K.dtdz, dx[j]);      // the material law of all C cells follows the loop
             } else if ((K.mSlab >> j) & 1) {
@@ -278,7 +284,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
         }
         ex[j] = e;
     }
-    if constexpr ((MODE == PF_NL || MODE == PF_LORENTZ_NL) && ALL_MAT && !F32) {
+    if constexpr ((MODE == PF_NL || MODE == PF_LORENTZ_NL) && ALL_MAT && !F32 && !A::newton) {
         NlVec<C> dv;
 #pragma unroll
         for (int j = 0; j < C; ++j) dv.v[j] = LOR ? A::sub(dx[j], POL ? pq[j] : pc[j]) : dx[j];
@@ -442,7 +448,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
         K.pA = g.polA; K.pB = g.polB; K.pC = g.polC * sD; K.den0 = g.nl_den0 * sD; K.den1 = g.nl_den1 * sD;
     }
     K.pG = (R)(1.0 + g.polB); K.pK = (R)((1.0 - g.polA) - g.polB);
-    K.ca = (R)g.cub_a; K.cb = (R)g.cub_b; K.cc = (R)g.cub_c;
+    K.ca = (R)g.cub_a; K.cb = (R)g.cub_b; K.cc = (R)g.cub_c; K.inv_cc = (R)TG.d.k.inv_c;
     K.jsrc = M.jsrc; K.jtfsf = M.jtfsf; K.mSlab = mSlab;
     K.wSrc = __any_sync(0xffffffffu, M.jsrc >= 0 || M.jtfsf >= 0);
     const CubicConsts *kc = &TG.d.k;
@@ -540,7 +546,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 }
 
 #ifndef PF_TILE_MINBLOCKS_F32
-#define PF_TILE_MINBLOCKS_F32 2
+#define PF_TILE_MINBLOCKS_F32 4   // measured on the Lorentz sweep: C=2 x 4 CTAs/SM 1023, C=2 x 3 978, C=4 x 3 869, C=4 x 2 762, C=1 x 2 778 Gcell-updates/s
 #endif
 template <class A>
 constexpr int tile_minblocks() { return std::is_same<typename A::real, float>::value ? PF_TILE_MINBLOCKS_F32 : PF_TILE_MINBLOCKS; }
@@ -761,7 +767,7 @@ struct ProfScope {
     }
 };
 
-enum { ARITH_EXACT = 0, ARITH_FUSED = 1, ARITH_FP32 = 2 };
+enum { ARITH_EXACT = 0, ARITH_FUSED = 1, ARITH_FP32 = 2, ARITH_NEWTON = 3 };
 
 template <int MODE, bool POL, int C, class A>
 static int launch_tile_a(int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
@@ -781,6 +787,9 @@ static int launch_tile(int arith, int n_tiles, const TileGrid *dg, const TileDes
                        int n0, int ks, int halo, cudaStream_t st)
 {
     if (arith == ARITH_FUSED) return launch_tile_a<MODE, POL, C, Fused>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    if constexpr (MODE == PF_NL || MODE == PF_LORENTZ_NL) {
+        if (arith == ARITH_NEWTON) return launch_tile_a<MODE, POL, C, ExactNewton>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    }
     return launch_tile_a<MODE, POL, C, Exact>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
 }
 
@@ -796,7 +805,7 @@ constexpr int TILE_C_FREE = PF_TILE_C_FREE;
 // wide = true: grids with (almost) no CPML cells, e.g. the pieces of a long grid -- 4 cells per thread
 // (measured 733 vs 684 Gcell-updates/s on a 1e8-cell Lorentz grid; the CPML-heavy sweep members prefer 2).
 #ifndef PF_TILE_C_F32
-#define PF_TILE_C_F32 4
+#define PF_TILE_C_F32 2
 #endif
 #ifndef PF_TILE_C_F32_FREE
 #define PF_TILE_C_F32_FREE 8
@@ -834,8 +843,12 @@ static int launch_tile_mode(int mode, int do_pol, int fma, bool wide, int n_tile
 static int arith_of(const PfGrid *grids, int n, int mode, int *arith)
 {
     int a = ARITH_EXACT;
+    const bool cub = mode == PF_NL || mode == PF_LORENTZ_NL;
+    bool newton = cub;   // the inlined Newton law needs every grid of the launch to ask for it and to be admissible
     for (int m = 0; m < n; ++m) {
         const PfGrid &g = grids[m];
+        // (PF_LORENTZ_NL is specified with the converged root: Newton whenever the coefficients admit it)
+        newton = newton && ((g.flags & PF_F_NEWTON) || mode == PF_LORENTZ_NL) && g.cub_a >= 0.0 && g.cub_b >= 0.0 && g.cub_c > 0.0;
         if (g.flags & PF_F_FP32) {
             // the fp32 cubic root is a Newton iteration that needs an increasing, convex polynomial
             if ((mode == PF_NL || mode == PF_LORENTZ_NL) && !(g.cub_a >= 0.0 && g.cub_b >= 0.0 && g.cub_c > 0.0))
@@ -845,6 +858,7 @@ static int arith_of(const PfGrid *grids, int n, int mode, int *arith)
             a = ARITH_FUSED;
         }
     }
+    if (a == ARITH_EXACT && newton) a = ARITH_NEWTON;
     *arith = a;
     return 0;
 }

@@ -11,6 +11,10 @@ import bench  # noqa: E402
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+variant = sys.argv[3] if len(sys.argv) > 3 else "closed"      # closed | newton | fp32
+from pyfdtd_b200 import Solver_Engine as SE  # noqa: E402
+SE.CUBIC = "newton" if variant == "newton" else "closed"
+SE.USE_FP32 = variant == "fp32"
 batch, members = bench.build_nl_batch(M, S)
 
 
@@ -21,4 +25,4 @@ def step():
 
 sec = bench._time_cuda(torch, step, 2)
 slab = sum(m.scalars["mr"] - m.scalars["mf"] for m in members)
-print({"members": M, "steps": S, "Gcell_updates_per_s": batch.cell_steps / sec / 1e9, "cubic_solves_per_s": slab * S / sec})
+print({"variant": variant, "members": M, "steps": S, "Gcell_updates_per_s": batch.cell_steps / sec / 1e9, "cubic_solves_per_s": slab * S / sec})
