@@ -181,12 +181,14 @@ __device__ __forceinline__ NlResultF nl_material_law_f32(float ca, float cb, flo
     float x = 0.f;
     if (d > 1e-8f) {
         x = __fdividef(d, cc);
-#pragma unroll
-        for (int it = 0; it < 3; ++it) {
+        float step;
+        int it = 0;
+        do {   // two iterations in the weakly nonlinear regime of the sweeps; ~log_1.5(x0/root) more when x0 is far above
             const float p = fmaf(fmaf(fmaf(ca, x, cb), x, cc), x, -d);
             const float dp = fmaf(fmaf(3.f * ca, x, 2.f * cb), x, cc);
-            x -= __fdividef(p, dp);
-        }
+            step = __fdividef(p, dp);
+            x -= step;
+        } while (++it < 48 && fabsf(step) > 1e-6f * x);
     }
     r.a = x;
     r.e = __fdividef(dx, fmaf(den1, x, den0));
