@@ -239,6 +239,14 @@ int pf_pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void
 int pf_pic_check(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
 /* deterministic cell-sorted deposition of Jx (requires particles sorted by cell)               */
 int pf_pic_deposit(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
+/* One whole particle step for a cell-sorted set: pf_pic_push_sorted with the deposition of the NEW state fused
+ * into its move pass (the particles are deposited while they are in registers; saves re-reading them).  Jx is
+ * deterministic (fixed summation tree: per old cell and sub-warp, lane-strided in chunk order, xor butterfly, then
+ * a fixed-order sum of the partial sums per node) but the tree differs from pf_pic_deposit's, so the two agree to
+ * rounding (~1e-15 relative), not bit for bit; oracle/pic_oracle.py: deposit_fused().  pf_pic_sub_warps() is the
+ * number of sub-warps per cell the tree is built with (a function of n / L).                        */
+int pf_pic_step_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream);
+int pf_pic_sub_warps(const PfPic *p);
 size_t pf_pic_scratch_bytes(const PfPic *p);
 
 #ifdef __cplusplus

@@ -91,6 +91,65 @@ def deposit(z, ux, uz, w, cell, L, *, dz, c, jx_scale):
     return jx_scale * J
 
 
+def sub_warps(n, L, sub_max=8):
+    """pic_sub_warps() of csrc/pf_pic.cu: warps per cell of the fused push + re-sort (+ deposit)."""
+    per_cell = n // max(1, L)
+    return int(min(sub_max, max(1, (per_cell + 255) // 256)))
+
+
+def deposit_fused(z, ux, uz, w, cell_old, cell_new, L, S, *, dz, c, jx_scale):
+    """Summation tree of pf_pic_step_sorted (k_pic_move<true> + k_pic_flush4).  Arrays are the PUSHED particles in their
+    OLD order (sorted by cell_old).  Sub-warp s of old cell cc owns a contiguous piece of the cell's particles (a multiple
+    of 32 long); lane l adds, in chunk order, the CIC shares of particles l, l+32, ... of the piece at the four nodes
+    cc-1 .. cc+2; lanes are combined by the xor butterfly 16,8,4,2,1; node nz = jx_scale * (sum over old cells
+    nz-2 .. nz+1 ascending, sub-warps ascending, of the partial sum that cell holds for nz)."""
+    assert np.all(np.diff(cell_old) >= 0), "particles must be sorted by their old cell"
+    inv_dz = 1.0 / dz
+    inv_c2 = 1.0 / (c * c)
+    g = np.sqrt(1.0 + (ux * ux + uz * uz) * inv_c2)
+    wv = w * (ux / g)
+    f = z * inv_dz - cell_new
+    t0 = wv * (1.0 - f)
+    t1 = wv * f
+    starts = np.searchsorted(cell_old, np.arange(L + 1), side="left")
+    part = np.zeros((L, S, 4))
+    lanes = np.arange(32)
+    for cc in range(L):
+        a0, b0 = int(starts[cc]), int(starts[cc + 1])
+        if a0 == b0:
+            continue
+        q = (((b0 - a0) + S - 1) // S + 31) // 32 * 32
+        for s in range(S):
+            lo = min(b0, a0 + s * q)
+            hi = min(b0, lo + q)
+            if lo == hi:
+                continue
+            d = np.clip(cell_new[lo:hi].astype(np.int64) - cc, -1, 1)
+            n = hi - lo
+            con = np.zeros((n, 4))
+            for dd in (-1, 0, 1):
+                m = d == dd
+                con[m, dd + 1] = t0[lo:hi][m]
+                con[m, dd + 2] = t1[lo:hi][m]
+            rows = np.concatenate([con, np.zeros(((-n) % 32, 4))]).reshape(-1, 32, 4)
+            lane = np.zeros((32, 4))
+            for r in rows:
+                lane = lane + r
+            for off in (16, 8, 4, 2, 1):
+                lane = lane + lane[lanes ^ off]
+            part[cc, s] = lane[0]
+    v = np.zeros(L)
+    for dc in (-2, -1, 0, 1):
+        k = 1 - dc
+        src = np.arange(L) + dc
+        ok = (src >= 0) & (src < L)
+        for s in range(S):
+            add = np.zeros(L)
+            add[ok] = part[src[ok], s, k]
+            v = v + add
+    return jx_scale * v
+
+
 def make_beam(n, L, dz, *, gamma=1.2, thermal=0.01, c=299792458.0, seed=1234, zlo=0.05, zhi=0.95):
     """uniform in z, beam gamma along z with a relative thermal spread."""
     rng = np.random.default_rng(seed)

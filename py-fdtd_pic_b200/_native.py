@@ -92,6 +92,8 @@ SYMBOLS = {
     "pf_pic_push_sorted": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
     "pf_pic_check": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
     "pf_pic_deposit": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
+    "pf_pic_step_sorted": (c_int, [_PP, c_void_p, c_size_t, c_void_p]),
+    "pf_pic_sub_warps": (c_int, [_PP]),
     "pf_pic_scratch_bytes": (c_size_t, [_PP]),
 }
 

@@ -213,9 +213,16 @@ __global__ void __launch_bounds__(1024) k_pic_scan(const int *__restrict__ count
     if (t == 1023) new_start[L] = part[1023];
 }
 
+// DEP = true additionally deposits while the particles are in registers (pf_pic_step_sorted): lane l of sub-warp
+// (c, s) accumulates, in chunk order, the CIC shares of its particles at the four nodes c-1 .. c+2 a particle of old
+// cell c can touch; the 32 lanes are combined by the fixed xor butterfly and the four sums go to part[(c*S+s)*4 + k].
+// k_pic_flush4 then adds the partial sums of every node in a fixed order.  Deterministic (no atomics), but a
+// different summation tree from pf_pic_deposit's -- oracle/pic_oracle.py: deposit_fused().
+template <bool DEP>
 __global__ void __launch_bounds__(PIC_THREADS) k_pic_move(PfPic p, PicDerived D, const long long *__restrict__ start,
                                                           const int *__restrict__ counts, const int *__restrict__ tot,
-                                                          const long long *__restrict__ new_start, int S)
+                                                          const long long *__restrict__ new_start, int S,
+                                                          double *__restrict__ part)
 {
     const long long wid = ((long long)blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -223,7 +230,11 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_move(PfPic p, PicDerived D,
     if (c >= p.L) return;
     long long a, b;
     sub_range(start[c], start[c + 1], S, sub, a, b);
-    if (a == b) return;
+    if (a == b) {
+        if (DEP && lane < 4) part[((size_t)c * S + sub) * 4 + lane] = 0.0;
+        return;
+    }
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     const unsigned lt = (1u << lane) - 1u;
     // first slot of each group in the new order (tot = per-cell totals), advanced past the cell's earlier sub-warps
     long long posL = 0, posS, posR = 0;
@@ -260,10 +271,52 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_move(PfPic p, PicDerived D,
             p.w_alt[dst] = w;
             p.cell_alt[dst] = c + d;
         }
+        if (DEP) {
+            double t0 = 0.0, t1 = 0.0;
+            if (i < b) {
+                const double g = sqrt(1.0 + (r.ux * r.ux + r.uz * r.uz) * D.inv_c2);
+                const double wv = w * (r.ux / g);
+                const double f = r.z * D.inv_dz - (double)(c + d);
+                t0 = wv * (1.0 - f);
+                t1 = wv * f;
+            }
+            // shares at nodes c-1, c, c+1, c+2 (adding 0.0 is exact, so absent lanes / other nodes do not perturb the sums)
+            acc0 = acc0 + (d == -1 ? t0 : 0.0);
+            acc1 = acc1 + (d == -1 ? t1 : (d == 0 ? t0 : 0.0));
+            acc2 = acc2 + (d == 0 ? t1 : (d == 1 ? t0 : 0.0));
+            acc3 = acc3 + (d == 1 ? t1 : 0.0);
+        }
         posL += __popc(bl);
         posS += __popc(bs);
         posR += __popc(br);
     }
+    if (DEP) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, off);
+            acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, off);
+            acc2 = acc2 + __shfl_xor_sync(0xffffffffu, acc2, off);
+            acc3 = acc3 + __shfl_xor_sync(0xffffffffu, acc3, off);
+        }
+        if (lane == 0) {
+            double *o = part + ((size_t)c * S + sub) * 4;
+            o[0] = acc0; o[1] = acc1; o[2] = acc2; o[3] = acc3;
+        }
+    }
+}
+
+// node nz = scale * sum over old cells c = nz-2 .. nz+1 (ascending), sub-warps ascending, of part[c][s][nz - c + 1]
+__global__ void __launch_bounds__(PIC_THREADS) k_pic_flush4(PfPic p, const double *__restrict__ part, int S)
+{
+    const int nz = blockIdx.x * PIC_THREADS + threadIdx.x;
+    if (nz >= p.L) return;
+    double v = 0.0;
+    for (int c = nz - 2; c <= nz + 1; ++c) {
+        if (c < 0 || c >= p.L) continue;
+        const int k = nz - c + 1;
+        for (int s2 = 0; s2 < S; ++s2) v = v + part[((size_t)c * S + s2) * 4 + k];
+    }
+    p.Jx[nz] = p.jx_scale * v;
 }
 
 // ------------------------------------------------------------------------------------------------ sort
@@ -302,7 +355,7 @@ static int key_bits(int L)
 }
 
 struct PicPlan {
-    size_t off_idx_in, off_idx_out, off_cub, off_acc, off_start, off_new_start, off_counts, off_tot, off_err, cub_bytes, total;
+    size_t off_idx_in, off_idx_out, off_cub, off_acc, off_start, off_new_start, off_counts, off_tot, off_part, off_err, cub_bytes, total;
 };
 
 static PicPlan pic_plan(const PfPic *p)
@@ -320,7 +373,8 @@ static PicPlan pic_plan(const PfPic *p)
     pl.off_new_start = pl.off_start + al256(sizeof(long long) * ((size_t)p->L + 1));
     pl.off_counts = pl.off_new_start + al256(sizeof(long long) * ((size_t)p->L + 1));
     pl.off_tot = pl.off_counts + al256(sizeof(int) * 3 * (size_t)p->L * PIC_SUB_MAX);
-    pl.off_err = pl.off_tot + al256(sizeof(int) * 3 * (size_t)p->L);
+    pl.off_part = pl.off_tot + al256(sizeof(int) * 3 * (size_t)p->L);
+    pl.off_err = pl.off_part + al256(sizeof(double) * 4 * (size_t)p->L * PIC_SUB_MAX);
     pl.total = pl.off_err + 256;
     return pl;
 }
@@ -415,12 +469,16 @@ int pf_pic_push(const PfPic *p, void *stream)
     return PF_OK;
 }
 
-int pf_pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream)
+static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream, bool deposit)
 {
     int rc = validate_pic(p);
     if (rc) return rc;
     if (!p->Ex || !p->Hy) return set_err(PF_E_ARG, "pf_pic_push_sorted: field arrays missing");
-    if (p->n == 0) return PF_OK;
+    if (deposit && !p->Jx) return set_err(PF_E_ARG, "pf_pic_step_sorted: Jx missing");
+    if (p->n == 0) {
+        if (deposit) PF_CUDA(cudaMemsetAsync(p->Jx, 0, sizeof(double) * (size_t)p->L, (cudaStream_t)stream));
+        return PF_OK;
+    }
     if (!p->z_alt || !p->ux_alt || !p->uz_alt || !p->w_alt || !p->cell_alt)
         return set_err(PF_E_ARG, "pf_pic_push_sorted: alternate (output) arrays missing");
     PicPlan pl = pic_plan(p);
@@ -441,10 +499,30 @@ int pf_pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void
     PF_LAUNCH_CHECK("k_pic_cell_totals");
     k_pic_scan<<<1, 1024, 0, st>>>(tot, p->L, new_start);
     PF_LAUNCH_CHECK("k_pic_scan");
-    k_pic_move<<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S);
-    PF_LAUNCH_CHECK("k_pic_move");
+    if (deposit) {
+        double *part = (double *)(s + pl.off_part);
+        k_pic_move<true><<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S, part);
+        PF_LAUNCH_CHECK("k_pic_move");
+        k_pic_flush4<<<(p->L + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(*p, part, S);
+        PF_LAUNCH_CHECK("k_pic_flush4");
+    } else {
+        k_pic_move<false><<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S, nullptr);
+        PF_LAUNCH_CHECK("k_pic_move");
+    }
     return PF_OK;
 }
+
+int pf_pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream)
+{
+    return pic_push_sorted(p, scratch, scratch_bytes, stream, false);
+}
+
+int pf_pic_step_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream)
+{
+    return pic_push_sorted(p, scratch, scratch_bytes, stream, true);
+}
+
+int pf_pic_sub_warps(const PfPic *p) { return p ? pic_sub_warps(p) : 1; }
 
 int pf_pic_check(const PfPic *p, void *scratch, size_t scratch_bytes, void *stream)
 {

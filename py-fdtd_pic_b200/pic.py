@@ -87,6 +87,24 @@ class ParticleSet:
         self._bind()
         self.sorted = True
 
+    def step_sorted(self, Ex, Hy):
+        """One whole particle step: push + stable re-sort + deposition of the new state, fused (pf_pic_step_sorted).
+        Returns the Jx tensor.  Same particles as push_sorted(); Jx equals deposit()'s to rounding (different, equally
+        deterministic summation tree)."""
+        if not self.sorted:
+            self.sort()
+        self.p.Ex, self.p.Hy = Ex.data_ptr(), Hy.data_ptr()
+        nat.check(nat.lib().pf_pic_step_sorted(ctypes.byref(self.p), self.scratch.data_ptr(), self.scratch_bytes,
+                                               nat.current_stream_ptr()), "pf_pic_step_sorted")
+        self.cur, self.alt = self.alt, self.cur
+        self.cell, self.cell_alt = self.cell_alt, self.cell
+        self._bind()
+        self.sorted = True
+        return self.Jx
+
+    def sub_warps(self):
+        return int(nat.lib().pf_pic_sub_warps(ctypes.byref(self.p)))
+
     def cfl_violated(self):
         return bool(nat.check(nat.lib().pf_pic_check(ctypes.byref(self.p), self.scratch.data_ptr(), self.scratch_bytes,
                                                      nat.current_stream_ptr()), "pf_pic_check"))
@@ -118,17 +136,24 @@ class CoupledPIC:
     ``grid`` is a _device.DeviceGrid whose descriptor gets its Jx pointer from the particle set; the
     field step runs through ENGINE_OPS (the engine that carries per-cell arrays, including Jx)."""
 
-    def __init__(self, grid, particles, mode="free"):
+    def __init__(self, grid, particles, mode="free", fused=False):
         from . import _device as dev
         self.grid, self.particles = grid, particles
         self.mode_id = dev.MODE_ID[mode]
         self.grid.g.Jx = particles.Jx.data_ptr()
         self.n = 0
+        self.fused = fused          # True: push + re-sort + deposit in one pass over the particles (step_sorted)
+        self._have_J = False
 
     def step(self, do_pol=False):
         lib = nat.lib()
-        self.particles.deposit()
+        if not (self.fused and self._have_J):
+            self.particles.deposit()
         nat.check(lib.pf_run_pass(self.grid.ref(), self.mode_id, int(do_pol), self.n, 1, nat.PF_ENGINE_OPS, None, 0, 0,
                                   None, 0, nat.current_stream_ptr()), "pf_run_pass")
-        self.particles.push_sorted(self.grid.tensor_view("Ex"), self.grid.tensor_view("Hy"))
+        if self.fused:               # the deposit of the pushed state is the current of the next field step
+            self.particles.step_sorted(self.grid.tensor_view("Ex"), self.grid.tensor_view("Hy"))
+            self._have_J = True
+        else:
+            self.particles.push_sorted(self.grid.tensor_view("Ex"), self.grid.tensor_view("Hy"))
         self.n += 1

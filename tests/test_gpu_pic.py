@@ -155,3 +155,62 @@ def test_fused_push_resort_equals_push_then_stable_sort(pic, n, L):
     J = ps.deposit().cpu().numpy()
     Jo = po.deposit(zo, uxo, uzo, wo, co, L, dz=dz, c=C0, jx_scale=Q)
     assert np.array_equal(J, Jo)
+
+
+@pytest.mark.parametrize("n,L", [(5000, 4097), (300_001, 4097), (200_003, 130), (77_777, 33), (0, 65)])
+def test_fused_step_push_resort_deposit(pic, n, L):
+    """pf_pic_step_sorted: the particles equal pf_pic_push_sorted's bit for bit; Jx equals the oracle's statement of
+    the fused summation tree bit for bit, and the plain deposit of the same particles to rounding."""
+    import torch
+    dz, dt = 8.3e-5, 2.6e-13
+    z, ux, uz, w, cell = po.make_beam(n, L, dz, seed=23, thermal=0.3)
+    Ex, Hy = fields(L, seed=9)
+    tEx, tHy = torch.as_tensor(Ex, device="cuda"), torch.as_tensor(Hy, device="cuda")
+    ps = pic.ParticleSet(z, ux, uz, w, L, dz, dt)
+    S = ps.sub_warps()
+    assert S == po.sub_warps(n, L)
+    zo, uxo, uzo, wo, co = po.sort_by_cell(z, ux, uz, w, cell)
+    for step in range(3):
+        J = ps.step_sorted(tEx, tHy).cpu().numpy()
+        zp, uxp, uzp, cp = po.push(zo, uxo, uzo, Ex, Hy, dz=dz, dt=dt, q_over_m=QM, c=C0, mu0=MU0)
+        Jf = po.deposit_fused(zp, uxp, uzp, wo, co, cp, L, S, dz=dz, c=C0, jx_scale=Q)   # pushed, old order
+        zo, uxo, uzo, wo, co = po.sort_by_cell(zp, uxp, uzp, wo, cp)
+        h = ps.host()
+        for k, want in (("z", zo), ("ux", uxo), ("uz", uzo), ("w", wo), ("cell", co)):
+            assert np.array_equal(h[k], want), (step, k)
+        assert np.array_equal(J, Jf), step
+        if n:
+            Jp = po.deposit(zo, uxo, uzo, wo, co, L, dz=dz, c=C0, jx_scale=Q)
+            assert rel(J, Jp) <= 1e-12
+    J2 = ps.deposit().cpu().numpy()            # the plain deposit still works on the result
+    if n:
+        assert rel(J2, J) <= 1e-12
+    else:
+        assert not np.any(J)
+
+
+def test_coupled_fused_step_matches_unfused(pic):
+    """CoupledPIC(fused=True) (field step, then push + re-sort + deposit in one pass) against the unfused sequence."""
+    from pyfdtd_b200 import BaseFDTD11, Solver_Engine as SE, _device as dev
+    from test_host_layer import build_objects
+    spec = dict(mode="free", freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000, epsRe=1.0)
+    outs = []
+    for fused in (False, True):
+        V, P, C_V, C_P = build_objects(spec)
+        C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=False)
+        L = len(V.Ex)
+        z, ux, uz, w, cell = po.make_beam(20_000, L, P.dz, seed=5)
+        ps = pic.ParticleSet(z, ux + 5e7, uz, w * 1e3, L, P.dz, P.delT)
+        arrs = BaseFDTD11._host_arrays(V, C_V, V.tempVarPol)
+        g = dev.DeviceGrid(L=L, T=P.timeSteps, arrays=arrs, scalars=BaseFDTD11.grid_scalars(V, P),
+                           srcE=np.asarray(Exs) / P.courantNo, srcH=np.asarray(Hys) / P.courantNo, probe_idx=[],
+                           flags=BaseFDTD11.grid_flags(P))
+        sim = pic.CoupledPIC(g, ps, mode="free", fused=fused)
+        for _ in range(20):
+            sim.step()
+        f = g.fetch(["Ex", "Hy"], probes=False)
+        outs.append((f["Ex"], f["Hy"], ps.host()))
+    (ExA, HyA, hA), (ExB, HyB, hB) = outs
+    assert np.max(np.abs(ExA)) > 0
+    assert rel(ExB, ExA) <= 1e-12 and rel(HyB, HyA) <= 1e-12
+    assert rel(hB["z"], hA["z"]) <= 1e-12 and rel(hB["ux"], hA["ux"]) <= 1e-12 and rel(hB["uz"], hA["uz"]) <= 1e-12

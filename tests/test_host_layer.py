@@ -219,3 +219,23 @@ def test_batched_ref_tester_matches_reference_ref_tester():
         assert val[m].item() == pytest.approx(TH.RefTester(None, P, y, 1)[2], rel=1e-12)
     with pytest.raises(ValueError):
         TH.ref_tester_batch(torch.ones((1, T), dtype=torch.float64), T)
+
+
+def test_pic_oracle_fused_summation_tree_agrees_with_the_plain_one():
+    """oracle/pic_oracle.py: deposit_fused (the tree of pf_pic_step_sorted) and deposit (pf_pic_deposit) sum the same
+    shares in different orders -- equal to rounding, and exactly charge-conserving in the same sense."""
+    import pic_oracle as po
+    L, dz, dt = 257, 8.3e-5, 2.6e-13
+    n = 40_000
+    z, ux, uz, w, cell = po.make_beam(n, L, dz, seed=3, thermal=0.3)
+    rng = np.random.default_rng(0)
+    Ex, Hy = 2e5 * rng.standard_normal(L), 5e2 * rng.standard_normal(L)
+    zo, uxo, uzo, wo, co = po.sort_by_cell(z, ux, uz, w, cell)
+    zp, uxp, uzp, cp = po.push(zo, uxo, uzo, Ex, Hy, dz=dz, dt=dt, q_over_m=-1.75882001076e11, c=299792458.0,
+                               mu0=1.25663706127e-06)
+    assert np.max(np.abs(cp.astype(np.int64) - co)) <= 1
+    for S in (1, 3, 8):
+        Jf = po.deposit_fused(zp, uxp, uzp, wo, co, cp, L, S, dz=dz, c=299792458.0, jx_scale=-1.6e-19)
+        Jp = po.deposit(*po.sort_by_cell(zp, uxp, uzp, wo, cp), L, dz=dz, c=299792458.0, jx_scale=-1.6e-19)
+        assert np.max(np.abs(Jf - Jp)) <= 1e-13 * np.max(np.abs(Jp))
+    assert po.sub_warps(20_000_000, 13194) == 6 and po.sub_warps(1000, 4097) == 1

@@ -37,5 +37,8 @@ t_ps = timed(lambda: ps.push_sorted(Ex, Hy))
 t_dep = timed(ps.deposit)
 t_push = timed(lambda: ps.push(Ex, Hy))
 ps.sort()
+t_fused = timed(lambda: ps.step_sorted(Ex, Hy))
+print("fused step (push + re-sort + deposit in the move pass) %.3f ms -> %.3e particle-steps/s" % (t_fused, n / t_fused * 1e3))
+ps.sort()
 print("n=%d  push_sorted %.3f ms  deposit %.3f ms  -> %.3e particle-steps/s;  plain push %.3f ms (%.3e /s)"
       % (n, t_ps, t_dep, n / (t_ps + t_dep) * 1e3, t_push, n / t_push * 1e3))
