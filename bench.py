@@ -238,6 +238,29 @@ def extras(torch, peak_gbs, quick=False):
             SE.USE_FP32, SE.CUBIC = False, "closed"
         del batch
         torch.cuda.empty_cache()
+    # --- the headline workload (config 2 sweep) in the optional arithmetic modes
+    if not quick:
+        modes = {}
+        for label, fma, fp32 in (("fma_contracted", True, False), ("fp32", False, True)):
+            SE.USE_FMA, SE.USE_FP32 = fma, fp32
+            try:
+                wl2 = ProductWorkload(1024, 512, 64)
+                b2 = wl2.batch
+                b2.upload()
+                b2.randomize_state(seed=1234)
+
+                def sweep_step():
+                    b2.reset_state(template=True)
+                    b2.run(do_pol=True)
+                sec = _time_cuda(torch, sweep_step, 3)
+                modes[label] = wl2.cell_steps / sec / 1e9
+            finally:
+                SE.USE_FMA, SE.USE_FP32 = False, False
+            del b2, wl2
+            torch.cuda.empty_cache()
+        out["lorentz_sweep_optional_modes_Gcell_updates_per_s"] = dict(
+            modes, note="same 1024-member workload as `value`; fma: PF_F_FMA (<= 1e-10 relative, tested); fp32: PF_F_FP32 "
+                        "(stated tolerance 1e-5 of the trace peak, profiles/r1g_fp32_accuracy.json)")
     # --- config 4: PIC push + cell sort + deterministic deposit
     L, dz, dt = 13194, 8.3276e-5, 2.6389e-13
     n = 2_000_000 if quick else 20_000_000
