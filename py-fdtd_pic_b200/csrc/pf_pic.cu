@@ -218,8 +218,11 @@ __global__ void __launch_bounds__(1024) k_pic_scan(const int *__restrict__ count
 // cell c can touch; the 32 lanes are combined by the fixed xor butterfly and the four sums go to part[(c*S+s)*4 + k].
 // k_pic_flush4 then adds the partial sums of every node in a fixed order.  Deterministic (no atomics), but a
 // different summation tree from pf_pic_deposit's -- oracle/pic_oracle.py: deposit_fused().
+#ifndef PF_PIC_MOVE_MINBLOCKS
+#define PF_PIC_MOVE_MINBLOCKS 4   // 62 instead of 78 registers for the depositing variant: 0.589 vs 0.616 ms per 2e7-particle step
+#endif
 template <bool DEP>
-__global__ void __launch_bounds__(PIC_THREADS) k_pic_move(PfPic p, PicDerived D, const long long *__restrict__ start,
+__global__ void __launch_bounds__(PIC_THREADS, DEP ? PF_PIC_MOVE_MINBLOCKS : 1) k_pic_move(PfPic p, PicDerived D, const long long *__restrict__ start,
                                                           const int *__restrict__ counts, const int *__restrict__ tot,
                                                           const long long *__restrict__ new_start, int S,
                                                           double *__restrict__ part)

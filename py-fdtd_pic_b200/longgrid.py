@@ -33,9 +33,13 @@ STATE_ALL = ("Ex", "Hy", "psiE", "psiH", "Dx", "P", "Pprev")
 # relative cost of one cell-update by cell class, measured on B200 with the tile engine (vacuum 60 ps,
 # Lorentz slab 131 ps per cell per 64-step block; CPML adds about the cost of a vacuum cell)
 CELL_COST = {"vacuum": 1.0, "slab": 2.2, "cpml": 1.0}
+# slab cell cost by integrator mode, from the 1-GPU rates of tools/bench_configs.py (vacuum 1680, Lorentz 837, Kerr-Lorentz
+# with the Newton root 201 Gcell-updates/s at a 70 % slab): equal-work rank boundaries need the mode's own ratio (with the
+# Lorentz ratio the Kerr-Lorentz grid scaled to 8 GPUs at 88.6 %)
+SLAB_COST = {"lorentz": 2.4, "lorentz_nl": 11.5, "nl": 11.5}
 
 
-def balanced_rank_cuts(Lg, pw, world_size, mf=None, mr=None):
+def balanced_rank_cuts(Lg, pw, world_size, mf=None, mr=None, slab_cost=None):
     """Rank boundaries that equalise the estimated WORK (not the cell count): the slab costs ~2.2x a
     vacuum cell, so equal-length ranges leave the vacuum-side ranks idle in every ghost exchange."""
     if mf is None or mr is None or world_size == 1:
@@ -46,7 +50,7 @@ def balanced_rank_cuts(Lg, pw, world_size, mf=None, mr=None):
         if b <= a:
             continue
         mid = (a + b) // 2
-        w = CELL_COST["slab"] if mf <= mid < mr else CELL_COST["vacuum"]
+        w = (slab_cost or CELL_COST["slab"]) if mf <= mid < mr else CELL_COST["vacuum"]
         if mid < pw or mid >= Lg - pw:
             w += CELL_COST["cpml"]
         seg.append((a, b, w))
@@ -64,7 +68,7 @@ def balanced_rank_cuts(Lg, pw, world_size, mf=None, mr=None):
     return cuts
 
 
-def plan_pieces(Lg, pw, world_size, k, max_piece=1 << 27, mf=None, mr=None):
+def plan_pieces(Lg, pw, world_size, k, max_piece=1 << 27, mf=None, mr=None, slab_cost=None):
     """Cut [0, Lg) into pieces.  Returns a list of dicts (rank, lo, hi) in global order.
 
     Rank boundaries balance the estimated work (``balanced_rank_cuts``; equal cell counts when the slab is
@@ -73,7 +77,7 @@ def plan_pieces(Lg, pw, world_size, k, max_piece=1 << 27, mf=None, mr=None):
     inside a piece is 32-bit)."""
     if Lg < 4 * k * world_size:
         raise ValueError("grid too short for this decomposition")
-    rank_cuts = balanced_rank_cuts(Lg, pw, world_size, mf, mr)
+    rank_cuts = balanced_rank_cuts(Lg, pw, world_size, mf, mr, slab_cost)
     if any(b - a < 4 * k for a, b in zip(rank_cuts[:-1], rank_cuts[1:])):
         rank_cuts = [r * Lg // world_size for r in range(world_size + 1)]
     extra = [c for c in (pw + 2 * k, Lg - pw - 2 * k)
@@ -150,7 +154,7 @@ class LongGrid:
         from . import _device as dev
         self.mode_id = dev.MODE_ID[mode]
         self.pieces = plan_pieces(self.Lg, pw, world_size, self.k, max_piece, mf=mf if mode != "free" else None,
-                                  mr=mr if mode != "free" else None)
+                                  mr=mr if mode != "free" else None, slab_cost=SLAB_COST.get(mode))
         self.mine = [p for p in self.pieces if p["rank"] == rank]
         self.sched = exchange_schedule(self.pieces, rank)
         T = len(srcE)
