@@ -33,10 +33,11 @@ STATE_ALL = ("Ex", "Hy", "psiE", "psiH", "Dx", "P", "Pprev")
 # relative cost of one cell-update by cell class, measured on B200 with the tile engine (vacuum 60 ps,
 # Lorentz slab 131 ps per cell per 64-step block; CPML adds about the cost of a vacuum cell)
 CELL_COST = {"vacuum": 1.0, "slab": 2.2, "cpml": 1.0}
-# slab cell cost by integrator mode, from the 1-GPU rates of tools/bench_configs.py (vacuum 1680, Lorentz 837, Kerr-Lorentz
-# with the Newton root 201 Gcell-updates/s at a 70 % slab): equal-work rank boundaries need the mode's own ratio (with the
-# Lorentz ratio the Kerr-Lorentz grid scaled to 8 GPUs at 88.6 %)
-SLAB_COST = {"lorentz": 2.4, "lorentz_nl": 11.5, "nl": 11.5}
+# slab cell cost relative to a vacuum cell OF THE SAME KERNEL, by integrator mode, fitted to the measured 8-GPU weak-scaling
+# efficiencies of tools/bench_configs.py (Lorentz: 93.1 % with 2.2, 86.7 % with 2.4 -> 2.0; Kerr-Lorentz with the Newton
+# root: 88.6 % with 2.2, 88.8 % with 11.5 -> 7): a vacuum cell of the material kernels costs more than one of the
+# vacuum-only kernel, so ratios taken from single-GPU rates of different kernels overestimate the slab
+SLAB_COST = {"lorentz": 2.0, "lorentz_nl": 7.0, "nl": 7.0}
 
 
 def balanced_rank_cuts(Lg, pw, world_size, mf=None, mr=None, slab_cost=None):
