@@ -281,12 +281,34 @@ def extras(torch, peak_gbs, quick=False):
     sec_push = _time_cuda(torch, lambda: ps.push(Ex, Hy), 5)
     ps.sort()
     sec_fused = _time_cuda(torch, lambda: ps.step_sorted(Ex, Hy), 5)   # deposit fused into the move pass
-    out["pic"] = {"particles": n, "particle_steps_per_s": n / sec_fused, "push_only_particles_per_s": n / sec_push,
+    # the same particle step COUPLED to the field grid: deposit -> one FDTD step subtracting Jx (ADE_ExUpdate's slot,
+    # BaseFDTD11.py:667; per-op engine, the one that carries per-cell arrays) -> push in the new fields
+    from pyfdtd_b200 import BaseFDTD11, _device as dev
+    tup = envDef.envSetup(9e9, 0.7, 7000, 8000)
+    P = MC.Params(*tup, False, 0.7, 9e9, 20)
+    P.TFSF, P.SineCont, P.Periods, P.LorentzMed, P.FreeSpace = True, True, 1000, False, True
+    V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
+    C_P = MC.CPML_Params(P.dz)
+    C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
+    C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=False)
+    Lc = len(V.Ex)
+    zc, uxc, uzc, wc = pic.make_beam(n, Lc, P.dz, seed=2)
+    psc = pic.ParticleSet(zc, uxc, uzc, wc, Lc, P.dz, P.delT)
+    gdev = dev.DeviceGrid(L=Lc, T=P.timeSteps, arrays=BaseFDTD11._host_arrays(V, C_V, V.tempVarPol),
+                          scalars=BaseFDTD11.grid_scalars(V, P), srcE=np.asarray(Exs) / P.courantNo,
+                          srcH=np.asarray(Hys) / P.courantNo, probe_idx=[], flags=BaseFDTD11.grid_flags(P))
+    sim = pic.CoupledPIC(gdev, psc, mode="free", fused=True)
+    for _ in range(3):
+        sim.step()
+    sec_coupled = _time_cuda(torch, sim.step, 10)
+    out["pic"] = {"particles": n, "particle_steps_per_s": n / sec_fused,
+                  "coupled_to_fdtd_particle_steps_per_s": n / sec_coupled, "coupled_grid_cells": Lc, "push_only_particles_per_s": n / sec_push,
                   "algorithmic_GBps": 60.0 * n / sec_fused / 1e9, "frac_of_hbm_peak": 60.0 * n / sec_fused / 1e9 / peak_gbs,
                   "separate_deposit_pass_particle_steps_per_s": n / sec,
                   "radix_sort_variant_particle_steps_per_s": n / sec_radix,
                   "note": "step = pf_pic_step_sorted: Boris push + stable counting re-sort by cell (count/scan/move) with "
-                          "the deterministic deposit fused into the move pass; 60 B/particle-step algorithmic"}
+                          "the deterministic deposit fused into the move pass; 60 B/particle-step algorithmic; coupled = the same "
+                          "step plus one FDTD step of the reference's default grid with the deposited Jx subtracted"}
     return out
 
 
@@ -520,11 +542,11 @@ def main():
     # (profiles/r1_final_k_tile_ncu.txt: dram__bytes_read.sum 539.5 MB + dram__bytes_write.sum 469.8 MB)
     traffic = 537.556736e6 + 462.760448e6 if (args.members == 1024 and k_block == 64 and args.n_freq == 64) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_tile<PF_LORENTZ,POL,8,Exact>", "peak_source": peak_src,
+                "traffic": None if (args.fp32 or args.fma) else traffic, "kernel": "k_tile<PF_LORENTZ, POL=1, C=2, %s>" % ("Fast32" if args.fp32 else "Fused" if args.fma else "Exact"), "peak_source": peak_src,
                 "kernel_ms_avg": avg_kernel_ms, "kernel_launches_timed": kn.value,
                 "kernel_share_of_step": kms.value / ms_total if ms_total else None,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "temporal_block_k": k_block,
-                "hbm_bytes_per_launch_model": hbm_model, "fp64_pipe": fp64,
+                "hbm_bytes_per_launch_model": hbm_model, "fp64_pipe": None if args.fp32 else fp64,
                 "note": "on-chip temporally blocked: algorithmic (k=1) bytes / time exceeds the HBM roofline by design"}
 
     cpu = None
