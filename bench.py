@@ -107,7 +107,7 @@ class ProductWorkload:
             m.T = steps_per_pass
             m.srcE, m.srcH = m.srcE[:steps_per_pass], m.srcH[:steps_per_pass]
             members.append(m)
-        self.members = members
+        self.members, self.share = members, share
         self.batch = sweep.MemberBatch(members, "lorentz", share_coef=share)
         self.cell_steps = self.batch.cell_steps
         self.dp_instr_per_step = sum(dp_instr_per_cell_step(m.L, m.scalars["pw"], m.scalars["mf"], m.scalars["mr"])
@@ -496,6 +496,7 @@ def main():
     lib.pf_profile_collect(kms, kn)
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region -------------------------------
+    # (a) one batch at a time: upload -> run -> download, strictly serial
     for _ in range(min(2, args.warmup)):
         step_e2e()
     barrier()
@@ -503,13 +504,30 @@ def main():
     for _ in range(args.steps):
         traces = step_e2e()
     torch.cuda.synchronize()
+    e2e_serial_s = time.perf_counter() - t0
+    # (b) the public pipelined runner (sweep.BatchPipeline): consecutive steps alternate between two batch pools, so the
+    # H2D of step i+1's inputs and the D2H + host unpacking of step i-1's traces overlap the time stepping of step i;
+    # every step still uploads its own inputs from pinned memory and returns its own traces to the host
+    batch_b = wl.sweep.MemberBatch(wl.members, "lorentz", share_coef=wl.share)
+    batch_b.upload()
+    batch_b.randomize_state(seed=4321 + rank)
+    pipe = wl.sweep.BatchPipeline([batch, batch_b])
+    pipe.run([0, 1], True, template=True, k_block=args.k_block)
+    barrier()
+    t0 = time.perf_counter()
+    results = pipe.run([i % 2 for i in range(args.steps)], True, template=True, k_block=args.k_block)
+    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    probe_checksum = float(sum(np.abs(t).sum() for t in traces))
+    probe_checksum = float(sum(np.abs(t).sum() for t in results[0]))
+    assert len(results) == args.steps
+    if abs(probe_checksum - float(sum(np.abs(t).sum() for t in traces))) > 1e-9 * max(1.0, abs(probe_checksum)):
+        raise SystemExit("bench: pipelined and serial e2e steps disagree")
+    del batch_b, pipe
 
-    t_dev = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t_dev = torch.tensor([ms_total, e2e_s * 1e3, e2e_serial_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = [float(x) for x in t_dev.cpu()]
+    ms_total, e2e_ms, e2e_serial_ms = [float(x) for x in t_dev.cpu()]
     total_cell_steps = wl.cell_steps * world * args.steps
     value = total_cell_steps / (ms_total * 1e-3) / 1e9
     e2e_value = total_cell_steps / (e2e_ms * 1e-3) / 1e9
@@ -582,7 +600,11 @@ def main():
                        "l2_policy": f"state {cfg_state_mb:.0f} MB per GPU > 126 MB L2, restored from a random template every step",
                        "parallelism": f"members sharded over {world} GPU(s), no collectives"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
-                    "ms_per_step": e2e_ms / args.steps, "probe_checksum": probe_checksum},
+                    "ms_per_step": e2e_ms / args.steps, "probe_checksum": probe_checksum,
+                    "how": "sweep.BatchPipeline: steps alternate between two batch pools; H2D of the next step's inputs and D2H of "
+                           "the previous step's traces overlap the time stepping (3 streams)",
+                    "serial_value": total_cell_steps / (e2e_serial_ms * 1e-3) / 1e9,
+                    "serial_how": "MemberBatch.upload -> run -> download_probes, one step at a time"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

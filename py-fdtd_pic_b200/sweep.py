@@ -203,6 +203,31 @@ class MemberBatch:
             out.append(a.reshape(max(n_p, 1), Tp)[:n_p, : m.T].copy())
         return out
 
+    def download_probes_async(self):
+        """Stream-ordered D2H of all probe traces into this batch's pinned buffer; returns a function that
+        waits for the copy and unpacks it like download_probes() (call it after other work was queued)."""
+        torch = self.torch
+        self.host_probe.copy_(self.pool[self.n_state + self.n_in:], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+
+        def finish():
+            done.synchronize()
+            hv = self.host_probe.numpy()
+            shapes = {(max(len(m.probe_idx), 1), len(m.probe_idx), (m.T + 31) // 32 * 32, m.T) for m in self.members}
+            if len(shapes) == 1:
+                rows, n_p, Tp, T = next(iter(shapes))
+                return list(hv.reshape(len(self.members), rows, Tp)[:, :n_p, :T].copy())
+            o0 = self.n_state + self.n_in
+            out = []
+            for i, m in enumerate(self.members):
+                Tp = (m.T + 31) // 32 * 32
+                n_p = len(m.probe_idx)
+                a = hv[self.off_probe[i] - o0: self.off_probe[i] - o0 + max(n_p, 1) * Tp]
+                out.append(a.reshape(max(n_p, 1), Tp)[:n_p, : m.T].copy())
+            return out
+        return finish
+
     def download_probe(self, i):
         """D2H of the probe traces of member i only -> array [n_probes, T]."""
         m = self.members[i]
@@ -237,6 +262,66 @@ class MemberBatch:
         Lp = (m.L + 31) // 32 * 32
         o = self.off_state[i] + STATE_NAMES.index(name) * Lp
         return self.pool[o:o + m.L].cpu().numpy()
+
+
+class BatchPipeline:
+    """A sweep larger than one batch (e.g. 4096 members in batches of 1024): the passes of successive
+    MemberBatch objects with the host-to-device copy of batch i+1's inputs and the device-to-host copy of
+    batch i-1's probe traces overlapped with the time stepping of batch i (three CUDA streams, events
+    between them; every batch owns its pinned staging buffers and its device pool, so nothing is shared).
+    A batch may appear several times in ``order`` (new inputs each time it is uploaded)."""
+
+    def __init__(self, batches):
+        torch = nat.require_cuda()
+        self.torch = torch
+        self.batches = list(batches)
+        self.s_in, self.s_run, self.s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(self, order, do_pol, *, template=False, k_block=0, on_result=None):
+        """Process batches[order[0]], batches[order[1]], ...; returns the list of probe-trace lists (or the
+        values of on_result(index_in_order, traces) if given)."""
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        for st in (self.s_in, self.s_run, self.s_out):
+            st.wait_stream(cur)
+        free = {}            # batch index -> event after which its pool / pinned input may be overwritten
+        pending, results = [], []
+
+        def drain(keep, batch=None):
+            # finish() copies out of the batch's pinned buffer: results are consumed in order, and always before the
+            # same batch's next device-to-host copy is queued
+            while len(pending) > keep or (batch is not None and any(p[2] == batch for p in pending)):
+                j, fin, _ = pending.pop(0)
+                tr = fin()
+                results.append(on_result(j, tr) if on_result else tr)
+
+        for j, bi in enumerate(order):
+            b = self.batches[bi]
+            with torch.cuda.stream(self.s_in):
+                if bi in free:
+                    self.s_in.wait_event(free[bi])     # the previous use of this batch has left the device pool
+                b.upload()
+                up = torch.cuda.Event()
+                up.record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(up)
+                b.reset_state(template=template)
+                b.run(do_pol=do_pol, k_block=k_block)
+                ran = torch.cuda.Event()
+                ran.record(self.s_run)
+            drain(keep=len(pending), batch=bi)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ran)
+                fin = b.download_probes_async()
+                out_done = torch.cuda.Event()
+                out_done.record(self.s_out)
+            free[bi] = out_done
+            pending.append((j, fin, bi))
+            drain(keep=1)          # unpack the previous batch on the host while this one runs
+        drain(keep=0)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_run)
+        return results
 
 
 # ------------------------------------------------------------------------------------------------

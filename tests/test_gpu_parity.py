@@ -693,3 +693,32 @@ def test_kerr_lorentz_fp32_variant(pk):
         pk.SE.KERR_LORENTZ, pk.SE.USE_FP32 = False, False
     for nm, got in (("Ex", V.Ex), ("Hy", V.Hy), ("x1ColAf", V.x1ColAf)):
         assert rel_err(got, want[nm]) <= FP32_TOL, (nm, rel_err(got, want[nm]))
+
+
+def test_batch_pipeline_equals_serial_batches(pk):
+    """sweep.BatchPipeline (H2D / time stepping / D2H of successive batches overlapped on three streams) returns, for
+    every entry of `order`, exactly what upload -> reset -> run -> download_probes returns for that batch -- including
+    back-to-back reuse of the same batch and heterogeneous (non-uniform) batches."""
+    a_members, _ = _lorentz_members(pk, [9e9, 9e9, 9e9])
+    b_members, _ = _lorentz_members(pk, [6e9, 10.5e9])
+    for i, m in enumerate(a_members):          # same grid, different drive
+        m.srcE, m.srcH = m.srcE * (1 + i), m.srcH * (1 + i)
+    batches = [pk.sweep.MemberBatch(a_members, "lorentz"), pk.sweep.MemberBatch(b_members, "lorentz")]
+    serial = []
+    for b in batches:
+        b.upload()
+        b.reset_state()
+        b.run(do_pol=True)
+        serial.append(b.download_probes())
+    pipe = pk.sweep.BatchPipeline(batches)
+    order = [0, 1, 0, 0, 1, 1]
+    got = pipe.run(order, True)
+    assert len(got) == len(order)
+    for j, bi in enumerate(order):
+        assert len(got[j]) == len(serial[bi])
+        for t, w in zip(got[j], serial[bi]):
+            assert np.array_equal(t, w), (j, bi)
+    seen = []
+    pipe.run([1, 0], True, on_result=lambda j, tr: seen.append((j, len(tr))))
+    assert seen == [(0, 2), (1, 3)]
+    assert np.max(np.abs(serial[0][2])) > 0
