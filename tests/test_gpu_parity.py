@@ -722,3 +722,64 @@ def test_batch_pipeline_equals_serial_batches(pk):
     pipe.run([1, 0], True, on_result=lambda j, tr: seen.append((j, len(tr))))
     assert seen == [(0, 2), (1, 3)]
     assert np.max(np.abs(serial[0][2])) > 0
+
+
+def test_newton_root_falls_back_to_the_closed_form_where_inadmissible(pk):
+    """pf_cubic_root0_newton: polynomials outside a, b >= 0, c > 0, d < 0 take the closed form, bit for bit."""
+    from pyfdtd_b200 import CubicEquationSolver as CES
+    g = load_golden("cubic_roots")
+    co = np.asarray(g["coeffs"], dtype=np.float64)
+    bad = ~((co[:, 0] >= 0) & (co[:, 1] >= 0) & (co[:, 2] > 0) & (co[:, 3] < 0))
+    assert bad.sum() > 10
+    closed = CES.root0_many(co)
+    newton = CES.root0_many(co, newton=True)
+    assert np.array_equal(newton[bad], closed[bad], equal_nan=True)
+    ok = ~bad & np.isfinite(closed)
+    assert np.max(np.abs(newton[ok] - closed[ok]) / np.maximum(1.0, np.abs(closed[ok]))) <= 1e-9
+
+
+def test_kerr_lorentz_batch_equals_single_runs(pk):
+    """PF_LORENTZ_NL through pf_run_batch (sweep members with different grids) == the same members run one by one."""
+    pk.SE.KERR_LORENTZ = True
+    try:
+        members, objs = _lorentz_members(pk, [6e9, 9e9, 10.5e9])
+        for i, m in enumerate(members):
+            m.srcE, m.srcH = m.srcE * (3.0 + i), m.srcH * (3.0 + i)
+        batch = pk.sweep.MemberBatch(members, "lorentz_nl")
+        batch.upload()
+        batch.reset_state()
+        batch.run(do_pol=True)
+        traces = batch.download_probes()
+        for i in range(len(members)):
+            single = pk.sweep.MemberBatch([members[i]], "lorentz_nl")
+            single.upload()
+            single.reset_state()
+            single.run(do_pol=True, k_block=17)
+            assert np.array_equal(single.download_probes()[0], traces[i]), i
+            assert np.array_equal(single.state(0, "Ex"), batch.state(i, "Ex")), i
+            assert np.max(batch.state(i, "Acubic")) > 0
+    finally:
+        pk.SE.KERR_LORENTZ = False
+
+
+def test_fp32_ragged_batch_tracks_fp64(pk):
+    """PF_F_FP32 on a heterogeneous, ragged batch: within the stated 1e-5 of the fp64 result's peak."""
+    freqs = [6e9, 7.3e9, 9e9]
+    members, _ = _lorentz_members(pk, freqs)
+    members[1].nsteps = 123
+    ref = pk.sweep.MemberBatch(members, "lorentz")
+    ref.upload(); ref.reset_state(); ref.run(do_pol=True)
+    want = ref.download_probes()
+    pk.SE.USE_FP32 = True
+    try:
+        m32, _ = _lorentz_members(pk, freqs)
+        m32[1].nsteps = 123
+        b = pk.sweep.MemberBatch(m32, "lorentz")
+    finally:
+        pk.SE.USE_FP32 = False
+    b.upload(); b.reset_state(); b.run(do_pol=True)
+    got = b.download_probes()
+    for i in range(len(freqs)):
+        assert rel_err(got[i], want[i]) <= FP32_TOL, i
+        assert rel_err(b.state(i, "Ex"), ref.state(i, "Ex")) <= FP32_TOL, i
+        assert not np.array_equal(got[i], want[i])

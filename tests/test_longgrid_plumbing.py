@@ -120,3 +120,22 @@ def test_ghost_exchange_over_gloo_world2(tmp_path):
     mp.spawn(_worker, args=(world, port, 24_000, 700, 32, 7, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert bool(np.load(tmp_path / f"ok{r}.npy")[0])
+
+
+def test_rank_boundaries_follow_the_mode_specific_slab_cost():
+    """balanced_rank_cuts: a costlier slab (Kerr-Lorentz) pushes the boundaries towards the vacuum side; estimated work
+    per rank is equal for the ratio the cuts were made with."""
+    import importlib
+    lg = importlib.import_module("pyfdtd_b200.longgrid")
+    Lg, pw, mf, mr, world = 8_000_000, 2394, 2_400_000, 7_999_998, 8
+    cuts_l = lg.balanced_rank_cuts(Lg, pw, world, mf, mr, lg.SLAB_COST["lorentz"])
+    cuts_k = lg.balanced_rank_cuts(Lg, pw, world, mf, mr, lg.SLAB_COST["lorentz_nl"])
+    assert cuts_l[0] == cuts_k[0] == 0 and cuts_l[-1] == cuts_k[-1] == Lg
+    assert all(b > a for a, b in zip(cuts_k[:-1], cuts_k[1:]))
+    assert cuts_k[1] > cuts_l[1]            # rank 0 (all the vacuum) takes more cells when the slab is dearer
+    for cuts, r in ((cuts_l, lg.SLAB_COST["lorentz"]), (cuts_k, lg.SLAB_COST["lorentz_nl"])):
+        work = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            slab = max(0, min(b, mr) - max(a, mf))
+            work.append((b - a - slab) + r * slab)
+        assert max(work) / min(work) < 1.02
