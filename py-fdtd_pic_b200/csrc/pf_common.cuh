@@ -246,16 +246,27 @@ __device__ __forceinline__ double cubic_root0_newton(double a, double b, double 
     const double a3 = 3.0 * a, b2 = 2.0 * b;
     double x = q2 * inv_c, r = inv_c, step;
     if (fma(fma(a3, x, b2), x, c) * inv_c > 1.5) return cubic_root0_newton_far(a, b, c, q2);
+#ifndef PF_NEWTON_PLAIN_START
+    // first-order start: with t = b x0/c the root is x0 (1 - t + O(t^2)) and 1/p' is (1 - 2t + O(t^2))/c, which saves an
+    // iteration in the weakly nonlinear regime (t ~ 5e-4 |E|^2 on the sweeps).  The iteration no longer starts above
+    // the root; from below its first step lands above it (p convex), from where it descends as before.
+    const double t = (b * inv_c) * x;
+    x = fma(-t, x, x);
+    r = fma(-2.0 * t, inv_c, inv_c);
+    constexpr int MIN_IT = 2;
+#else
+    constexpr int MIN_IT = 3;
+#endif
     int it = 0;
     do {
         const double p = fma(fma(fma(a, x, b), x, c), x, -q2);
         const double dp = fma(fma(a3, x, b2), x, c);
-        r = fma(r, fma(-dp, r, 1.0), r);                 // 0 < r dp < 2 always: dp only decreases from p'(x0) <= 1.5 c
+        r = fma(r, fma(-dp, r, 1.0), r);                 // 0 < r dp < 2: p'(x) <= p'(x0) <= 1.5 c and r <= 1/c
         step = p * r;
         x -= step;
         ++it;
         // superlinear: once a step is below 1e-10 x the error left after it is far below one ulp
-    } while (it < 3 || (it < 24 && fabs(step) > 1e-10 * x));
+    } while (it < MIN_IT || (it < 24 && fabs(step) > 1e-10 * x));
     return x;
 }
 __device__ __forceinline__ double cubic_root0_newton(const CubicConsts &k, double q2)
