@@ -260,7 +260,7 @@ def extras(torch, peak_gbs, quick=False):
             torch.cuda.empty_cache()
         out["lorentz_sweep_optional_modes_Gcell_updates_per_s"] = dict(
             modes, note="same 1024-member workload as `value`; fma: PF_F_FMA (<= 1e-10 relative, tested); fp32: PF_F_FP32 "
-                        "(stated tolerance 1e-5 of the trace peak, profiles/r1g_fp32_accuracy.json)")
+                        "(stated tolerance 1e-5 of the trace peak, profiles/r1l_fp32_accuracy.json)")
     # --- config 4: PIC push + cell sort + deterministic deposit
     L, dz, dt = 13194, 8.3276e-5, 2.6389e-13
     n = 2_000_000 if quick else 20_000_000

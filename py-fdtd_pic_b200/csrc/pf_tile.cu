@@ -220,6 +220,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
         hl = hy[j];
         R e = ex[j];
         R pnow = R(0);
+        R vnew = R(0);   // fp32 mode: P^{n+1} - P^n of this step
         if (LOR && HAS_MAT) {
             if (POL) {
                 if constexpr (F32) {
@@ -231,6 +232,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                     pq[j] = v;
                     pc[j] = A::add(pc[j], v);
                     pnow = pc[j];
+                    vnew = v;
                 } else {
                     pq[j] = A::add(A::add(A::mul(K.pA, pc[j]), A::mul(K.pB, pq[j])), A::mul(K.pC, e));
                     pnow = pq[j];
@@ -254,8 +256,10 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
             if (MODE == PF_LORENTZ) {
                 R em;
                 if constexpr (F32) {
-                    dx[j] = A::add(dx[j], A::mad(dH, K.dtdz, A::mul(dH, K.dtdz_lo)));
-                    em = A::sub(dx[j], pnow);
+                    // fp32 mode carries Dn = D - P instead of D: Dn' = Dn + dD - (P' - P).  D and P are each a few
+                    // times E, so forming D - P every step would amplify their accumulated rounding (x4.8 at 9 GHz)
+                    dx[j] = A::add(dx[j], A::sub(A::mad(dH, K.dtdz, A::mul(dH, K.dtdz_lo)), vnew));
+                    em = dx[j];
                 } else {
                     dx[j] = A::mad(dH, K.dtdz, dx[j]);
                     em = div_const_fast(A::sub(dx[j], pnow), K.eps0, K.inv_eps0, divkey);
@@ -263,8 +267,8 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                 e = (!GEN || ((K.mSlab >> j) & 1)) ? em : e;
             } else if constexpr (F32) {   // cubic law on Dx (PF_NL) or on Dx - P (PF_LORENTZ_NL)
                 if (!GEN || ((K.mSlab >> j) & 1)) {
-                    dx[j] = A::add(dx[j], A::mad(dH, K.dtdz, A::mul(dH, K.dtdz_lo)));
-                    const R dn = LOR ? A::sub(dx[j], pnow) : dx[j];
+                    dx[j] = A::add(dx[j], A::sub(A::mad(dH, K.dtdz, A::mul(dH, K.dtdz_lo)), vnew));   // Dn (LOR) or D
+                    const R dn = dx[j];
                     const NlResultF nl = nl_material_law_f32(K.ca, K.cb, K.cc, dn, K.inv_eps0, K.den0, K.den1);
                     acub[j] = nl.a;
                     e = nl.e;
@@ -422,6 +426,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
                     const double p0 = sl ? inP[lz0 + j] : 0.0, p1 = sl ? inPp[lz0 + j] : 0.0;
                     pa[j] = F32 ? p0 * sD : p0;
                     pb[j] = F32 ? (p0 - p1) * sD : p1;   // fp32 mode carries P^n - P^{n-1} (difference form)
+                    if (F32) dx[j] = sl ? (inDx[lz0 + j] - p0) * sD : 0.0;   // ... and Dn = D - P in place of D
                 }
             }
         }
@@ -523,7 +528,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
         double *__restrict__ outDx = TG.buf[dst][S_DX];
 #pragma unroll
         for (int j = 0; j < C; ++j)
-            if ((sm >> j) & 1) outDx[lz0 + j] = F32 ? dx[j] * uD : dx[j];
+            if ((sm >> j) & 1) outDx[lz0 + j] = F32 ? (LOR ? ((double)dx[j] + (double)pa[j]) * uD : dx[j] * uD) : dx[j];
         if (LOR) {
             double *__restrict__ outP = TG.buf[dst][S_P];
             double *__restrict__ outPp = TG.buf[dst][S_PP];
@@ -550,8 +555,14 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 #ifndef PF_TILE_MINBLOCKS_F32
 #define PF_TILE_MINBLOCKS_F32 4   // measured on the Lorentz sweep: C=2 x 4 CTAs/SM 1023, C=2 x 3 978, C=4 x 3 869, C=4 x 2 762, C=1 x 2 778 Gcell-updates/s
 #endif
+#ifndef PF_TILE_MINBLOCKS_NEWTON
+#define PF_TILE_MINBLOCKS_NEWTON PF_TILE_MINBLOCKS
+#endif
 template <class A>
-constexpr int tile_minblocks() { return std::is_same<typename A::real, float>::value ? PF_TILE_MINBLOCKS_F32 : PF_TILE_MINBLOCKS; }
+constexpr int tile_minblocks()
+{
+    return std::is_same<typename A::real, float>::value ? PF_TILE_MINBLOCKS_F32 : (A::newton ? PF_TILE_MINBLOCKS_NEWTON : PF_TILE_MINBLOCKS);
+}
 
 template <int MODE, bool POL, int C, class A>
 __global__ void __launch_bounds__(TILE_CELLS / C, tile_minblocks<A>())
