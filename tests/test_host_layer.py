@@ -239,3 +239,33 @@ def test_pic_oracle_fused_summation_tree_agrees_with_the_plain_one():
         Jp = po.deposit(*po.sort_by_cell(zp, uxp, uzp, wo, cp), L, dz=dz, c=299792458.0, jx_scale=-1.6e-19)
         assert np.max(np.abs(Jf - Jp)) <= 1e-13 * np.max(np.abs(Jp))
     assert po.sub_warps(20_000_000, 13194) == 6 and po.sub_warps(1000, 4097) == 1
+
+
+def test_python_constants_match_header_enums(tmp_path):
+    """Modes, engines and flags of _native.py are the header's enum values (compiled from the header itself)."""
+    names = ["PF_FREE", "PF_LORENTZ", "PF_NL", "PF_LORENTZ_NL", "PF_ENGINE_OPS", "PF_ENGINE_TILE", "PF_F_TFSF",
+             "PF_F_CPML_M", "PF_F_CPML_P", "PF_F_CANONICAL", "PF_F_FMA", "PF_F_FP32", "PF_F_NEWTON"]
+    src = tmp_path / "en.c"
+    src.write_text('#include <stdio.h>\n#include "pyfdtd_b200.h"\nint main(){printf("' + " ".join(["%d"] * len(names)) +
+                   '\\n", ' + ", ".join(names) + ");return 0;}\n")
+    exe = tmp_path / "en"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = list(map(int, subprocess.check_output([str(exe)]).split()))
+    assert got == [getattr(nat, n) for n in names]
+    from pyfdtd_b200 import _device as dev
+    assert dev.MODE_ID == {"free": nat.PF_FREE, "lorentz": nat.PF_LORENTZ, "nl": nat.PF_NL, "lorentz_nl": nat.PF_LORENTZ_NL}
+
+
+def test_kerr_lorentz_scalars_and_flags():
+    """Host-side description of the PF_LORENTZ_NL composition and of the optional arithmetic flags."""
+    V, P, C_V, C_P = build_objects(dict(mode="lorentz", freq=9e9, dom=0.15, win=[300, 320]))
+    lin = BaseFDTD11.grid_scalars(V, P)
+    ker = BaseFDTD11.grid_scalars(V, P, kerr_lorentz=True)
+    chi3 = float(V.chi3Stat)
+    assert (ker["cub_a"], ker["cub_b"], ker["cub_c"]) == (chi3 ** 2, 2 * chi3, 1.0)
+    assert ker["nl_den0"] == P.permit_0 and ker["nl_den1"] == P.permit_0 * chi3
+    assert all(ker[k] == lin[k] for k in ("polA", "polB", "polC", "dt_over_dz", "eps0", "mf", "mr"))
+    base = BaseFDTD11.grid_flags(P)
+    assert BaseFDTD11.grid_flags(P, fp32=True) == base | nat.PF_F_FP32
+    assert BaseFDTD11.grid_flags(P, newton=True) == base | nat.PF_F_NEWTON
+    assert BaseFDTD11.grid_flags(P, fma=True, fp32=True, newton=True) == base | nat.PF_F_FMA | nat.PF_F_FP32 | nat.PF_F_NEWTON
