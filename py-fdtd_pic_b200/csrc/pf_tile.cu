@@ -558,14 +558,18 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 #ifndef PF_TILE_MINBLOCKS_NEWTON
 #define PF_TILE_MINBLOCKS_NEWTON PF_TILE_MINBLOCKS
 #endif
-template <class A>
+#ifndef PF_TILE_MINBLOCKS_FREE
+#define PF_TILE_MINBLOCKS_FREE 4   // 128 instead of 164 registers, 4 CTAs of 128 threads per SM: 1670 vs 1645 Gcell-updates/s (5e7 cells)
+#endif
+template <int MODE, class A>
 constexpr int tile_minblocks()
 {
-    return std::is_same<typename A::real, float>::value ? PF_TILE_MINBLOCKS_F32 : (A::newton ? PF_TILE_MINBLOCKS_NEWTON : PF_TILE_MINBLOCKS);
+    return std::is_same<typename A::real, float>::value ? PF_TILE_MINBLOCKS_F32
+           : (A::newton ? PF_TILE_MINBLOCKS_NEWTON : (MODE == PF_FREE ? PF_TILE_MINBLOCKS_FREE : PF_TILE_MINBLOCKS));
 }
 
 template <int MODE, bool POL, int C, class A>
-__global__ void __launch_bounds__(TILE_CELLS / C, tile_minblocks<A>())
+__global__ void __launch_bounds__(TILE_CELLS / C, tile_minblocks<MODE, A>())
 k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, int src, int n_done,
        int n0, int ksteps, int halo)
 {
