@@ -115,8 +115,9 @@ def spatial_stab(Nz, dz, freq, dt, wp, w0, gam):
     if rad * dt > np.pi / 2 and freq <= 5e9:
         raise ValueError("unstable timestep")
     sw = np.sinc(np.pi * freq * dt)
-    es = (wp ** 2) / (w0 ** 2) - 1
-    sqN = (rad ** 2 * sw ** 2 - es * w0 ** 2 * np.cos(rad * dt) + 1.0j * gam * rad * sw)
+    # Drude limit w0 = 0 (not reachable in the reference, which divides by w0^2 here): es*w0^2 -> wp^2
+    es_w02 = wp ** 2 if w0 == 0 else ((wp ** 2) / (w0 ** 2) - 1) * w0 ** 2
+    sqN = (rad ** 2 * sw ** 2 - es_w02 * np.cos(rad * dt) + 1.0j * gam * rad * sw)
     sqD = (rad ** 2 * sw ** 2 - w0 ** 2 * np.cos(rad * dt) + 1.0j * gam * rad * sw)
     arg = (rad / c0) * (dz / 2) * sw * np.sqrt(sqN / sqD)
     ans = (2 / dz) * np.arcsin(arg)

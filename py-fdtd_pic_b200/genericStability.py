@@ -17,8 +17,10 @@ def numerical_wavenumber(dz, freq, dt, wp, w0, gam):
     rad = 2 * np.pi * freq
     c0 = sci.speed_of_light
     sw = np.sinc(np.pi * freq * dt)
-    es = (wp ** 2) / (w0 ** 2) - 1
-    sqN = (rad ** 2 * sw ** 2 - es * w0 ** 2 * np.cos(rad * dt) + 1.0j * gam * rad * sw)
+    # Drude limit (resonantFreq = 0; the reference's expression divides by w0^2): es*w0^2 -> wp^2 - w0^2 = wp^2.
+    # For w0 != 0 the reference's own expression is kept, bit for bit.
+    es_w02 = wp ** 2 if w0 == 0 else ((wp ** 2) / (w0 ** 2) - 1) * w0 ** 2
+    sqN = (rad ** 2 * sw ** 2 - es_w02 * np.cos(rad * dt) + 1.0j * gam * rad * sw)
     sqD = (rad ** 2 * sw ** 2 - w0 ** 2 * np.cos(rad * dt) + 1.0j * gam * rad * sw)
     arg = (rad / c0) * (dz / 2) * sw * np.sqrt(sqN / sqD)
     return abs((2 / dz) * np.arcsin(arg))

@@ -783,3 +783,23 @@ def test_fp32_ragged_batch_tracks_fp64(pk):
         assert rel_err(got[i], want[i]) <= FP32_TOL, i
         assert rel_err(b.state(i, "Ex"), ref.state(i, "Ex")) <= FP32_TOL, i
         assert not np.array_equal(got[i], want[i])
+
+
+@pytest.mark.parametrize("engine", ["tile", "ops"])
+def test_drude_limit_matches_oracle(pk, engine):
+    """omega_0 = 0 (Drude medium) through IntegratorLinLor1D: bit-identical to the oracle on both engines."""
+    spec = dict(mode="lorentz", freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000)
+    c = oracle_case(spec)
+    c.medium = dict(c.medium, w0=0.0, wp=2 * np.pi * 12e9, gam=2 * np.pi * 0.2e9)
+    want = fo.run_case(c)
+    pk.SE.ENGINE = engine
+    try:
+        V, P, C_V, C_P = pk.build_objects(spec)
+        V.omega_0E, V.plasmaFreqE, V.gammaE = 0.0, 2 * np.pi * 12e9, 2 * np.pi * 0.2e9
+        V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    finally:
+        pk.SE.ENGINE = "auto"
+    assert V.plasmaFreqE == want["plasmaFreqE"]
+    for nm, got in (("Ex", V.Ex), ("Hy", V.Hy), ("P", V.polarisationCurr), ("Dx", V.Dx), ("x1ColAf", V.x1ColAf)):
+        assert np.array_equal(got, want[nm]), nm
+    assert np.max(np.abs(want["P"])) > 0
