@@ -679,8 +679,11 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     }
 }
 
-// Copy the interior of every tile from buffer `from` to buffer `to`.  only_odd = 1 restricts it to
-// grids whose result ended in buffer 1 (an odd number of launches), for the final copy-back.
+// Copy the interior of every tile from buffer `from` to buffer `to` -- only the cells a launch stores: Ex / Hy everywhere,
+// psi_E / psi_H on their CPML update ranges, Dx / P / Pprev inside the slab (the same index rules as k_tile's store masks).
+// Every other cell of the scratch buffer is never written and never read, so it needs no seeding, and the cells the
+// caller's arrays hold there are left untouched.  only_odd = 1 restricts the copy to grids whose result ended in
+// buffer 1 (an odd number of launches), for the final copy-back.
 __global__ void __launch_bounds__(256) k_tile_copy(const TileGrid *__restrict__ grids,
                                                   const TileDesc *__restrict__ tiles, int halo,
                                                   int k_block, int mode, int from, int to, int only_odd)
@@ -691,15 +694,28 @@ __global__ void __launch_bounds__(256) k_tile_copy(const TileGrid *__restrict__ 
         int launches = (TG.nsteps + k_block - 1) / k_block;
         if ((launches & 1) == 0) return;
     }
-    int W = TILE_CELLS - 2 * halo;
-    int narr = (mode == PF_LORENTZ || mode == PF_LORENTZ_NL) ? 7 : (mode == PF_NL ? 5 : 4);
+    const PfGrid &g = TG.d.g;
+    const int W = TILE_CELLS - 2 * halo;
+    const int narr = (mode == PF_LORENTZ || mode == PF_LORENTZ_NL) ? 7 : (mode == PF_NL ? 5 : 4);
+    const int L = g.L, z0 = (int)g.z0, Lg = (int)g.Lg;
+    const bool cpml_m = g.flags & PF_F_CPML_M, cpml_p = g.flags & PF_F_CPML_P;
     for (int a = 0; a < narr; ++a) {
         const double *__restrict__ s = TG.buf[from][a];
         double *__restrict__ d = TG.buf[to][a];
         if (!s || !d) continue;
         for (int i = threadIdx.x; i < W; i += blockDim.x) {
-            int lz = td.base + halo + i;
-            if (lz >= 0 && lz < TG.d.g.L) d[lz] = s[lz];
+            const int lz = td.base + halo + i;
+            if (lz < 0 || lz >= L) continue;
+            const int gz = z0 + lz;
+            bool ok = true;
+            if (a == S_PSIE || a == S_PSIH) {
+                const bool in_pml = (cpml_m && gz < g.pw) || (cpml_p && gz >= Lg - g.pw);
+                const bool upd = (a == S_PSIE) ? (lz >= 1 && gz >= 1 && gz <= Lg - 1) : (lz <= L - 2 && gz >= 1 && gz <= Lg - 2);
+                ok = in_pml && upd;
+            } else if (a >= S_DX) {
+                ok = lz >= 1 && gz >= g.mf && gz < g.mr;
+            }
+            if (ok) d[lz] = s[lz];
         }
     }
 }
@@ -966,11 +982,8 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
     TileDesc *dt = (TileDesc *)(sbase + plan.off_tiles);
     PF_CUDA(cudaMemcpyAsync(dg, hg.data(), sizeof(TileGrid) * n, cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaMemcpyAsync(dt, ht.data(), sizeof(TileDesc) * ht.size(), cudaMemcpyHostToDevice, st));
-    // A launch stores only the cells a state array is defined on (psi inside the CPML, Dx/P inside
-    // the slab), so seed the second buffer with the caller's arrays once: the final copy-back then
-    // returns every untouched cell unchanged.
-    k_tile_copy<<<(int)ht.size(), 256, 0, st>>>(dg, dt, halo, k_block, mode, 0, 1, 0);
-    PF_LAUNCH_CHECK("k_tile_copy");
+    // A launch stores only the cells a state array is defined on (psi inside the CPML, Dx/P inside the slab) and
+    // reads only those; the copy-back below moves exactly those cells, so the scratch buffer needs no seeding.
 
     const bool wide = mostly_interior(grids, n);
     const bool snaps = snap_out && snap_interval > 0 && n == 1;
@@ -1000,10 +1013,10 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
     }
     if (snaps) {
         // variable-length launches: parity is not a function of nsteps/k_block; copy back explicitly
-        if (src == 1)
-            for (int a = 0; a < na; ++a)
-                if (hg[0].buf[1][a]) PF_CUDA(cudaMemcpyAsync(hg[0].buf[0][a], hg[0].buf[1][a], sizeof(double) * grids[0].L,
-                                        cudaMemcpyDeviceToDevice, st));
+        if (src == 1) {
+            k_tile_copy<<<(int)ht.size(), 256, 0, st>>>(dg, dt, halo, k_block, mode, 1, 0, 0);
+            PF_LAUNCH_CHECK("k_tile_copy");
+        }
     } else {
         k_tile_copy<<<(int)ht.size(), 256, 0, st>>>(dg, dt, halo, k_block, mode, 1, 0, 1);
         PF_LAUNCH_CHECK("k_tile_copy");
