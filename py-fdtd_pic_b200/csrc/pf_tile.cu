@@ -1018,8 +1018,12 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
             PF_LAUNCH_CHECK("k_tile_copy");
         }
     } else {
-        k_tile_copy<<<(int)ht.size(), 256, 0, st>>>(dg, dt, halo, k_block, mode, 1, 0, 1);
-        PF_LAUNCH_CHECK("k_tile_copy");
+        bool any_odd = false;      // grids whose result ended in the scratch buffer
+        for (int m = 0; m < n; ++m) any_odd = any_odd || ((((nsteps[m] + k_block - 1) / k_block) & 1) != 0);
+        if (any_odd) {
+            k_tile_copy<<<(int)ht.size(), 256, 0, st>>>(dg, dt, halo, k_block, mode, 1, 0, 1);
+            PF_LAUNCH_CHECK("k_tile_copy");
+        }
     }
     // host vectors go out of scope: the async H2D copies above were issued from pageable memory,
     // which cudaMemcpyAsync stages before returning.
