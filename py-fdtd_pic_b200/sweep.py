@@ -391,6 +391,69 @@ def run_two_pass_batch(objs, lorentz=True, k_block=0, rank=0, world_size=1, devi
     return mine, srcs, refl
 
 
+def nonlinear_sweep(freqs, amplitudes, domainSize, lowLimTim, highLimTim, *, nsteps=None, rank=0, world_size=1,
+                    harmonics=(1, 3), download_traces=False, k_block=0):
+    """BASELINE config 3: the cubic nonlinear integrator (Solver_Engine.IntegratorNL1D, Solver_Engine.py:220-271) over
+    every (frequency, amplitude) pair as ONE batch -- the amplitude scales the member's source tables Exs / Hys, the
+    grid is the one ``envSetup(f, ..., nonLinMed=True)`` gives for its frequency (members of one frequency share their
+    CPML profiles).  Members are dealt round-robin over ``world_size`` ranks (member % world_size == rank), no collective.
+
+    Returns a dict for the members this rank owns: ``index`` (position in the frequency-major (f, amp) list), ``freq``,
+    ``amp``, ``harmonic_amplitude`` [n_owned, len(harmonics), 2] = 2|FFT|/T of Port1 (slab front) and Port2 (slab rear) at
+    the bins nearest k*f -- computed on the device (batched FFT per distinct timeSteps; what the reference's missing
+    ``transH.CZT`` call, MasterController.py:669, was after), and ``Port1`` / ``Port2`` traces if ``download_traces``."""
+    from . import MasterController as MC
+    torch = nat.require_cuda()
+    pairs = [(float(f), float(a)) for f in freqs for a in amplitudes]
+    mine = [i for i in range(len(pairs)) if i % world_size == rank]
+    base, members, share = {}, [], []
+    for j, i in enumerate(mine):
+        f, amp = pairs[i]
+        if f not in base:
+            tup = envDef.envSetup(f, domainSize, lowLimTim, highLimTim, nonLinMed=True)
+            P = MC.Params(*tup, False, domainSize, f, 20)
+            P.TFSF, P.SineCont, P.Periods, P.nonLinMed, P.FreeSpace, P.LorentzMed = True, True, 1000, True, False, False
+            V = MC.Variables(P.Nz, P.timeSteps, P.vidInterval, 1)
+            C_P = MC.CPML_Params(P.dz)
+            C_V = MC.CPML_Variables(P.Nz, P.timeSteps)
+            C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=False, nonlinear=True)
+            base[f] = (V, P, C_V, C_P, np.asarray(Exs), np.asarray(Hys), j)
+        V, P, C_V, C_P, Exs, Hys, first = base[f]
+        m = Member(V, P, C_V, C_P, Exs * amp, Hys * amp, [P.materialFrontEdge, P.materialRearEdge], nsteps=nsteps)
+        members.append(m)
+        share.append(first)
+    out = dict(index=np.asarray(mine, dtype=np.int64), freq=np.asarray([pairs[i][0] for i in mine]),
+               amp=np.asarray([pairs[i][1] for i in mine]))
+    if not members:
+        out["harmonic_amplitude"] = np.zeros((0, len(harmonics), 2))
+        return out
+    batch = MemberBatch(members, "nl", share_coef=share)
+    batch.upload()
+    batch.reset_state()
+    batch.run(do_pol=False, k_block=k_block)
+    # harmonic content of the two port traces, on the device
+    groups = {}
+    for j, m in enumerate(members):
+        groups.setdefault(m.T, []).append(j)
+    H = torch.zeros((len(members), len(harmonics), 2), dtype=torch.float64, device=batch.device)
+    for T, idxs in groups.items():
+        Tp = (T + 31) // 32 * 32
+        rows = torch.stack([batch.pool[batch.off_probe[j]: batch.off_probe[j] + 2 * Tp].view(2, Tp)[:, :T] for j in idxs])
+        spec = torch.fft.rfft(rows, dim=-1).abs() * (2.0 / T)                     # [n, 2, T//2+1]
+        dt = torch.tensor([members[j].P.delT for j in idxs], dtype=torch.float64, device=batch.device)
+        f0 = torch.tensor([members[j].P.freq_in for j in idxs], dtype=torch.float64, device=batch.device)
+        for h, k in enumerate(harmonics):
+            bins = torch.clamp(torch.round(k * f0 * dt * T).long(), 0, spec.shape[-1] - 1)      # nearest bin to k*f
+            H[torch.as_tensor(idxs, device=batch.device), h] = spec[torch.arange(len(idxs), device=batch.device), :, bins]
+    out["harmonic_amplitude"] = H.cpu().numpy()
+    if download_traces:
+        tr = batch.download_probes()
+        out["Port1"] = [t[0] for t in tr]
+        out["Port2"] = [t[1] for t in tr]
+    out["cell_steps"] = batch.cell_steps
+    return out
+
+
 def frequency_sweep(V, P, domainSize, lowLimTim, highLimTim, Low=3e9, Interval=1e8, points=20, batched=True,
                     device_postproc=True):
     """MasterController.LoopedSim(loop=True) :533-569.  Returns (freqs, measured R, analytical R,

@@ -803,3 +803,42 @@ def test_drude_limit_matches_oracle(pk, engine):
     for nm, got in (("Ex", V.Ex), ("Hy", V.Hy), ("P", V.polarisationCurr), ("Dx", V.Dx), ("x1ColAf", V.x1ColAf)):
         assert np.array_equal(got, want[nm]), nm
     assert np.max(np.abs(want["P"])) > 0
+
+
+def test_nonlinear_sweep_matches_single_runs_and_oracle(pk):
+    """sweep.nonlinear_sweep (BASELINE config 3: frequency x amplitude members of the cubic integrator in one batch):
+    the unit-amplitude member is IntegratorNL1D's run; a scaled member is the oracle's run with scaled sources; the
+    on-device harmonic amplitudes equal a host FFT of the downloaded traces; sharding covers every member once."""
+    freqs, amps = [9e9, 7.5e9], [1.0, 4.0]
+    res = pk.sweep.nonlinear_sweep(freqs, amps, 0.15, 300, 320, download_traces=True)
+    assert list(res["index"]) == [0, 1, 2, 3] and list(res["amp"]) == [1.0, 4.0, 1.0, 4.0]
+    # member 0 == Controller / IntegratorNL1D at 9 GHz
+    V, P, C_V, C_P = pk.build_objects(dict(mode="nl", freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000))
+    V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    assert rel_err(res["Port1"][0], V.Port1) <= RTOL and rel_err(res["Port2"][0], V.Port2) <= RTOL
+    # member 1 (amplitude 4) == oracle with scaled sources
+    c = oracle_case(dict(mode="nl", freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000))
+    wp, _ = fo.spatial_stab(c.Nz, c.dz, c.freq, c.dt, c.medium["wp"], c.medium["w0"], c.medium["gam"])
+    oExs, oHys = fo.sources(c)
+    pa = fo.PassArrays(c, wp, oExs * 4.0, oHys * 4.0, [c.mf, c.mr], False)
+    fo.lib().orc_run(ctypes.byref(pa.g), fo.MODE_ID["nl"], 0, 0, c.T, c.T)
+    assert rel_err(res["Port1"][1], pa.probe_out[0]) <= RTOL
+    assert not np.allclose(res["Port1"][1], 4.0 * res["Port1"][0], rtol=1e-6, atol=0)      # it IS nonlinear
+    # harmonic amplitudes against a host FFT
+    for j, (f, a) in enumerate([(f, a) for f in freqs for a in amps]):
+        T = len(res["Port1"][j])
+        Vj, Pj, _, _ = pk.build_objects(dict(mode="nl", freq=f, dom=0.15, win=[300, 320]))
+        for port, key in enumerate(("Port1", "Port2")):
+            spec = np.abs(np.fft.rfft(res[key][j])) * 2.0 / T
+            for h, k in enumerate((1, 3)):
+                b = min(int(round(k * f * Pj.delT * T)), len(spec) - 1)
+                assert res["harmonic_amplitude"][j, h, port] == pytest.approx(spec[b], rel=1e-9, abs=1e-14)
+    assert res["harmonic_amplitude"][1, 0, 0] > 3.0 * res["harmonic_amplitude"][0, 0, 0]
+    # two-rank sharding: disjoint, complete, same numbers
+    r0 = pk.sweep.nonlinear_sweep(freqs, amps, 0.15, 300, 320, rank=0, world_size=2)
+    r1 = pk.sweep.nonlinear_sweep(freqs, amps, 0.15, 300, 320, rank=1, world_size=2)
+    assert sorted(list(r0["index"]) + list(r1["index"])) == [0, 1, 2, 3]
+    both = np.zeros_like(res["harmonic_amplitude"])
+    both[r0["index"]] = r0["harmonic_amplitude"]
+    both[r1["index"]] = r1["harmonic_amplitude"]
+    assert np.array_equal(both, res["harmonic_amplitude"])
