@@ -808,8 +808,10 @@ static int launch_tile_a(int n_tiles, const TileGrid *dg, const TileDesc *dt, in
 {
     const size_t sm = TileSmem<MODE, C, typename A::real>::bytes;
     ProfScope prof(st);
-    static bool set = false;
-    if (!set) { PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); set = true; }
+    static bool set[64] = {};   // the attribute is per device
+    int dev = 0;
+    PF_CUDA(cudaGetDevice(&dev));
+    if (!set[dev & 63]) { PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); set[dev & 63] = true; }
     k_tile<MODE, POL, C, A><<<n_tiles, TILE_CELLS / C, sm, st>>>(dg, dt, src, n_done, n0, ks, halo);
     PF_LAUNCH_CHECK("k_tile");
     return 0;
