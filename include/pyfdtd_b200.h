@@ -205,10 +205,16 @@ long long pf_halo_pack(const PfGrid *g, int mode, int side, int k, double *buf, 
 long long pf_halo_unpack(const PfGrid *g, int mode, int side, int k, const double *buf, void *stream);
 
 /* ---- PIC (builder-defined spec; the reference only has the Jx slot) ------ */
+enum {
+    PF_PIC_F_OFFSETS_VALID = 1 /* promise by the caller: the particle set is exactly what the previous
+                                  pf_pic_push_sorted / pf_pic_step_sorted call on this scratch buffer produced
+                                  (alternate arrays swapped in, nothing modified since), so the per-cell offsets
+                                  that call left in the scratch are reused instead of being searched again   */
+};
 typedef struct PfPic {
     int64_t n;            /* macro-particles                                                     */
     int32_t L;            /* grid cells (Nz+1)                                                   */
-    int32_t _pad;
+    int32_t flags;        /* PF_PIC_F_*; 0 is always valid                                         */
     double dz, dt;        /* grid spacing / time step                                            */
     double q_over_m;      /* charge/mass of the species [C/kg]                                   */
     double c;             /* speed of light                                                      */

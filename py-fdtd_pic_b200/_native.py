@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("PYFDTD_B200_LIB") or os.path.join(HERE, "libpyfdtd_b2
 
 PF_FREE, PF_LORENTZ, PF_NL, PF_LORENTZ_NL = 0, 1, 2, 3
 PF_ENGINE_OPS, PF_ENGINE_TILE = 0, 1
+PF_PIC_F_OFFSETS_VALID = 1
 PF_F_TFSF, PF_F_CPML_M, PF_F_CPML_P, PF_F_CANONICAL, PF_F_FMA, PF_F_FP32, PF_F_NEWTON = 1, 2, 4, 8, 16, 32, 64
 
 _dp = c_void_p  # device pointers travel as integers
@@ -43,7 +44,7 @@ class PfGrid(ctypes.Structure):
 class PfPic(ctypes.Structure):
     """Mirror of ``struct PfPic``."""
     _fields_ = [
-        ("n", c_int64), ("L", c_int32), ("_pad", c_int32),
+        ("n", c_int64), ("L", c_int32), ("flags", c_int32),
         ("dz", c_double), ("dt", c_double), ("q_over_m", c_double), ("c", c_double), ("mu0", c_double),
         ("jx_scale", c_double),
         ("z", _dp), ("ux", _dp), ("uz", _dp), ("w", _dp), ("cell", _dp),

@@ -491,8 +491,14 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
     long long *start = (long long *)(s + pl.off_start), *new_start = (long long *)(s + pl.off_new_start);
     int *counts = (int *)(s + pl.off_counts), *err = (int *)(s + pl.off_err);
     PF_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
-    k_pic_cell_start<<<(p->L + 1 + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(p->cell, p->n, p->L, start);
-    PF_LAUNCH_CHECK("k_pic_cell_start");
+    if (p->flags & PF_PIC_F_OFFSETS_VALID) {
+        // the previous fused call's new offsets ARE this call's offsets (caller's promise): 8 (L+1) bytes instead of a
+        // binary search per cell
+        PF_CUDA(cudaMemcpyAsync(start, new_start, sizeof(long long) * ((size_t)p->L + 1), cudaMemcpyDeviceToDevice, st));
+    } else {
+        k_pic_cell_start<<<(p->L + 1 + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(p->cell, p->n, p->L, start);
+        PF_LAUNCH_CHECK("k_pic_cell_start");
+    }
     const int S = pic_sub_warps(p);
     int *tot = (int *)(s + pl.off_tot);
     unsigned wblocks = (unsigned)(((long long)p->L * S * 32 + PIC_THREADS - 1) / PIC_THREADS);

@@ -60,6 +60,7 @@ class ParticleSet:
         self.scratch = torch.empty(sb, dtype=torch.uint8, device=self.device)
         self.scratch_bytes = sb
         self.sorted = False
+        self._offsets_valid = False    # the scratch holds the cell offsets of the current arrays (PF_PIC_F_OFFSETS_VALID)
 
     def _bind(self):
         p = self.p
@@ -73,6 +74,7 @@ class ParticleSet:
         self.p.Ex, self.p.Hy = Ex.data_ptr(), Hy.data_ptr()
         nat.check(nat.lib().pf_pic_push(ctypes.byref(self.p), nat.current_stream_ptr()), "pf_pic_push")
         self.sorted = False
+        self._offsets_valid = False
 
     def push_sorted(self, Ex, Hy):
         """Push + stable re-sort in one (requires a cell-sorted set; sorts once if it is not).  Faster than
@@ -80,12 +82,14 @@ class ParticleSet:
         if not self.sorted:
             self.sort()
         self.p.Ex, self.p.Hy = Ex.data_ptr(), Hy.data_ptr()
+        self.p.flags = nat.PF_PIC_F_OFFSETS_VALID if self._offsets_valid else 0
         nat.check(nat.lib().pf_pic_push_sorted(ctypes.byref(self.p), self.scratch.data_ptr(), self.scratch_bytes,
                                                nat.current_stream_ptr()), "pf_pic_push_sorted")
         self.cur, self.alt = self.alt, self.cur
         self.cell, self.cell_alt = self.cell_alt, self.cell
         self._bind()
         self.sorted = True
+        self._offsets_valid = True
 
     def step_sorted(self, Ex, Hy):
         """One whole particle step: push + stable re-sort + deposition of the new state, fused (pf_pic_step_sorted).
@@ -94,12 +98,14 @@ class ParticleSet:
         if not self.sorted:
             self.sort()
         self.p.Ex, self.p.Hy = Ex.data_ptr(), Hy.data_ptr()
+        self.p.flags = nat.PF_PIC_F_OFFSETS_VALID if self._offsets_valid else 0
         nat.check(nat.lib().pf_pic_step_sorted(ctypes.byref(self.p), self.scratch.data_ptr(), self.scratch_bytes,
                                                nat.current_stream_ptr()), "pf_pic_step_sorted")
         self.cur, self.alt = self.alt, self.cur
         self.cell, self.cell_alt = self.cell_alt, self.cell
         self._bind()
         self.sorted = True
+        self._offsets_valid = True
         return self.Jx
 
     def sub_warps(self):
@@ -117,6 +123,7 @@ class ParticleSet:
         self.cell, self.cell_alt = self.cell_alt, self.cell
         self._bind()
         self.sorted = True
+        self._offsets_valid = False
 
     def deposit(self):
         """Deposit Jx (requires cell-sorted particles; sorts first if needed).  Returns the Jx tensor."""
