@@ -391,19 +391,11 @@ def run_two_pass_batch(objs, lorentz=True, k_block=0, rank=0, world_size=1, devi
     return mine, srcs, refl
 
 
-def nonlinear_sweep(freqs, amplitudes, domainSize, lowLimTim, highLimTim, *, nsteps=None, rank=0, world_size=1,
-                    harmonics=(1, 3), download_traces=False, k_block=0):
-    """BASELINE config 3: the cubic nonlinear integrator (Solver_Engine.IntegratorNL1D, Solver_Engine.py:220-271) over
-    every (frequency, amplitude) pair as ONE batch -- the amplitude scales the member's source tables Exs / Hys, the
-    grid is the one ``envSetup(f, ..., nonLinMed=True)`` gives for its frequency (members of one frequency share their
-    CPML profiles).  Members are dealt round-robin over ``world_size`` ranks (member % world_size == rank), no collective.
-
-    Returns a dict for the members this rank owns: ``index`` (position in the frequency-major (f, amp) list), ``freq``,
-    ``amp``, ``harmonic_amplitude`` [n_owned, len(harmonics), 2] = 2|FFT|/T of Port1 (slab front) and Port2 (slab rear) at
-    the bins nearest k*f -- computed on the device (batched FFT per distinct timeSteps; what the reference's missing
-    ``transH.CZT`` call, MasterController.py:669, was after), and ``Port1`` / ``Port2`` traces if ``download_traces``."""
+def nonlinear_sweep_members(freqs, amplitudes, domainSize, lowLimTim, highLimTim, *, nsteps=None, rank=0, world_size=1):
+    """Host-side half of nonlinear_sweep (no device needed): the frequency-major (f, amp) list, the indices this rank owns
+    (index % world_size == rank), their Member objects (one setup chain per distinct frequency, sources scaled by the
+    amplitude) and, per member, the position of the member whose CPML profiles it shares."""
     from . import MasterController as MC
-    torch = nat.require_cuda()
     pairs = [(float(f), float(a)) for f in freqs for a in amplitudes]
     mine = [i for i in range(len(pairs)) if i % world_size == rank]
     base, members, share = {}, [], []
@@ -419,9 +411,25 @@ def nonlinear_sweep(freqs, amplitudes, domainSize, lowLimTim, highLimTim, *, nst
             C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=False, nonlinear=True)
             base[f] = (V, P, C_V, C_P, np.asarray(Exs), np.asarray(Hys), j)
         V, P, C_V, C_P, Exs, Hys, first = base[f]
-        m = Member(V, P, C_V, C_P, Exs * amp, Hys * amp, [P.materialFrontEdge, P.materialRearEdge], nsteps=nsteps)
-        members.append(m)
+        members.append(Member(V, P, C_V, C_P, Exs * amp, Hys * amp, [P.materialFrontEdge, P.materialRearEdge], nsteps=nsteps))
         share.append(first)
+    return pairs, mine, members, share
+
+
+def nonlinear_sweep(freqs, amplitudes, domainSize, lowLimTim, highLimTim, *, nsteps=None, rank=0, world_size=1,
+                    harmonics=(1, 3), download_traces=False, k_block=0):
+    """BASELINE config 3: the cubic nonlinear integrator (Solver_Engine.IntegratorNL1D, Solver_Engine.py:220-271) over
+    every (frequency, amplitude) pair as ONE batch -- the amplitude scales the member's source tables Exs / Hys, the
+    grid is the one ``envSetup(f, ..., nonLinMed=True)`` gives for its frequency (members of one frequency share their
+    CPML profiles).  Members are dealt round-robin over ``world_size`` ranks (member % world_size == rank), no collective.
+
+    Returns a dict for the members this rank owns: ``index`` (position in the frequency-major (f, amp) list), ``freq``,
+    ``amp``, ``harmonic_amplitude`` [n_owned, len(harmonics), 2] = 2|FFT|/T of Port1 (slab front) and Port2 (slab rear) at
+    the bins nearest k*f -- computed on the device (batched FFT per distinct timeSteps; what the reference's missing
+    ``transH.CZT`` call, MasterController.py:669, was after), and ``Port1`` / ``Port2`` traces if ``download_traces``."""
+    torch = nat.require_cuda()
+    pairs, mine, members, share = nonlinear_sweep_members(freqs, amplitudes, domainSize, lowLimTim, highLimTim, nsteps=nsteps,
+                                                          rank=rank, world_size=world_size)
     out = dict(index=np.asarray(mine, dtype=np.int64), freq=np.asarray([pairs[i][0] for i in mine]),
                amp=np.asarray([pairs[i][1] for i in mine]))
     if not members:

@@ -139,3 +139,28 @@ def test_rank_boundaries_follow_the_mode_specific_slab_cost():
             slab = max(0, min(b, mr) - max(a, mf))
             work.append((b - a - slab) + r * slab)
         assert max(work) / min(work) < 1.02
+
+
+def test_nonlinear_sweep_members_shard_without_overlap():
+    """Host half of sweep.nonlinear_sweep (config 3): frequency-major (f, amp) list dealt round-robin over the ranks;
+    one setup chain per distinct frequency on a rank, sources scaled by the amplitude, profile sharing inside the rank."""
+    import importlib
+    sw = importlib.import_module("pyfdtd_b200.sweep")
+    freqs, amps = [9e9, 7.5e9, 6e9], [0.5, 2.0, 8.0]
+    world = 2
+    seen = []
+    for rank in range(world):
+        pairs, mine, members, share = sw.nonlinear_sweep_members(freqs, amps, 0.15, 300, 320, nsteps=100, rank=rank,
+                                                                 world_size=world)
+        assert pairs == [(f, a) for f in freqs for a in amps]
+        assert mine == [i for i in range(9) if i % world == rank] and len(members) == len(mine)
+        seen += mine
+        for j, i in enumerate(mine):
+            f, a = pairs[i]
+            m = members[j]
+            assert m.P.freq_in == f and m.nsteps == 100 and m.probe_idx == [m.P.materialFrontEdge, m.P.materialRearEdge]
+            first = share[j]
+            assert first <= j and members[first].P is m.P                      # shares the first same-frequency member's grid
+            a0 = pairs[mine[first]][1]
+            assert np.allclose(m.srcE / a, members[first].srcE / a0, rtol=1e-14, atol=0)
+    assert sorted(seen) == list(range(9))
