@@ -160,3 +160,36 @@ def test_drude_limit_of_the_lorentz_ade_behaves_like_a_plasma():
         assert abs(meas - fresnel) <= 0.05, (f0, fp, meas, fresnel)
     assert got[(9e9, 12e9)][0] > 0.95                       # overdense: mirror
     assert got[(9e9, 5e9)][0] < got[(7e9, 5e9)][0] < 0.25     # underdense: weak, falling with frequency
+
+
+def test_oracle_newton_root_and_the_ill_conditioning_of_the_closed_form_on_kerr_coefficients():
+    """oracle/fdtd_oracle.c: orc_cubic_root_newton (the root PF_LORENTZ_NL is specified with) is the positive root of
+    the polynomial to rounding level, while the reference's closed form, on the same Kerr coefficients
+    (chi3^2, 2 chi3, 1), runs in its three-real-root branch and misses the root by orders of magnitude more --
+    which is why the composition is not specified through it."""
+    import ctypes
+    import fdtd_oracle as fo
+    lib = fo.lib()
+    lib.orc_cubic_root_newton.argtypes = [ctypes.c_double] * 4
+    lib.orc_cubic_root_newton.restype = ctypes.c_double
+    chi3 = 1e-3
+    a, b, c = chi3 ** 2, 2 * chi3, 1.0
+    rng = np.random.default_rng(5)
+    worst_newton, worst_closed = 0.0, 0.0
+    for q2 in 10.0 ** rng.uniform(-6, 4, 400):
+        xn = lib.orc_cubic_root_newton(a, b, c, q2)
+        xc = lib.orc_cubic_root0(a, b, c, -q2)
+        exact = q2 / (1 + chi3 * xn) ** 2            # fixed point of A (1 + chi3 A)^2 = q2, evaluated at the Newton root
+        worst_newton = max(worst_newton, abs(xn - exact) / xn)
+        resid_c = abs(((a * xc + b) * xc + c) * xc - q2) / q2
+        worst_closed = max(worst_closed, resid_c)
+        assert abs(((a * xn + b) * xn + c) * xn - q2) / q2 <= 4e-16 * (1 + 3 * chi3 * xn) + 1e-15
+    assert worst_newton <= 1e-14
+    assert worst_closed > 1e-12                         # the closed form is measurably off on these coefficients
+    # admissible random polynomials: Newton == largest real root of numpy.roots
+    for _ in range(100):
+        a, b, c = 10.0 ** rng.uniform(-8, -2), 10.0 ** rng.uniform(-5, -1), 10.0 ** rng.uniform(-1, 1)
+        q2 = 10.0 ** rng.uniform(-6, 3)
+        r = np.roots([a, b, c, -q2])
+        want = float(np.max(r[np.abs(r.imag) < 1e-9 * np.abs(r.real).max()].real))
+        assert lib.orc_cubic_root_newton(a, b, c, q2) == pytest.approx(want, rel=1e-10)
