@@ -193,3 +193,56 @@ def test_oracle_newton_root_and_the_ill_conditioning_of_the_closed_form_on_kerr_
         r = np.roots([a, b, c, -q2])
         want = float(np.max(r[np.abs(r.imag) < 1e-9 * np.abs(r.real).max()].real))
         assert lib.orc_cubic_root_newton(a, b, c, q2) == pytest.approx(want, rel=1e-10)
+
+
+def test_pic_oracle_is_pinned_to_known_physics():
+    """The PIC model has no reference implementation, so its CPU definition (oracle/pic_oracle.py) is pinned
+    to known answers instead: free drift, the exact momentum gain in a uniform E field, conservation of |u| and the
+    relativistic gyro-frequency in a uniform B field, specular walls, and charge-current conservation of the CIC deposit
+    (both summation trees)."""
+    import pic_oracle as po
+    C0, MU0, QM, Q = 299792458.0, 1.25663706127e-06, -1.75882001076e11, -1.602176634e-19
+    L, dz, dt = 2049, 1e-4, 2e-13
+    kw = dict(dz=dz, dt=dt, q_over_m=QM, c=C0, mu0=MU0)
+    rng = np.random.default_rng(1)
+    n = 1000
+    z = rng.uniform(0.2, 0.8, n) * (L - 1) * dz
+    ux, uz = 1e7 * rng.standard_normal(n), 2e8 * (1 + 0.01 * rng.standard_normal(n))
+    zero = np.zeros(L)
+    # (a) no fields: z += vz dt, momenta untouched
+    z1, ux1, uz1, c1 = po.push(z, ux, uz, zero, zero, **kw)
+    g = np.sqrt(1 + (ux ** 2 + uz ** 2) / C0 ** 2)
+    assert np.array_equal(ux1, ux) and np.array_equal(uz1, uz)
+    np.testing.assert_allclose(z1, z + uz / g * dt, rtol=1e-15)
+    assert np.array_equal(c1, np.floor(z1 / dz).astype(np.int32))
+    # (b) uniform Ex: two half kicks add up to q/m E dt exactly (to rounding), uz unchanged
+    E0 = 3e5
+    _, ux2, uz2, _ = po.push(z, ux, uz, np.full(L, E0), zero, **kw)
+    np.testing.assert_allclose(ux2 - ux, QM * E0 * dt, rtol=1e-9)
+    assert np.array_equal(uz2, uz)
+    # (c) uniform By: |u| conserved, rotation angle per step = 2 atan(q B dt / (2 gamma m))
+    B0 = 0.5
+    H0 = np.full(L, B0 / MU0)
+    _, ux3, uz3, _ = po.push(z, ux, uz, zero, H0, **kw)
+    np.testing.assert_allclose(np.hypot(ux3, uz3), np.hypot(ux, uz), rtol=1e-14)
+    ang = np.arctan2(ux3, uz3) - np.arctan2(ux, uz)
+    want = 2 * np.arctan(QM * dt * 0.5 * B0 / g)
+    np.testing.assert_allclose(np.abs(ang), np.abs(want), rtol=1e-9)
+    # (d) specular walls keep particles inside and flip uz
+    zmax = (L - 1) * dz
+    zw, _, uzw, _ = po.push(np.array([1e-9, zmax - 1e-9]), np.zeros(2), np.array([-2e8, 2e8]), zero, zero, **kw)
+    assert np.all((zw >= 0) & (zw <= zmax)) and uzw[0] > 0 and uzw[1] < 0
+    # (e) deposit: total current = sum q w vx for both summation trees, each particle's share goes to its two nodes
+    w = rng.uniform(0.5, 2.0, n) * 1e10
+    cell = np.clip(np.floor(z / dz).astype(np.int64), 0, L - 2).astype(np.int32)
+    zs, uxs, uzs, ws, cs = po.sort_by_cell(z, ux, uz, w, cell)
+    J = po.deposit(zs, uxs, uzs, ws, cs, L, dz=dz, c=C0, jx_scale=Q)
+    gs = np.sqrt(1 + (uxs ** 2 + uzs ** 2) / C0 ** 2)
+    assert np.sum(J) == pytest.approx(Q * np.sum(ws * uxs / gs), rel=1e-12)
+    Jf = po.deposit_fused(zs, uxs, uzs, ws, cs, cs, L, 2, dz=dz, c=C0, jx_scale=Q)
+    assert np.sum(Jf) == pytest.approx(np.sum(J), rel=1e-12)
+    one = po.deposit(np.array([10.25 * dz]), np.array([1e7]), np.array([0.0]), np.array([1.0]), np.array([10], dtype=np.int32),
+                     L, dz=dz, c=C0, jx_scale=1.0)
+    vx = 1e7 / np.sqrt(1 + (1e7 / C0) ** 2)
+    assert one[10] == pytest.approx(0.75 * vx, rel=1e-12) and one[11] == pytest.approx(0.25 * vx, rel=1e-12)
+    assert np.count_nonzero(one) == 2
