@@ -246,3 +246,20 @@ def test_pic_oracle_is_pinned_to_known_physics():
     vx = 1e7 / np.sqrt(1 + (1e7 / C0) ** 2)
     assert one[10] == pytest.approx(0.75 * vx, rel=1e-12) and one[11] == pytest.approx(0.25 * vx, rel=1e-12)
     assert np.count_nonzero(one) == 2
+
+
+def test_kerr_lorentz_oracle_state_satisfies_its_constitutive_relation():
+    """Mode "lorentz_nl" end state: inside the slab Acubic = |Ex|^2 and Dx - P = eps0 (eps_inf + chi3 |Ex|^2) Ex to rounding
+    level -- the composition's definition holds for the fields the oracle returns (strongly nonlinear drive)."""
+    import fdtd_oracle as fo
+    c = fo.make_case("lorentz_nl", 9e9, 0.15, 300, 320, source="gauss", amplitude=4.0)
+    out = fo.run_case(c)
+    sl = slice(c.mf, c.mr)
+    Ex, Dn, A = out["Ex"][sl], (out["Dx"] - out["P"])[sl], out["Acubic"][sl]
+    chi3 = c.medium["chi3"]
+    live = A > 0
+    assert live.sum() > 100 and np.max(A) > 10.0                      # chi3 |E|^2 up to a few per cent and beyond
+    np.testing.assert_allclose(A[live], Ex[live] ** 2, rtol=1e-12)
+    np.testing.assert_allclose(Dn[live], fo.EPS0 * (fo.KERR_EPS_INF + chi3 * Ex[live] ** 2) * Ex[live], rtol=1e-12)
+    dead = ~live                                                       # below the reference's 1e-8 threshold: linear law
+    np.testing.assert_allclose(Dn[dead], fo.EPS0 * Ex[dead], rtol=1e-12, atol=1e-30)
