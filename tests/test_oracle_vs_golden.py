@@ -3,9 +3,12 @@ oracle/make_golden.py).  This is what pins the oracle (the referen
 no vectors).  Bitwise equality is expected when the host libm / numpy SIMD dispatch match the machine
 that generated the goldens; the hard bound is BASELINE's 1e-10 relative."""
 import json
+import os
 
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 import fdtd_oracle as fo
 from conftest import load_golden
@@ -263,3 +266,24 @@ def test_kerr_lorentz_oracle_state_satisfies_its_constitutive_relation():
     np.testing.assert_allclose(Dn[live], fo.EPS0 * (fo.KERR_EPS_INF + chi3 * Ex[live] ** 2) * Ex[live], rtol=1e-12)
     dead = ~live                                                       # below the reference's 1e-8 threshold: linear law
     np.testing.assert_allclose(Dn[dead], fo.EPS0 * Ex[dead], rtol=1e-12, atol=1e-30)
+
+
+def test_builder_defined_models_have_not_drifted():
+    """tests/golden/builder_*.npz (oracle/make_builder_golden.py): regression pins of the models the reference does not
+    contain -- Kerr-Lorentz composition, Drude limit, PIC step.  Not reference parity: they hold the DEFINITIONS still."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_builder_golden", os.path.join(ROOT, "oracle", "make_builder_golden.py"))
+    mbg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mbg)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        mbg.OUT = tmp
+        mbg.kerr_lorentz(); mbg.drude(); mbg.pic()
+        for name in ("builder_kerr_lorentz", "builder_drude", "builder_pic"):
+            new = np.load(os.path.join(tmp, name + ".npz"))
+            old = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+            assert sorted(new.files) == sorted(old.files)
+            for k in old.files:
+                a, b = np.asarray(new[k], dtype=np.float64), np.asarray(old[k], dtype=np.float64)
+                scale = max(float(np.max(np.abs(b))), 1e-300)
+                assert float(np.max(np.abs(a - b))) <= 1e-11 * scale, (name, k)
