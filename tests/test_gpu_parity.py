@@ -6,6 +6,7 @@ BASELINE's 1e-10 relative against the reference goldens; for the cubic path Ex w
 and Acubic within 1e-10 absolute (CUDA pow() is not bit-identical to glibc pow()).
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -842,3 +843,39 @@ def test_nonlinear_sweep_matches_single_runs_and_oracle(pk):
     both[r0["index"]] = r0["harmonic_amplitude"]
     both[r1["index"]] = r1["harmonic_amplitude"]
     assert np.array_equal(both, res["harmonic_amplitude"])
+
+
+def test_gpu_reproduces_the_builder_fixtures(pk):
+    """tests/golden/builder_*.npz (oracle outputs, oracle/make_builder_golden.py) through the product path: the
+    Kerr-Lorentz composition and the Drude limit via Controller, the PIC step via ParticleSet."""
+    import pic_oracle as po
+    from pyfdtd_b200 import pic
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "builder_kerr_lorentz.npz"))
+    pk.SE.KERR_LORENTZ = True
+    try:
+        V, P, C_V, C_P = pk.build_objects(KERR_SPEC)
+        V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    finally:
+        pk.SE.KERR_LORENTZ = False
+    for nm, got in (("Ex", V.Ex), ("Hy", V.Hy), ("Dx", V.Dx), ("P", V.polarisationCurr), ("Acubic", V.Acubic), ("x1ColAf", V.x1ColAf)):
+        assert rel_err(got, g[nm]) <= RTOL, nm
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "builder_drude.npz"))
+    V, P, C_V, C_P = pk.build_objects(dict(mode="lorentz", freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000))
+    V.omega_0E, V.plasmaFreqE, V.gammaE = 0.0, 2 * np.pi * 12e9, 2 * np.pi * 0.2e9
+    V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    for nm, got in (("Ex", V.Ex), ("Hy", V.Hy), ("P", V.polarisationCurr), ("x1ColAf", V.x1ColAf)):
+        assert rel_err(got, g[nm]) <= 1e-12, nm
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "builder_pic.npz"))
+    L, dz, dt, n = 257, 8.3e-5, 2.6e-13, 20_000
+    z, ux, uz, w, cell = po.make_beam(n, L, dz, seed=3, thermal=0.3)
+    rng = np.random.default_rng(0)
+    Ex, Hy = 2e5 * rng.standard_normal(L), 5e2 * rng.standard_normal(L)
+    ps = pic.ParticleSet(z, ux, uz, w, L, dz, dt)
+    tEx, tHy = pk.torch.as_tensor(Ex, device="cuda"), pk.torch.as_tensor(Hy, device="cuda")
+    for _ in range(3):
+        Jf = ps.step_sorted(tEx, tHy).cpu().numpy()
+    h = ps.host()
+    assert np.array_equal(h["cell"], g["cell"])
+    for k in ("z", "ux", "uz"):
+        assert rel_err(h[k], g[k]) <= 1e-12, k
+    assert rel_err(Jf, g["J_fused"]) <= 1e-12 and rel_err(ps.deposit().cpu().numpy(), g["J"]) <= 1e-12
