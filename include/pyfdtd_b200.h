@@ -14,6 +14,10 @@
  *     layer turns these codes into exceptions.
  *   - The library never allocates caller-visible memory; scratch is provided by the caller and
  *     sized by the pf_*_scratch_bytes() queries.
+ *   - Process-global state: the last-error string (per thread), the launch counter (atomic) and the
+ *     optional profiling event list (mutex-guarded).  Nothing is remembered about earlier calls'
+ *     buffers: every entry point works from its arguments alone, so calls from several host threads
+ *     (one per GPU) do not interact.
  *
  * All arrays of one grid have length L = Nz+1 (MasterController.py:149-159), indices are the
  * reference's own cell indices.
@@ -28,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 
 enum { PF_OK = 0, PF_E_ARG = -1, PF_E_CUDA = -2, PF_E_UNSUPPORTED = -3, PF_E_SCRATCH = -4 };
 
@@ -93,9 +97,15 @@ typedef struct PfGrid {
     int32_t flags;    /* PF_F_*                                                                  */
     int32_t n_probes; /* number of probe cells                                                   */
     int32_t probe_stride; /* row length of probe_out (= timeSteps)                               */
+    int32_t n_src;    /* entries of srcE / srcH (= timeSteps).  pf_run_* reject n0 + nsteps > n_src
+                         (and > probe_stride when n_probes > 0) with PF_E_ARG instead of reading /
+                         writing past the tables; 0 = length not given, not checked                 */
+    int32_t reserved0; /* must be 0                                                                 */
     /* global-index window for domain decomposition: this grid holds cells [z0, z0+L) of a global
      * grid of Lg cells (z0 = 0, Lg = L for an undecomposed grid).  Index-dependent rules (update
-     * ranges, CPML ranges, slab, source, probes) are evaluated on global indices.               */
+     * ranges, CPML ranges, slab, source, probes) are evaluated on global indices.
+     * LIMIT: the kernels evaluate these rules in 32-bit arithmetic, so Lg must be < 2^31 - 2^12 cells
+     * (a 1e9-cell grid is fine; pf_run_* return PF_E_UNSUPPORTED beyond); L itself is an int32.   */
     int64_t z0, Lg;
     /* scalars */
     double dt_over_dz;          /* P.delT/P.dz                         BaseFDTD11.py:753         */
@@ -182,9 +192,19 @@ size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine);
  * arrays of dst[m]; the caller alternates the two buffer sets and exchanges ghost cells in between
  * (pf_halo_pack / pf_halo_unpack).  `halo` (>= ksteps) is the overlap the tiles are cut with.  Arrays
  * that exist only on CPML / slab cells may be NULL for a piece that holds no such cell.  Both buffer
- * sets must start out identical.  scratch: pf_run_block_scratch_bytes() bytes (tile tables only).   */
+ * sets must start out identical.  scratch: pf_run_block_scratch_bytes() bytes (tile tables only).
+ * block_flags: PF_BLOCK_F_* (0 is always valid).                                                      */
+enum {
+    PF_BLOCK_F_TABLES_VALID = 1, /* promise by the caller: `scratch` still holds the tile tables the previous
+                                    pf_run_block call on it wrote (nothing else has written to that memory since)
+                                    and they were built from these same two descriptor arrays -- the library then
+                                    skips the host-side rebuild and the H2D copy of the tables.  The library keeps
+                                    NO record of earlier calls: without this flag the tables are always rebuilt.  */
+    PF_BLOCK_F_SWAPPED = 2       /* with TABLES_VALID: src / dst are exchanged relative to the call that built the
+                                    tables (the steady state of a ping-pong run alternates this bit)               */
+};
 int pf_run_block(const PfGrid *src, const PfGrid *dst, int n_grids, int mode, int do_pol, int n0, int ksteps, int halo,
-                 void *scratch, size_t scratch_bytes, void *stream);
+                 int block_flags, void *scratch, size_t scratch_bytes, void *stream);
 size_t pf_run_block_scratch_bytes(const PfGrid *grids, int n_grids, int halo);
 
 /* Per-launch timing of the tile kernel (the dominant kernel): while enabled, every k_tile launch is

@@ -130,6 +130,7 @@ class DeviceGrid:
         g.L, g.pw, g.mf, g.mr, g.nzsrc = self.L, scalars["pw"], scalars["mf"], scalars["mr"], scalars["nzsrc"]
         g.flags = flags
         g.n_probes, g.probe_stride = n_probe, Tp
+        g.n_src = min(len(srcE), len(srcH))
         g.z0, g.Lg = z0, self.L if Lg is None else Lg
         for k in ("dt_over_dz", "eps0", "polA", "polB", "polC", "cub_a", "cub_b", "cub_c", "nl_den0", "nl_den1",
                   "cE0", "cE1", "cH0", "cH1", "c2_pml"):

@@ -16,6 +16,8 @@ LIB_PATH = os.environ.get("PYFDTD_B200_LIB") or os.path.join(HERE, "libpyfdtd_b2
 PF_FREE, PF_LORENTZ, PF_NL, PF_LORENTZ_NL = 0, 1, 2, 3
 PF_ENGINE_OPS, PF_ENGINE_TILE = 0, 1
 PF_PIC_F_OFFSETS_VALID = 1
+PF_BLOCK_F_TABLES_VALID, PF_BLOCK_F_SWAPPED = 1, 2
+PF_ABI_VERSION = 2
 PF_F_TFSF, PF_F_CPML_M, PF_F_CPML_P, PF_F_CANONICAL, PF_F_FMA, PF_F_FP32, PF_F_NEWTON = 1, 2, 4, 8, 16, 32, 64
 
 _dp = c_void_p  # device pointers travel as integers
@@ -25,7 +27,7 @@ class PfGrid(ctypes.Structure):
     """Mirror of ``struct PfGrid`` (include/pyfdtd_b200.h)."""
     _fields_ = [
         ("L", c_int32), ("pw", c_int32), ("mf", c_int32), ("mr", c_int32), ("nzsrc", c_int32),
-        ("flags", c_int32), ("n_probes", c_int32), ("probe_stride", c_int32),
+        ("flags", c_int32), ("n_probes", c_int32), ("probe_stride", c_int32), ("n_src", c_int32), ("reserved0", c_int32),
         ("z0", c_int64), ("Lg", c_int64),
         ("dt_over_dz", c_double), ("eps0", c_double),
         ("polA", c_double), ("polB", c_double), ("polC", c_double),
@@ -81,7 +83,7 @@ SYMBOLS = {
     "pf_run_pass": (c_int, [_G, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_batch": (c_int, [_G, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_scratch_bytes": (c_size_t, [_G, c_int, c_int]),
-    "pf_run_block": (c_int, [_G, _G, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "pf_run_block": (c_int, [_G, _G, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_block_scratch_bytes": (c_size_t, [_G, c_int, c_int]),
     "pf_profile_enable": (c_int, [c_int]),
     "pf_profile_collect": (c_int, [POINTER(c_double), POINTER(c_int)]),
@@ -119,7 +121,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if L.pf_abi_version() != 1:
+        if L.pf_abi_version() != PF_ABI_VERSION:
             raise NativeError("libpyfdtd_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/pyfdtd_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -11,8 +12,8 @@
 
 namespace pf {
 
-extern char g_err[512];
-extern unsigned long long g_launches;
+extern thread_local char g_err[512];               // pf_last_error(): per host thread
+extern std::atomic<unsigned long long> g_launches; // pf_launch_count()
 
 int set_err(int code, const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);

@@ -7,8 +7,8 @@
 
 namespace pf {
 
-char g_err[512] = "";
-unsigned long long g_launches = 0;
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
 
 int set_err(int code, const char *fmt, ...)
 {
@@ -58,7 +58,7 @@ extern "C" {
 
 int pf_abi_version(void) { return PF_ABI_VERSION; }
 const char *pf_last_error(void) { return pf::g_err; }
-unsigned long long pf_launch_count(void) { return pf::g_launches; }
+unsigned long long pf_launch_count(void) { return pf::g_launches.load(); }
 
 int pf_host_exp(const double *x, double *y, long long n)
 {

@@ -30,7 +30,9 @@
 // (the reference's exclusive range end, BaseFDTD11.py:312,326).
 #include <type_traits>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include "pf_common.cuh"
 
@@ -70,7 +72,8 @@ template <int MODE, int C, class R>
 struct TileSmem {
     static constexpr int NT = TILE_CELLS / C;
     static constexpr int N_ARR = 7;
-    static constexpr size_t bytes = sizeof(R) * ((size_t)N_ARR * TILE_CELLS + 2 * NT + 2 + 2 * TILE_KMAX);
+    // + warp-exchange area (PF_WARP_XCHG): two mbarriers (8 B each) per warp
+    static constexpr size_t bytes = sizeof(R) * ((size_t)N_ARR * TILE_CELLS + 2 * NT + 2 + 2 * TILE_KMAX) + 16 + 16 * (NT / 32 + 1);
 };
 
 // Shared memory is addressed as pf_smem[offset + index] with plain integer offsets: going through
@@ -123,6 +126,50 @@ struct TileShared {
     SmemArray<R> cEu, cHu;        // update coefficient of the cell, 0 where the field is never updated
     SmemArray<R> cb, c2u;         // CPML field-correction coefficients, 0 outside / at the quirk cell
     SmemArray<R> edgeH, edgeE, srcE, srcH;
+    unsigned xw;                  // PF_WARP_XCHG: byte address of the per-warp exchange area (16-byte aligned)
+};
+
+// ---- neighbour-warp exchange (PF_WARP_XCHG) ---------------------------------------------------------
+// The one Hy / Ex value a thread needs from its neighbour thread travels through the shared edge arrays exactly as
+// in the barrier scheme; what changes is who waits for whom.  Inside a warp a __syncwarp orders the store and the
+// neighbour lane's load.  Between adjacent warps the value is handed over with an mbarrier of arrival count 1
+// (producer lane: store, __syncwarp, arrive(release); consumer warp: try_wait(acquire) on the phase parity, load).
+// The two directions of a warp boundary alternate strictly (H_init, E_0, H_0, E_1, ...), so neither warp can run
+// more than one phase ahead of the other: the single edge slot is never overwritten before it was read, one parity
+// bit per direction tracks the phase, and no CTA-wide barrier is left in the time loop.  Warps whose neighbour
+// holds no grid cell (dead warp / tile end) neither wait nor arrive on that side; the slot they read stays 0.
+// Exchange area: per warp w 16 bytes = [mbarH u64][mbarE u64].
+__device__ __forceinline__ unsigned xw_barH(unsigned xw, int w) { return xw + 16u * (unsigned)w; }
+__device__ __forceinline__ unsigned xw_barE(unsigned xw, int w) { return xw + 16u * (unsigned)w + 8u; }
+__device__ __forceinline__ void xw_init(unsigned bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void xw_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// orders a lane's edge store before the neighbour lane's load (and before the publishing lane's arrive)
+__device__ __forceinline__ void xw_syncwarp()
+{
+#ifndef PF_WX_NOSYNCWARP   // timing experiment: cost of the convergence check the compiler wraps around bar.warp.sync
+    __syncwarp();
+#endif
+}
+__device__ __forceinline__ void xw_wait(unsigned bar, unsigned parity)
+{
+    // every lane of the warp tests the same barrier in the same instruction: the loop branch is uniform
+    asm volatile("{\n.reg .pred p;\nXW_WAIT:\nmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n@!p bra.uni XW_WAIT;\n}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+// what a warp knows about its two neighbours (warp-uniform)
+struct WarpLink {
+    bool sendH, sendE;     // this LANE publishes the warp's Hy edge to the right (lane 31) / Ex edge to the left (lane 0)
+    unsigned pH, pE;       // phase parity of the next H / E hand-over this warp WAITS for
+    unsigned fH, fE;       // 1: the parity alternates (live neighbour); 0: no neighbour on that side -- the wait is on the
+                           // CTA's dummy barrier with parity 1 (the phase before the first: always complete), no branch
+    unsigned barL, barR;   // mbarrier this warp waits on: the left neighbour's H barrier, the right neighbour's E barrier
+    unsigned barS;         // this warp's own H barrier (its E barrier is at +8)
 };
 
 // CTA-wide barrier usable from warp-uniform divergent code: every warp executes exactly two of
@@ -199,7 +246,7 @@ __device__ __forceinline__ NlResultF nl_material_law_f32(float ca, float cb, flo
 //   pc = P^n (current polarisation), pq = P^{n-1}: the new P^{n+1} is written over pq, so the
 //   caller alternates (pc,pq) <-> (pq,pc) instead of shifting the history (no register moves).
 template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, bool SP, class R = typename A::real>
-__device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepConsts<R> &K, const CubicConsts *kcp, int tid, int s,
+__device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepConsts<R> &K, const CubicConsts *kcp, WarpLink &W, int tid, int s,
                                           R (&ex)[C], R (&hy)[C], R (&dx)[C], R (&pc)[C],
                                           R (&pq)[C], R (&pe)[C], R (&ph)[C], R (&acub)[C],
                                           R (&rbe)[C], R (&rce)[C], R (&rcm)[C])
@@ -212,6 +259,10 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
     constexpr bool HAS_PML = GEN || PML;
     // ===== E half-step: history shift + polarisation, ADE_ExUpdate, CPML_Psi_e, source,
     //                    ADE_DxUpdate, ADE_ExCreate | AcubicFinder + NonLinExUpdate =====
+#ifdef PF_WARP_XCHG
+    xw_wait(W.barL, W.pH);   // the left neighbour warp's Hy edge of the previous step (or H_init)
+    W.pH ^= W.fH;
+#endif
     R hl = S.edgeH[tid - 1];
     unsigned divkey = 0;
 #pragma unroll
@@ -325,7 +376,12 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
             if (j == K.jsrc && !(HAS_MAT && ((K.mSlab >> j) & 1))) ex[j] = A::add(ex[j], S.srcE[s]);
     }
     S.edgeE[tid] = ex[0];
+#ifdef PF_WARP_XCHG
+    xw_syncwarp();
+    if (W.sendE) xw_arrive(W.barS + 8u);   // lane 0 of a warp with a live left neighbour
+#else
     cta_sync();
+#endif
     if (SP && K.wSrc) {   // one-point TF/SF correction (Solver_Engine.py:309-310), before ADE_HyUpdate
 #pragma unroll
         for (int j = 0; j < C; ++j)
@@ -335,6 +391,10 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
     // ===== H half-step: TF/SF correction, ADE_HyUpdate, CPML_Psi_m =====
     // the neighbour's Ex is requested first and consumed last (cell C-1), behind the cells that only
     // need the thread's own Ex, so the shared-memory latency is covered
+#ifdef PF_WARP_XCHG
+    xw_wait(W.barR, W.pE);   // the right neighbour warp's Ex edge of this step
+    W.pE ^= W.fE;
+#endif
     const R exr = S.edgeE[tid + 1];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
@@ -351,6 +411,10 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
         hy[j] = h;
     }
     S.edgeH[tid] = hy[C - 1];
+#ifdef PF_WARP_XCHG
+    xw_syncwarp();
+    if (W.sendH) xw_arrive(W.barS);        // lane 31 of a warp with a live right neighbour
+#endif
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -365,7 +429,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
 //                 is needed; only the material law is selected per cell.
 // -------------------------------------------------------------------------------------------------
 template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, class R = typename A::real>
-__device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R> &S, const CellMasks &M,
+__device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R> &S, const CellMasks &M, WarpLink W,
                                           int tid, int lz0, int ks, int src, int nabs0)
 {
     constexpr int NT = TILE_CELLS / C;
@@ -477,7 +541,12 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
     };
 
     S.edgeH[tid] = hy[C - 1];
+#ifdef PF_WARP_XCHG
+    xw_syncwarp();
+    if (W.sendH) xw_arrive(W.barS);   // H_init: the first E half-step of the right neighbour warp needs it
+#else
     cta_sync();
+#endif
     constexpr bool SWAP = LOR && HAS_MAT && POL && !F32;   // P history alternates between pa and pb
     bool swapped = false;   // true: current P is in pb, previous in pa
     // The time loop exists twice: warps that own a source cell or a probe run the version with those
@@ -485,19 +554,24 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
     auto time_loop = [&](auto sp) {
         constexpr bool SP = decltype(sp)::value;
         int s = 0;
+#ifdef PF_WARP_XCHG
+#define PF_STEP_SYNC()
+#else
+#define PF_STEP_SYNC() cta_sync()
+#endif
         for (; s + 1 < ks; s += 2) {
-            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
             if (SP) probes(s);
-            cta_sync();
-            if (SWAP) tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, tid, s + 1, ex, hy, dx, pb, pa, pe, ph, acub, rbe, rce, rcm);
-            else tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, tid, s + 1, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            PF_STEP_SYNC();
+            if (SWAP) tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s + 1, ex, hy, dx, pb, pa, pe, ph, acub, rbe, rce, rcm);
+            else tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s + 1, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
             if (SP) probes(s + 1);
-            cta_sync();
+            PF_STEP_SYNC();
         }
         if (s < ks) {
-            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
             if (SP) probes(s);
-            cta_sync();
+            PF_STEP_SYNC();
             swapped = SWAP;
         }
     };
@@ -595,6 +669,7 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     S.edgeE.base = S.edgeH.base + RB * NT;
     S.srcE.base = S.edgeE.base + RB * NT + RB;
     S.srcH.base = S.srcE.base + RB * TILE_KMAX;
+    S.xw = (S.srcH.base + RB * TILE_KMAX + 15u) & ~15u;
 
     const TileDesc td = tiles[blockIdx.x];
     const TileGrid &TG = grids[td.grid];
@@ -663,11 +738,44 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     const int cls0 = __shfl_sync(0xffffffffu, cls, 0);
     cls = __all_sync(0xffffffffu, cls == cls0) ? cls0 : 4;
 
+    WarpLink W;
+    W.pH = W.pE = W.fH = W.fE = 0u;
+    W.sendH = W.sendE = false;
+    W.barL = W.barR = W.barS = 0u;
+#ifdef PF_WARP_XCHG
+    {
+        // a neighbour warp is live iff at least one of its cells lies inside the grid (same test as cls == 5 above)
+        const int w = tid >> 5, lane = tid & 31;
+        const int wfirst = td.base + w * 32 * C;           // first cell of this warp
+        const bool live = cls != 5;
+        const bool left = live && w > 0 && wfirst - 1 >= 0 && wfirst - 32 * C < L;
+        const bool right = live && w < NT / 32 - 1 && wfirst + 32 * C < L && wfirst + 64 * C - 1 >= 0;
+        const unsigned dummy = xw_barH(S.xw, NT / 32);   // never arrived on
+        W.sendH = right && lane == 31;
+        W.sendE = left && lane == 0;
+        W.barS = xw_barH(S.xw, w);
+        W.barL = left ? xw_barH(S.xw, w - 1) : dummy;
+        W.barR = right ? xw_barE(S.xw, w + 1) : dummy;
+        W.fH = left ? 1u : 0u;  W.pH = left ? 0u : 1u;
+        W.fE = right ? 1u : 0u; W.pE = right ? 0u : 1u;
+        if (lane == 0) {
+            xw_init(xw_barH(S.xw, w));
+            xw_init(xw_barE(S.xw, w));
+            if (w == 0) xw_init(dummy);
+        }
+        S.edgeH[tid] = R(0);   // slots of dead warps are read as 0 by their live neighbours
+        S.edgeE[tid] = R(0);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();   // the only CTA-wide barrier of the launch: mbarriers initialised, source tables loaded
+        if (cls == 5) return;
+    }
+#endif
+
     switch (cls) {
-    case 0: tile_body<MODE, POL, C, A, false, false, false>(TG, S, M, tid, lz0, ks, src, nabs0); break;
-    case 1: tile_body<MODE, POL, C, A, false, true, false>(TG, S, M, tid, lz0, ks, src, nabs0); break;
-    case 2: tile_body<MODE, POL, C, A, false, false, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
-    case 3: tile_body<MODE, POL, C, A, false, true, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
+    case 0: tile_body<MODE, POL, C, A, false, false, false>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    case 1: tile_body<MODE, POL, C, A, false, true, false>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    case 2: tile_body<MODE, POL, C, A, false, false, true>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    case 3: tile_body<MODE, POL, C, A, false, true, true>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
     case 5:
         // nothing to compute: publish zero edges once, then only keep the CTA's barrier count
         S.edgeH[tid] = R(0);
@@ -675,7 +783,7 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
         cta_sync();
         for (int s = 0; s < ks; ++s) { cta_sync(); cta_sync(); }
         break;
-    default: tile_body<MODE, POL, C, A, true, true, true>(TG, S, M, tid, lz0, ks, src, nabs0); break;
+    default: tile_body<MODE, POL, C, A, true, true, true>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
     }
 }
 
@@ -736,8 +844,23 @@ static inline bool piece_has_pml(const PfGrid &g)
 }
 static inline bool piece_has_slab(const PfGrid &g) { return g.z0 < g.mr && g.z0 + g.L > g.mf; }
 
+// n0 .. n0+nsteps-1 must lie inside the caller's source tables and probe rows (PfGrid.n_src / probe_stride)
+int check_step_range(const PfGrid &g, int n0, int nsteps, const char *who)
+{
+    if (n0 < 0 || nsteps < 0) return set_err(PF_E_ARG, "%s: negative step range", who);
+    if (nsteps == 0) return 0;
+    const long long end = (long long)n0 + nsteps;
+    if (g.n_src > 0 && end > g.n_src)
+        return set_err(PF_E_ARG, "%s: steps %d..%lld run past the source tables (n_src = %d)", who, n0, end - 1, g.n_src);
+    if (g.n_probes > 0 && end > g.probe_stride)
+        return set_err(PF_E_ARG, "%s: steps %d..%lld run past the probe rows (probe_stride = %d)", who, n0, end - 1, g.probe_stride);
+    return 0;
+}
+
 static int tile_supported(const PfGrid &g, int mode)
 {
+    if (g.Lg >= (1LL << 31) - (1LL << 12) || g.z0 < -(1LL << 30) || g.z0 + g.L > g.Lg + (1LL << 12))
+        return set_err(PF_E_UNSUPPORTED, "tile engine: global indices are evaluated in 32 bits (Lg = %lld)", (long long)g.Lg);
     if (!(g.flags & PF_F_CANONICAL)) return set_err(PF_E_UNSUPPORTED, "tile engine needs PF_F_CANONICAL coefficients");
     if (g.Jx) return set_err(PF_E_UNSUPPORTED, "tile engine: Jx must be NULL");
     if (mode != PF_FREE && (g.flags & PF_F_TFSF) && g.nzsrc - 1 >= g.mf - 1 && g.nzsrc - 1 < g.mr)
@@ -781,7 +904,8 @@ static TilePlan tile_plan(const PfGrid *grids, int n, int mode, int halo)
 }
 
 // ---- optional per-launch timing of the dominant kernel (bench.py's roofline numerator) ----------
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mutex;   // guards g_prof_events (launches may come from one host thread per GPU)
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 
 struct ProfScope {
@@ -795,6 +919,7 @@ struct ProfScope {
     {
         if (a && b) {
             cudaEventRecord(b, st);
+            std::lock_guard<std::mutex> lk(g_prof_mutex);
             g_prof_events.emplace_back(a, b);
         }
     }
@@ -808,10 +933,14 @@ static int launch_tile_a(int n_tiles, const TileGrid *dg, const TileDesc *dt, in
 {
     const size_t sm = TileSmem<MODE, C, typename A::real>::bytes;
     ProfScope prof(st);
-    static bool set[64] = {};   // the attribute is per device
+    static std::atomic<unsigned long long> attr_set{0};   // the attribute is per device; bit = device ordinal (idempotent, race-free)
     int dev = 0;
     PF_CUDA(cudaGetDevice(&dev));
-    if (!set[dev & 63]) { PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); set[dev & 63] = true; }
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(attr_set.load(std::memory_order_acquire) & bit)) {
+        PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        attr_set.fetch_or(bit, std::memory_order_release);
+    }
     k_tile<MODE, POL, C, A><<<n_tiles, TILE_CELLS / C, sm, st>>>(dg, dt, src, n_done, n0, ks, halo);
     PF_LAUNCH_CHECK("k_tile");
     return 0;
@@ -912,34 +1041,18 @@ static bool mostly_interior(const PfGrid *grids, int n)
     return pml * 8 < cells;
 }
 
-// Tile tables of the last pf_run_block call, kept on the device (in the caller's scratch) so that the
-// steady state of a long run -- the same two buffer sets, alternating -- costs no host-side rebuild and no
-// H2D copy per block: the tables hold both buffer sets and the kernel's `src` argument selects the
-// direction.
-struct BlockCache {
-    void *scratch = nullptr;
-    int n = 0, mode = -1, halo = 0, n_tiles = 0;
-    bool wide = false;
-    std::vector<PfGrid> a, b;   // descriptors the tables were built from (buffer 0 / buffer 1)
-};
-static BlockCache g_block_cache;
-
-static bool same_grids(const std::vector<PfGrid> &v, const PfGrid *g, int n)
-{
-    return (int)v.size() == n && memcmp(v.data(), g, sizeof(PfGrid) * (size_t)n) == 0;
-}
-
 // Runs the tile engine over n grids.  snap_* only with n == 1.
 int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int *nsteps, int k_block,
              double *snap_out, int snap_interval, int snap_rows, void *scratch, size_t scratch_bytes,
              cudaStream_t st)
 {
     if (n <= 0) return PF_OK;
-    g_block_cache.scratch = nullptr;   // this call writes its own tables; never trust a stale block cache
     if (k_block <= 0) k_block = TILE_KDEF;
     if (k_block > TILE_KMAX) k_block = TILE_KMAX;
     for (int m = 0; m < n; ++m) {
         int rc = tile_supported(grids[m], mode);
+        if (rc) return rc;
+        rc = check_step_range(grids[m], n0, nsteps[m], "pf_run_batch");
         if (rc) return rc;
     }
     const int halo = k_block;
@@ -1034,14 +1147,16 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
 
 // One launch: advance n grids by `ks` steps (absolute steps n0 .. n0+ks-1) reading the arrays of
 // src[m] and writing the arrays of dst[m] (the caller owns both buffers and alternates them).
-// halo >= ks is the overlap the tiles are cut with.  scratch holds only the tile tables.
-int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol, int n0, int ks, int halo,
+// halo >= ks is the overlap the tiles are cut with.  scratch holds only the tile tables: they carry both
+// buffer sets (the kernel's `src` argument selects the direction), so the steady state of a ping-pong run
+// -- the caller promises PF_BLOCK_F_TABLES_VALID -- costs no host-side rebuild and no H2D copy.  Nothing about
+// earlier calls is remembered here.
+int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol, int n0, int ks, int halo, int block_flags,
                void *scratch, size_t scratch_bytes, cudaStream_t st)
 {
     if (n <= 0 || ks <= 0) return PF_OK;
     if (halo < ks) halo = ks;
     if (halo > TILE_KMAX) return set_err(PF_E_ARG, "pf_run_block: ksteps/halo %d exceeds the tile engine limit %d", halo, TILE_KMAX);
-    BlockCache &bc = g_block_cache;
     const size_t off_tiles = align_up(sizeof(TileGrid) * (size_t)n, 256);
     TileGrid *dg = (TileGrid *)scratch;
     TileDesc *dt = (TileDesc *)((char *)scratch + off_tiles);
@@ -1050,20 +1165,25 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
         int rc = arith_of(src, n, mode, &fma);
         if (rc) return rc;
     }
-    if (bc.scratch == scratch && bc.n == n && bc.mode == mode && bc.halo == halo) {
-        if (same_grids(bc.a, src, n) && same_grids(bc.b, dst, n))
-            return launch_tile_mode(mode, do_pol, fma, bc.wide, bc.n_tiles, dg, dt, 0, 0, n0, ks, halo, st);
-        if (same_grids(bc.b, src, n) && same_grids(bc.a, dst, n))
-            return launch_tile_mode(mode, do_pol, fma, bc.wide, bc.n_tiles, dg, dt, 1, 0, n0, ks, halo, st);
-    }
-    bc.scratch = nullptr;
     const int W = TILE_CELLS - 2 * halo;
-    std::vector<TileGrid> hg(n);
-    std::vector<TileDesc> ht;
+    long long n_tiles = 0;
     for (int m = 0; m < n; ++m) {
         int rc = tile_supported(src[m], mode);
         if (rc) return rc;
         if (dst[m].L != src[m].L) return set_err(PF_E_ARG, "pf_run_block: src/dst length mismatch in grid %d", m);
+        rc = check_step_range(src[m], n0, ks, "pf_run_block");
+        if (rc) return rc;
+        n_tiles += (src[m].L + W - 1) / W;
+    }
+    const size_t need = off_tiles + align_up(sizeof(TileDesc) * (size_t)n_tiles, 256);
+    if (!scratch || scratch_bytes < need) return set_err(PF_E_SCRATCH, "pf_run_block needs %zu bytes of scratch, got %zu", need, scratch_bytes);
+    const bool wide = mostly_interior(src, n);
+    if (block_flags & PF_BLOCK_F_TABLES_VALID)
+        return launch_tile_mode(mode, do_pol, fma, wide, (int)n_tiles, dg, dt, (block_flags & PF_BLOCK_F_SWAPPED) ? 1 : 0, 0, n0, ks, halo, st);
+    std::vector<TileGrid> hg(n);
+    std::vector<TileDesc> ht;
+    ht.reserve((size_t)n_tiles);
+    for (int m = 0; m < n; ++m) {
         TileGrid &t = hg[m];
         t.d = make_grid_dev(src[m]);
         double *a0[7] = {src[m].Ex, src[m].Hy, src[m].psiE, src[m].psiH, src[m].Dx, src[m].P, src[m].Pprev};
@@ -1078,16 +1198,9 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
         int ntile = (src[m].L + W - 1) / W;
         for (int i = 0; i < ntile; ++i) ht.push_back(TileDesc{m, i * W - halo});
     }
-    size_t need = off_tiles + align_up(sizeof(TileDesc) * ht.size(), 256);
-    if (!scratch || scratch_bytes < need) return set_err(PF_E_SCRATCH, "pf_run_block needs %zu bytes of scratch, got %zu", need, scratch_bytes);
     PF_CUDA(cudaMemcpyAsync(dg, hg.data(), sizeof(TileGrid) * n, cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaMemcpyAsync(dt, ht.data(), sizeof(TileDesc) * ht.size(), cudaMemcpyHostToDevice, st));
-    bc.scratch = scratch;
-    bc.n = n; bc.mode = mode; bc.halo = halo; bc.n_tiles = (int)ht.size();
-    bc.wide = mostly_interior(src, n);
-    bc.a.assign(src, src + n);
-    bc.b.assign(dst, dst + n);
-    return launch_tile_mode(mode, do_pol, fma, bc.wide, (int)ht.size(), dg, dt, 0, 0, n0, ks, halo, st);
+    return launch_tile_mode(mode, do_pol, fma, wide, (int)ht.size(), dg, dt, 0, 0, n0, ks, halo, st);
 }
 
 int ops_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, double *snap_out,
@@ -1116,6 +1229,7 @@ int pf_profile_collect(double *ms_total, int *n_launches)
 {
     double tot = 0.0;
     int n = 0;
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
     for (auto &ev : g_prof_events) {
         float ms = 0.f;
         PF_CUDA(cudaEventSynchronize(ev.second));
@@ -1132,11 +1246,11 @@ int pf_profile_collect(double *ms_total, int *n_launches)
 }
 
 int pf_run_block(const PfGrid *src, const PfGrid *dst, int n_grids, int mode, int do_pol, int n0, int ksteps, int halo,
-                 void *scratch, size_t scratch_bytes, void *stream)
+                 int block_flags, void *scratch, size_t scratch_bytes, void *stream)
 {
     if (!src || !dst || n_grids < 0) return set_err(PF_E_ARG, "pf_run_block: bad arguments");
     if (mode < PF_FREE || mode > PF_LORENTZ_NL) return set_err(PF_E_ARG, "pf_run_block: bad mode %d", mode);
-    return tile_block(src, dst, n_grids, mode, do_pol, n0, ksteps, halo, scratch, scratch_bytes, (cudaStream_t)stream);
+    return tile_block(src, dst, n_grids, mode, do_pol, n0, ksteps, halo, block_flags, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 size_t pf_run_block_scratch_bytes(const PfGrid *grids, int n_grids, int halo)
@@ -1165,6 +1279,10 @@ int pf_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, int e
     cudaStream_t st = (cudaStream_t)stream;
     if (engine == PF_ENGINE_OPS && (g->flags & PF_F_FP32))
         return set_err(PF_E_UNSUPPORTED, "PF_F_FP32 is a mode of the tile engine only");
+    {
+        int rc = check_step_range(*g, n0, nsteps, "pf_run_pass");
+        if (rc) return rc;
+    }
     if (engine == PF_ENGINE_OPS) return ops_run_pass(g, mode, do_pol, n0, nsteps, snap_out, snap_interval, snap_rows, st);
     if (engine == PF_ENGINE_TILE)
         return tile_run(g, 1, mode, do_pol, n0, &nsteps, 0, snap_out, snap_interval, snap_rows, scratch, scratch_bytes, st);

@@ -203,6 +203,7 @@ class LongGrid:
                 g.L, g.pw, g.mf, g.mr, g.nzsrc = L, pw, mf, mr, nzsrc
                 g.flags = flags
                 g.n_probes, g.probe_stride = len(own), T
+                g.n_src = T
                 g.z0, g.Lg = z0, self.Lg
                 for kk, v in scalars.items():
                     if hasattr(g, kk) and kk not in ("pw", "mf", "mr", "nzsrc"):
@@ -235,6 +236,7 @@ class LongGrid:
         self.scratch_bytes = sb
         self.cur = 0
         self.n_done = 0
+        self._tables_built = False    # the tile tables in self.scratch were written by this object's last pf_run_block
         self.halo_bufs = {}
         self.cells_owned = sum(p["hi"] - p["lo"] for p in self.mine)
         self._local_of = {p["index"]: i for i, p in enumerate(self.mine)}
@@ -271,14 +273,22 @@ class LongGrid:
     # -- time stepping -------------------------------------------------------------------------
     def run(self, nsteps, do_pol=True):
         lib = nat.lib()
+        if self.n_done + nsteps > self.T:
+            raise ValueError(f"LongGrid.run: steps {self.n_done}..{self.n_done + nsteps - 1} run past the source tables (T = {self.T})")
         done = 0
         while done < nsteps:
             ks = min(self.k, nsteps - done)
             if len(self.pieces) > 1:
                 self.exchange()
+            # the tables hold buffer set 0 as `src`; this object owns the scratch, so after the first call they stay valid
+            bflags = 0
+            if self._tables_built:
+                bflags = nat.PF_BLOCK_F_TABLES_VALID | (nat.PF_BLOCK_F_SWAPPED if self.cur != self._tables_src else 0)
             nat.check(lib.pf_run_block(self.grids[self.cur], self.grids[self.cur ^ 1], len(self.mine), self.mode_id,
-                                       int(do_pol), self.n_done, ks, self.k, self.scratch.data_ptr(), self.scratch_bytes,
+                                       int(do_pol), self.n_done, ks, self.k, bflags, self.scratch.data_ptr(), self.scratch_bytes,
                                        nat.current_stream_ptr()), "pf_run_block")
+            if not self._tables_built:
+                self._tables_built, self._tables_src = True, self.cur
             self.cur ^= 1
             self.n_done += ks
             done += ks

@@ -154,6 +154,8 @@ class CoupledPIC:
 
     def step(self, do_pol=False):
         lib = nat.lib()
+        if self.n >= self.grid.T:
+            raise ValueError(f"CoupledPIC.step: step {self.n} is past the grid's source tables (T = {self.grid.T})")
         if not (self.fused and self._have_J):
             self.particles.deposit()
         nat.check(lib.pf_run_pass(self.grid.ref(), self.mode_id, int(do_pol), self.n, 1, nat.PF_ENGINE_OPS, None, 0, 0,

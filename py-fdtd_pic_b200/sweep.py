@@ -40,10 +40,23 @@ class Member:
         canon = dev.canonical_form(P, arrs, None)
         if canon is None or not dev.probes_ok_for_tiles(self.probe_idx):
             raise ValueError("sweep member is not in the tile engine's canonical form; run it through Controller")
-        self.scalars = BaseFDTD11.grid_scalars(V, P, kerr_lorentz=SE.KERR_LORENTZ)
-        self.scalars.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
+        self._canon = canon
+        self.scalars = None
+        self.set_mode("lorentz_nl" if SE.KERR_LORENTZ else None)
         self.flags = BaseFDTD11.grid_flags(P, SE.USE_FMA, SE.USE_FP32, SE.CUBIC == "newton") | nat.PF_F_CANONICAL
         self.coef = {"beX": C_V.beX, "ceX": C_V.ceX, "cmY": C_V.cmY}
+
+
+    def set_mode(self, mode):
+        """Scalars of the PfGrid for integrator ``mode``: only "lorentz_nl" (the Kerr-Lorentz composition) uses its own
+        cubic coefficients; MemberBatch calls this with the mode the batch actually runs, so the module-level switch
+        Solver_Engine.KERR_LORENTZ cannot leak into a batch of another mode."""
+        kerr = mode == "lorentz_nl"
+        if self.scalars is None or kerr != self._kerr:
+            canon = self._canon
+            self._kerr = kerr
+            self.scalars = BaseFDTD11.grid_scalars(self.V, self.P, kerr_lorentz=kerr)
+            self.scalars.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
 
 
 class MemberBatch:
@@ -56,6 +69,8 @@ class MemberBatch:
         self.mode = mode
         self.mode_id = dev.MODE_ID[mode]
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        for m in members:
+            m.set_mode(mode)
         M = len(members)
         # ---- layout (doubles): [state of all members][coef+src of all members][probes of all members]
         self.off_state, self.off_in, self.off_probe = [], [], []
@@ -132,6 +147,7 @@ class MemberBatch:
             g.L, g.pw, g.mf, g.mr, g.nzsrc = m.L, s["pw"], s["mf"], s["mr"], s["nzsrc"]
             g.flags = m.flags
             g.n_probes, g.probe_stride = len(m.probe_idx), Tp
+            g.n_src = min(len(m.srcE), len(m.srcH))
             g.z0, g.Lg = 0, m.L
             for k in ("dt_over_dz", "eps0", "polA", "polB", "polC", "cub_a", "cub_b", "cub_c", "nl_den0", "nl_den1",
                       "cE0", "cE1", "cH0", "cH1", "c2_pml"):

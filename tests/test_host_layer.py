@@ -146,7 +146,7 @@ def test_library_exports_every_header_symbol():
     lib = nat.lib()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.pf_abi_version() == 1
+    assert lib.pf_abi_version() == 2
 
 
 def test_ctypes_structs_match_header(tmp_path):

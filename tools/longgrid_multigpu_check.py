@@ -54,7 +54,7 @@ if os.environ.get("PF_LONGGRID_BREAKDOWN"):
             grid.exchange()
         torch.cuda.synchronize(); t1 = time.perf_counter()
         nat.check(nat.lib().pf_run_block(grid.grids[grid.cur], grid.grids[grid.cur ^ 1], len(grid.mine), grid.mode_id, 1,
-                                         grid.n_done, a.k, a.k, grid.scratch.data_ptr(), grid.scratch_bytes,
+                                         grid.n_done, a.k, a.k, 0, grid.scratch.data_ptr(), grid.scratch_bytes,
                                          nat.current_stream_ptr()), "pf_run_block")
         t2 = time.perf_counter()
         torch.cuda.synchronize(); t3 = time.perf_counter()
