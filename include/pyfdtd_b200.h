@@ -146,6 +146,31 @@ unsigned long long pf_launch_count(void);
 int pf_host_exp(const double *x, double *y, long long n);
 int pf_host_pow(const double *x, double e, double *y, long long n);
 
+int pf_host_sin(const double *x, double *y, long long n, int threads);   /* libm sin / cos, elementwise, on `threads`  */
+int pf_host_cos(const double *x, double *y, long long n, int threads);   /* host threads (0 = all)                      */
+
+/* Host-side setup of a whole sweep in one call: for every member the CPML recursive-convolution
+ * profiles (BaseFDTD11.CPML_ScalingCalc :222-272, CPML_Ex_RC_Define :274-286, CPML_HY_RC_Define :288-296) and the
+ * per-step source tables (Solver_Engine.SourceManager :89-124 over BaseFDTD11.SmoothTurnOn :104-120, divided by
+ * courantNo as PfGrid.srcE / srcH want them), written straight into the caller's upload buffer `out` at the given
+ * offsets (in doubles).  Same IEEE operations in the same order as the reference's loops (libm exp / pow / sin):
+ * bit-identical to the per-member Python chain.  Members are independent; `threads` host threads (0 = all).        */
+typedef struct PfSetupMember {
+    int32_t L;        /* Nz+1: the three profile arrays are written over [0, L), zero outside the CPML cells        */
+    int32_t pw;       /* pmlWidth                                                                                   */
+    int32_t n_src;    /* source entries to generate (<= timeSteps)                                                  */
+    int32_t src_kind; /* 0: the caller fills the source tables itself, 1: P.SineCont (SmoothTurnOn)                 */
+    int32_t tfsf;     /* P.TFSF: Hys scaled by 1/CharImp                          Solver_Engine.py:103-104         */
+    int32_t pump;     /* P.nonLinMed: pump at 0.8 f added, 0.1 / 0.01 weights     Solver_Engine.py:95-100          */
+    double dz, delT, eps0;
+    double kappaMax, r_scale, r_a_scale, sigmaOpt, alphaMax;   /* CPML_Params, MasterController.py:341-360          */
+    double c0, freq, courantNo, period, periods, charImp;      /* Params members the source uses                    */
+    double amp;       /* the member's amplitude: multiplies Exs and Hys (1.0 for a plain frequency sweep)           */
+    int64_t off_beX, off_ceX, off_cmY; /* offsets into out[]; off_beX < 0: profiles not written (shared with another member) */
+    int64_t off_srcE, off_srcH;        /* off_srcE < 0: sources not written                                          */
+} PfSetupMember;
+int pf_host_sweep_inputs(const PfSetupMember *members, int n_members, double *out, int threads);
+
 /* ---- leaf ops: one call = one reference leaf function on one grid ---------------------- */
 int pf_ade_ex_update(const PfGrid *g, void *stream);        /* BaseFDTD11.py:663-669  ADE_ExUpdate               */
 int pf_ade_hy_update(const PfGrid *g, void *stream);        /* BaseFDTD11.py:640-656  ADE_HyUpdate               */

@@ -55,6 +55,18 @@ class PfPic(ctypes.Structure):
     ]
 
 
+class PfSetupMember(ctypes.Structure):
+    """Mirror of ``struct PfSetupMember``."""
+    _fields_ = [
+        ("L", c_int32), ("pw", c_int32), ("n_src", c_int32), ("src_kind", c_int32), ("tfsf", c_int32), ("pump", c_int32),
+        ("dz", c_double), ("delT", c_double), ("eps0", c_double),
+        ("kappaMax", c_double), ("r_scale", c_double), ("r_a_scale", c_double), ("sigmaOpt", c_double), ("alphaMax", c_double),
+        ("c0", c_double), ("freq", c_double), ("courantNo", c_double), ("period", c_double), ("periods", c_double),
+        ("charImp", c_double), ("amp", c_double),
+        ("off_beX", c_int64), ("off_ceX", c_int64), ("off_cmY", c_int64), ("off_srcE", c_int64), ("off_srcH", c_int64),
+    ]
+
+
 # every symbol include/pyfdtd_b200.h declares: name -> (restype, argtypes)
 _G = POINTER(PfGrid)
 _PP = POINTER(PfPic)
@@ -66,6 +78,9 @@ SYMBOLS = {
     "pf_launch_count": (ctypes.c_ulonglong, []),
     "pf_host_exp": (c_int, [c_void_p, c_void_p, ctypes.c_longlong]),
     "pf_host_pow": (c_int, [c_void_p, c_double, c_void_p, ctypes.c_longlong]),
+    "pf_host_sin": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int]),
+    "pf_host_cos": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int]),
+    "pf_host_sweep_inputs": (c_int, [c_void_p, c_int, c_void_p, c_int]),
     "pf_ade_ex_update": (c_int, [_G, c_void_p]),
     "pf_ade_hy_update": (c_int, [_G, c_void_p]),
     "pf_cpml_psi_e_update": (c_int, [_G, c_void_p]),

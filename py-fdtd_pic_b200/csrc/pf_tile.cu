@@ -246,7 +246,7 @@ __device__ __forceinline__ NlResultF nl_material_law_f32(float ca, float cb, flo
 //   pc = P^n (current polarisation), pq = P^{n-1}: the new P^{n+1} is written over pq, so the
 //   caller alternates (pc,pq) <-> (pq,pc) instead of shifting the history (no register moves).
 template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, bool SP, class R = typename A::real>
-__device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepConsts<R> &K, const CubicConsts *kcp, WarpLink &W, int tid, int s,
+__device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepConsts<R> &K, const CubicConsts *kcp, WarpLink &W, int tid, int s, bool more,
                                           R (&ex)[C], R (&hy)[C], R (&dx)[C], R (&pc)[C],
                                           R (&pq)[C], R (&pe)[C], R (&ph)[C], R (&acub)[C],
                                           R (&rbe)[C], R (&rce)[C], R (&rcm)[C])
@@ -285,7 +285,10 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                     pnow = pc[j];
                     vnew = v;
                 } else {
+#ifndef PF_PHASE_BALANCE
                     pq[j] = A::add(A::add(A::mul(K.pA, pc[j]), A::mul(K.pB, pq[j])), A::mul(K.pC, e));
+#endif
+                    // PF_PHASE_BALANCE: P^{n+1} was already written to pq behind the previous step's H half-step (below)
                     pnow = pq[j];
                 }
             } else {
@@ -414,6 +417,20 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
 #ifdef PF_WARP_XCHG
     xw_syncwarp();
     if (W.sendH) xw_arrive(W.barS);        // lane 31 of a warp with a live right neighbour
+#endif
+#ifdef PF_PHASE_BALANCE
+    // The polarisation update of the NEXT step (ADE_PolarisationCurrent_Ex: P^{n+2} from P^{n+1}, P^n and the Ex this step
+    // just produced) is issued here, behind the H half-step, instead of at the top of the next E half-step: the same
+    // operations on the same values, but the fp64 work is now split 14 : 16 between the two barrier-separated phases of a
+    // step instead of 24 : 6, so two co-resident CTAs load the FP64 pipe evenly whatever their relative phase.
+    // Roles are those of the next step: its current P is this step's pq, its previous P (overwritten) this step's pc.
+    if constexpr (LOR && HAS_MAT && POL && !F32) {
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < C; ++j)
+                pc[j] = A::add(A::add(A::mul(K.pA, pq[j]), A::mul(K.pB, pc[j])), A::mul(K.pC, ex[j]));
+        }
+    }
 #endif
 }
 
@@ -549,6 +566,13 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 #endif
     constexpr bool SWAP = LOR && HAS_MAT && POL && !F32;   // P history alternates between pa and pb
     bool swapped = false;   // true: current P is in pb, previous in pa
+#ifdef PF_PHASE_BALANCE
+    if constexpr (SWAP) {   // step 0's polarisation update (every later one rides behind the previous step's H half-step)
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+            pb[j] = A::add(A::add(A::mul(g.polA, pa[j]), A::mul(g.polB, pb[j])), A::mul(g.polC, ex[j]));
+    }
+#endif
     // The time loop exists twice: warps that own a source cell or a probe run the version with those
     // (warp-uniform) tests, every other warp a loop with nothing in it but the update itself.
     auto time_loop = [&](auto sp) {
@@ -560,16 +584,16 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 #define PF_STEP_SYNC() cta_sync()
 #endif
         for (; s + 1 < ks; s += 2) {
-            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s, true, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
             if (SP) probes(s);
             PF_STEP_SYNC();
-            if (SWAP) tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s + 1, ex, hy, dx, pb, pa, pe, ph, acub, rbe, rce, rcm);
-            else tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s + 1, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            if (SWAP) tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s + 1, s + 2 < ks, ex, hy, dx, pb, pa, pe, ph, acub, rbe, rce, rcm);
+            else tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s + 1, s + 2 < ks, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
             if (SP) probes(s + 1);
             PF_STEP_SYNC();
         }
         if (s < ks) {
-            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s, false, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
             if (SP) probes(s);
             PF_STEP_SYNC();
             swapped = SWAP;

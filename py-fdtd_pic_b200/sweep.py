@@ -59,108 +59,159 @@ class Member:
             self.scalars.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
 
 
+def _round32(x):
+    return (np.asarray(x, dtype=np.int64) + 31) // 32 * 32
+
+
+_GRID_DTYPE = np.dtype(nat.PfGrid)
+_SCALAR_KEYS = ("dt_over_dz", "eps0", "polA", "polB", "polC", "cub_a", "cub_b", "cub_c", "nl_den0", "nl_den1",
+                "cE0", "cE1", "cH0", "cH1", "c2_pml")
+
+
 class MemberBatch:
-    """Device-resident batch of members + the PfGrid array handed to pf_run_batch."""
+    """Device-resident batch of members + the PfGrid array handed to pf_run_batch.
+
+    Two ways in: a list of ``Member`` objects (each built by the per-member setup chain), or
+    ``MemberBatch.from_table`` with a ``sweep_setup.MemberTable`` -- the setup of the whole sweep vectorised over members,
+    with the CPML profiles and source tables written into the pinned upload buffer by one native call."""
 
     def __init__(self, members, mode, device=None, share_coef=None):
-        torch = nat.require_cuda()
-        self.torch = torch
-        self.members = members
-        self.mode = mode
-        self.mode_id = dev.MODE_ID[mode]
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         for m in members:
             m.set_mode(mode)
         M = len(members)
-        # ---- layout (doubles): [state of all members][coef+src of all members][probes of all members]
-        self.off_state, self.off_in, self.off_probe = [], [], []
-        cur = 0
-        for m in members:
-            Lp = (m.L + 31) // 32 * 32
-            self.off_state.append(cur)
-            cur += len(STATE_NAMES) * Lp
-        self.n_state = cur
-        share_coef = share_coef or list(range(M))      # member -> index of the member whose coef it reuses
-        self.share = share_coef
-        for i, m in enumerate(members):
-            Lp = (m.L + 31) // 32 * 32
-            Tp = (m.T + 31) // 32 * 32
-            self.off_in.append(cur)
-            cur += (len(COEF_NAMES) * Lp if share_coef[i] == i else 0) + 2 * Tp
-        self.n_in = cur - self.n_state
-        for m in members:
-            Tp = (m.T + 31) // 32 * 32
-            self.off_probe.append(cur)
-            cur += max(len(m.probe_idx), 1) * Tp
-        self.n_probe = cur - self.n_state - self.n_in
-        self.n_total = cur
-        self.pool = torch.empty(cur, dtype=torch.float64, device=self.device)
-        self.host_in = torch.zeros(self.n_in, dtype=torch.float64).pin_memory()
-        self.host_probe = torch.zeros(self.n_probe, dtype=torch.float64).pin_memory()
-        pidx = np.concatenate([np.asarray(m.probe_idx or [0], dtype=np.int32) for m in members])
-        self.pidx_off = np.concatenate([[0], np.cumsum([max(len(m.probe_idx), 1) for m in members])])
-        self.host_pidx = torch.from_numpy(pidx).pin_memory()
-        self.pidx = torch.empty(len(pidx), dtype=torch.int32, device=self.device)
-        self.grids = (nat.PfGrid * M)()
-        self.nsteps = (ctypes.c_int * M)(*[m.nsteps for m in members])
-        self._fill_host_inputs()
-        self._fill_descriptors()
-        self.scratch_bytes = nat.lib().pf_run_scratch_bytes(self.grids, M, nat.PF_ENGINE_TILE)
-        self.scratch = torch.empty(self.scratch_bytes, dtype=torch.uint8, device=self.device)
-        self.h2d_bytes = self.n_in * 8 + len(pidx) * 4
-        self.d2h_bytes = self.n_probe * 8
-        self.cell_steps = sum(m.L * m.nsteps for m in members)
-
-    # -- host staging -------------------------------------------------------------------------
-    def _coef_offset(self, i, name):
-        j = self.share[i]
-        Lp = (self.members[j].L + 31) // 32 * 32
-        return self.off_in[j] + COEF_NAMES.index(name) * Lp
-
-    def _src_offset(self, i, which):
-        m = self.members[i]
-        Lp = (m.L + 31) // 32 * 32
-        Tp = (m.T + 31) // 32 * 32
-        base = self.off_in[i] + (len(COEF_NAMES) * Lp if self.share[i] == i else 0)
-        return base + which * Tp
-
-    def _fill_host_inputs(self):
+        self.members = members
+        share = np.asarray(share_coef if share_coef is not None else np.arange(M), dtype=np.int64)
+        n_probes = np.array([len(m.probe_idx) for m in members], dtype=np.int64)
+        pidx = np.concatenate([np.asarray(m.probe_idx or [0], dtype=np.int32) for m in members]) if M else np.zeros(0, np.int32)
+        self._setup(mode, device, L=np.array([m.L for m in members], dtype=np.int64),
+                    T=np.array([m.T for m in members], dtype=np.int64),
+                    nsteps=np.array([m.nsteps for m in members], dtype=np.int64), n_probes=n_probes, pidx=pidx, share=share,
+                    n_src=np.array([min(len(m.srcE), len(m.srcH)) for m in members], dtype=np.int64))
+        # host staging: per member (the per-member chain produced the arrays)
         hv = self.host_in.numpy()
         o0 = self.n_state
-        for i, m in enumerate(self.members):
-            if self.share[i] == i:
-                for name in COEF_NAMES:
-                    o = self._coef_offset(i, name) - o0
+        for i, m in enumerate(members):
+            if share[i] == i:
+                for a, name in enumerate(COEF_NAMES):
+                    o = int(self.off_coef[i] + a * self.Lp[i]) - o0
                     hv[o:o + m.L] = m.coef[name]
-            o = self._src_offset(i, 0) - o0
+            o = int(self.off_src[i]) - o0
             hv[o:o + len(m.srcE)] = m.srcE
-            o = self._src_offset(i, 1) - o0
+            o = int(self.off_src[i] + self.Tp[i]) - o0
             hv[o:o + len(m.srcH)] = m.srcH
+        scal = {k: np.array([float(m.scalars[k]) for m in members]) for k in _SCALAR_KEYS}
+        geo = {k: np.array([m.scalars[k] for m in members], dtype=np.int64) for k in ("pw", "mf", "mr", "nzsrc")}
+        self._fill_descriptors(geo, scal, np.array([m.flags for m in members], dtype=np.int64))
 
-    def _fill_descriptors(self):
+    @classmethod
+    def from_table(cls, table, mode, device=None, T_alloc=None, threads=0, pinned_tag=None):
+        """Batch of every row of a ``sweep_setup.MemberTable``.  T_alloc (optional, >= nsteps): rows of the source / probe
+        tables to allocate instead of the member's full timeSteps (benchmarks of truncated passes)."""
+        from . import sweep_setup
+        self = cls.__new__(cls)
+        self.members = None
+        self.table = table
+        T = table.T if T_alloc is None else np.full(table.n, int(T_alloc), dtype=np.int64)
+        if np.any(T < table.nsteps):
+            raise ValueError("MemberBatch.from_table: T_alloc is shorter than nsteps")
+        n_probes = np.full(table.n, table.probes.shape[1], dtype=np.int64)
+        self._setup(mode, device, L=table.L, T=T, nsteps=table.nsteps, n_probes=n_probes,
+                    pidx=table.probes.astype(np.int32).reshape(-1), share=table.share, n_src=T, pinned_tag=pinned_tag)
+        own = table.share == np.arange(table.n)
+        o0 = self.n_state
+        sweep_setup.build_inputs(table, self.host_in.numpy(), np.where(own, self.off_coef - o0, -1),
+                                 np.where(own, self.off_coef + self.Lp - o0, -1),
+                                 np.where(own, self.off_coef + 2 * self.Lp - o0, -1), self.off_src - o0,
+                                 self.off_src + self.Tp - o0, T, threads=threads)
+        self._fill_descriptors({k: getattr(table, k) for k in ("pw", "mf", "mr", "nzsrc")},
+                               {k: getattr(table, k) for k in _SCALAR_KEYS}, table.flags)
+        return self
+
+    # -- layout + descriptors, vectorised over members --------------------------------------------
+    def _setup(self, mode, device, *, L, T, nsteps, n_probes, pidx, share, n_src, pinned_tag=None):
+        torch = nat.require_cuda()
+        self.torch = torch
+        self.mode = mode
+        self.mode_id = dev.MODE_ID[mode]
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        M = len(L)
+        self.M = M
+        self.L, self.T, self.nsteps_arr, self.n_probes, self.n_src = (np.asarray(x, dtype=np.int64)
+                                                                       for x in (L, T, nsteps, n_probes, n_src))
+        self.share = np.asarray(share, dtype=np.int64)
+        self.Lp, self.Tp = _round32(self.L), _round32(self.T)
+        rows = np.maximum(self.n_probes, 1)
+        # layout (doubles): [state of all members][coef (owners only) + src of all members][probes of all members]
+        sz_state = len(STATE_NAMES) * self.Lp
+        self.off_state = np.concatenate([[0], np.cumsum(sz_state)])[:-1]
+        self.n_state = int(sz_state.sum())
+        own = self.share == np.arange(M)
+        sz_in = np.where(own, len(COEF_NAMES) * self.Lp, 0) + 2 * self.Tp
+        off_in = self.n_state + np.concatenate([[0], np.cumsum(sz_in)])[:-1]
+        self.n_in = int(sz_in.sum())
+        self.off_coef = off_in[self.share]                       # a sharing member points at its owner's profiles
+        self.off_src = off_in + np.where(own, len(COEF_NAMES) * self.Lp, 0)
+        sz_probe = rows * self.Tp
+        self.off_probe = self.n_state + self.n_in + np.concatenate([[0], np.cumsum(sz_probe)])[:-1]
+        self.n_probe = int(sz_probe.sum())
+        self.n_total = self.n_state + self.n_in + self.n_probe
+        self.pool = torch.empty(self.n_total, dtype=torch.float64, device=self.device)
+        # upload staging: an own pinned buffer, or (pinned_tag) a slot of the grow-only cache in _device -- pinning hundreds of
+        # megabytes costs more than filling them, so a chunked sweep reuses two slots; the trace staging buffer is only
+        # allocated if traces are ever downloaded (a device-side reflection extraction never does)
+        self.host_in = (torch.zeros(self.n_in, dtype=torch.float64).pin_memory() if pinned_tag is None
+                        else dev.pinned_buffer(self.n_in, tag=pinned_tag))
+        self._host_probe = None
+        self.pidx_off = np.concatenate([[0], np.cumsum(rows)])
+        self.host_pidx = torch.from_numpy(np.ascontiguousarray(pidx, dtype=np.int32)).pin_memory()
+        self.pidx = torch.empty(len(pidx), dtype=torch.int32, device=self.device)
+        self.grids = (nat.PfGrid * M)()
+        self.nsteps = (ctypes.c_int * M)(*[int(v) for v in self.nsteps_arr])
+        self.h2d_bytes = self.n_in * 8 + len(pidx) * 4
+        self.d2h_bytes = self.n_probe * 8
+        self.cell_steps = int((self.L * self.nsteps_arr).sum())
+
+    def _fill_descriptors(self, geo, scal, flags):
+        M = self.M
+        g = np.frombuffer(self.grids, dtype=_GRID_DTYPE, count=M) if M else np.zeros(0, dtype=_GRID_DTYPE)
         base = self.pool.data_ptr()
-        for i, m in enumerate(self.members):
-            g = self.grids[i]
-            Lp = (m.L + 31) // 32 * 32
-            Tp = (m.T + 31) // 32 * 32
-            s = m.scalars
-            g.L, g.pw, g.mf, g.mr, g.nzsrc = m.L, s["pw"], s["mf"], s["mr"], s["nzsrc"]
-            g.flags = m.flags
-            g.n_probes, g.probe_stride = len(m.probe_idx), Tp
-            g.n_src = min(len(m.srcE), len(m.srcH))
-            g.z0, g.Lg = 0, m.L
-            for k in ("dt_over_dz", "eps0", "polA", "polB", "polC", "cub_a", "cub_b", "cub_c", "nl_den0", "nl_den1",
-                      "cE0", "cE1", "cH0", "cH1", "c2_pml"):
-                setattr(g, k, float(s[k]))
-            for a, name in enumerate(STATE_NAMES):
-                setattr(g, name, base + 8 * (self.off_state[i] + a * Lp))
-            for name in COEF_NAMES:
-                setattr(g, name, base + 8 * self._coef_offset(i, name))
-            g.bmY = g.beX
-            g.srcE = base + 8 * self._src_offset(i, 0)
-            g.srcH = base + 8 * self._src_offset(i, 1)
-            g.probe_idx = self.pidx.data_ptr() + 4 * int(self.pidx_off[i])
-            g.probe_out = base + 8 * self.off_probe[i]
+        g["L"], g["pw"], g["mf"], g["mr"], g["nzsrc"] = self.L, geo["pw"], geo["mf"], geo["mr"], geo["nzsrc"]
+        g["flags"] = flags
+        g["n_probes"], g["probe_stride"], g["n_src"] = self.n_probes, self.Tp, self.n_src
+        g["z0"], g["Lg"] = 0, self.L
+        for k in _SCALAR_KEYS:
+            g[k] = scal[k]
+        for a, name in enumerate(STATE_NAMES):
+            g[name] = base + 8 * (self.off_state + a * self.Lp)
+        Lp_owner = self.Lp[self.share]
+        for a, name in enumerate(COEF_NAMES):
+            g[name] = base + 8 * (self.off_coef + a * Lp_owner)
+        g["bmY"] = g["beX"]
+        g["srcE"] = base + 8 * self.off_src
+        g["srcH"] = base + 8 * (self.off_src + self.Tp)
+        g["probe_idx"] = self.pidx.data_ptr() + 4 * self.pidx_off[:-1]
+        g["probe_out"] = base + 8 * self.off_probe
+        self.scratch_bytes = nat.lib().pf_run_scratch_bytes(self.grids, M, nat.PF_ENGINE_TILE)
+        self.scratch = self.torch.empty(self.scratch_bytes, dtype=self.torch.uint8, device=self.device)
+
+    @property
+    def host_probe(self):
+        if self._host_probe is None:
+            self._host_probe = self.torch.zeros(self.n_probe, dtype=self.torch.float64).pin_memory()
+        return self._host_probe
+
+    def set_pass(self, table):
+        """Re-point the descriptors at another pass of the same members (same grids and inputs; other update scalars and
+        probe cells) -- e.g. pass 0 / pass 1 of the two-pass Lorentz integrator."""
+        if table.n != self.M or np.any(table.L != self.L):
+            raise ValueError("set_pass: the table describes other members")
+        self.pidx = self.torch.as_tensor(table.probes.astype(np.int32).reshape(-1), device=self.device)
+        g = np.frombuffer(self.grids, dtype=_GRID_DTYPE, count=self.M)
+        for k in _SCALAR_KEYS:
+            g[k] = getattr(table, k)
+        g["flags"] = table.flags
+        g["probe_idx"] = self.pidx.data_ptr() + 4 * self.pidx_off[:-1]
+        self.table = table
 
     # -- device side --------------------------------------------------------------------------
     def upload(self):
@@ -190,34 +241,35 @@ class MemberBatch:
         self.state_template = torch.rand(self.n_state, dtype=torch.float64, device=self.device, generator=gen) * 2 - 1
         scale = torch.tensor([self.STATE_SCALE[name] for name in STATE_NAMES], dtype=torch.float64,
                              device=self.device)[:, None]
-        for i, m in enumerate(self.members):      # a member's state arrays are one contiguous [8, Lp] block
-            Lp = (m.L + 31) // 32 * 32
-            o = self.off_state[i]
+        for i in range(self.M):      # a member's state arrays are one contiguous [8, Lp] block
+            Lp = int(self.Lp[i])
+            o = int(self.off_state[i])
             self.state_template[o:o + len(STATE_NAMES) * Lp].view(len(STATE_NAMES), Lp).mul_(scale)
         return self.state_template
 
     def run(self, do_pol, n0=0, k_block=0):
-        nat.check(nat.lib().pf_run_batch(self.grids, len(self.members), self.mode_id, int(do_pol), int(n0),
+        nat.check(nat.lib().pf_run_batch(self.grids, self.M, self.mode_id, int(do_pol), int(n0),
                                          self.nsteps, int(k_block), self.scratch.data_ptr(), self.scratch_bytes,
                                          nat.current_stream_ptr()), "pf_run_batch")
+
+    def _unpack_probes(self, hv):
+        rows = np.maximum(self.n_probes, 1)
+        if self.M and len({(int(r), int(p), int(t), int(T)) for r, p, t, T in zip(rows, self.n_probes, self.Tp, self.T)}) == 1:
+            # uniform batch (the sweep case): one strided copy instead of one per member
+            return list(hv.reshape(self.M, int(rows[0]), int(self.Tp[0]))[:, :int(self.n_probes[0]), :int(self.T[0])].copy())
+        out = []
+        o0 = self.n_state + self.n_in
+        for i in range(self.M):
+            Tp, n_p, r = int(self.Tp[i]), int(self.n_probes[i]), int(rows[i])
+            a = hv[int(self.off_probe[i]) - o0: int(self.off_probe[i]) - o0 + r * Tp]
+            out.append(a.reshape(r, Tp)[:n_p, : int(self.T[i])].copy())
+        return out
 
     def download_probes(self):
         """D2H of all probe traces (one copy) -> list of arrays [n_probes, T] per member."""
         self.host_probe.copy_(self.pool[self.n_state + self.n_in:], non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
-        hv = self.host_probe.numpy()
-        shapes = {(max(len(m.probe_idx), 1), len(m.probe_idx), (m.T + 31) // 32 * 32, m.T) for m in self.members}
-        if len(shapes) == 1:        # uniform batch (the sweep case): one strided copy instead of one per member
-            rows, n_p, Tp, T = next(iter(shapes))
-            return list(hv.reshape(len(self.members), rows, Tp)[:, :n_p, :T].copy())
-        out = []
-        o0 = self.n_state + self.n_in
-        for i, m in enumerate(self.members):
-            Tp = (m.T + 31) // 32 * 32
-            n_p = len(m.probe_idx)
-            a = hv[self.off_probe[i] - o0: self.off_probe[i] - o0 + max(n_p, 1) * Tp]
-            out.append(a.reshape(max(n_p, 1), Tp)[:n_p, : m.T].copy())
-        return out
+        return self._unpack_probes(self.host_probe.numpy())
 
     def download_probes_async(self):
         """Stream-ordered D2H of all probe traces into this batch's pinned buffer; returns a function that
@@ -229,55 +281,52 @@ class MemberBatch:
 
         def finish():
             done.synchronize()
-            hv = self.host_probe.numpy()
-            shapes = {(max(len(m.probe_idx), 1), len(m.probe_idx), (m.T + 31) // 32 * 32, m.T) for m in self.members}
-            if len(shapes) == 1:
-                rows, n_p, Tp, T = next(iter(shapes))
-                return list(hv.reshape(len(self.members), rows, Tp)[:, :n_p, :T].copy())
-            o0 = self.n_state + self.n_in
-            out = []
-            for i, m in enumerate(self.members):
-                Tp = (m.T + 31) // 32 * 32
-                n_p = len(m.probe_idx)
-                a = hv[self.off_probe[i] - o0: self.off_probe[i] - o0 + max(n_p, 1) * Tp]
-                out.append(a.reshape(max(n_p, 1), Tp)[:n_p, : m.T].copy())
-            return out
+            return self._unpack_probes(self.host_probe.numpy())
         return finish
 
     def download_probe(self, i):
         """D2H of the probe traces of member i only -> array [n_probes, T]."""
-        m = self.members[i]
-        Tp = (m.T + 31) // 32 * 32
-        n_p = len(m.probe_idx)
-        a = self.pool[self.off_probe[i]: self.off_probe[i] + max(n_p, 1) * Tp].cpu().numpy()
-        return a.reshape(max(n_p, 1), Tp)[:n_p, : m.T].copy()
+        Tp, n_p = int(self.Tp[i]), int(self.n_probes[i])
+        o = int(self.off_probe[i])
+        a = self.pool[o: o + max(n_p, 1) * Tp].cpu().numpy()
+        return a.reshape(max(n_p, 1), Tp)[:n_p, : int(self.T[i])].copy()
 
-    def probe_peaks(self, probe=0, keep_from=None, keep_to=None):
+    def probe_rows(self, idxs, probe, T):
+        """Device tensor [len(idxs), T] of probe row ``probe`` of the given members (which share T): a strided view of
+        the pool when the members are evenly spaced (the uniform sweep), a gather otherwise."""
+        torch = self.torch
+        Tp = (T + 31) // 32 * 32
+        offs = self.off_probe[np.asarray(idxs)] + probe * Tp
+        if len(offs) > 1 and np.all(np.diff(offs) == offs[1] - offs[0]):
+            return torch.as_strided(self.pool, (len(offs), T), (int(offs[1] - offs[0]), 1), int(offs[0]))
+        return torch.stack([self.pool[int(o): int(o) + T] for o in offs])
+
+    def probe_peaks(self, probe=0, keep_from=None, keep_to=None, on_device=False):
         """RefTester's scalar of probe ``probe`` of every member, computed on the device (batched FFT per
         distinct timeSteps; nothing but the result, one double per member, is copied to the host).
         keep_from / keep_to: per-member first / last sample index of the read window (others are zeroed)."""
         from . import TransformHandler as transH
         torch = self.torch
-        M = len(self.members)
         kf = None if keep_from is None else np.asarray(keep_from, dtype=np.int64)
         kt = None if keep_to is None else np.asarray(keep_to, dtype=np.int64)
-        groups = {}
-        for i, m in enumerate(self.members):
-            groups.setdefault(m.T, []).append(i)
-        out = torch.empty(M, dtype=torch.float64, device=self.device)
-        for T, idxs in groups.items():
-            Tp = (T + 31) // 32 * 32
-            rows = torch.stack([self.pool[self.off_probe[i] + probe * Tp: self.off_probe[i] + probe * Tp + T] for i in idxs])
-            val, _ = transH.ref_tester_batch(rows, T, None if kf is None else kf[idxs], None if kt is None else kt[idxs])
-            out[torch.as_tensor(idxs, device=self.device)] = val
+        out = torch.empty(self.M, dtype=torch.float64, device=self.device)
+        bins = torch.empty(self.M, dtype=torch.int64, device=self.device)
+        for T in np.unique(self.T):
+            idxs = np.flatnonzero(self.T == T)
+            rows = self.probe_rows(idxs, probe, int(T))
+            val, idx = transH.ref_tester_batch(rows, int(T), None if kf is None else kf[idxs], None if kt is None else kt[idxs],
+                                               check=not on_device)
+            sel = torch.as_tensor(idxs, device=self.device)
+            out[sel] = val
+            bins[sel] = idx
+        if on_device:        # no host synchronisation: (values, peak bins) stay on the device; the caller checks bins != 0
+            return out, bins
         return out.cpu().numpy()
 
     def state(self, i, name):
         """Device -> host copy of one state array of member i (tests / final fields)."""
-        m = self.members[i]
-        Lp = (m.L + 31) // 32 * 32
-        o = self.off_state[i] + STATE_NAMES.index(name) * Lp
-        return self.pool[o:o + m.L].cpu().numpy()
+        o = int(self.off_state[i] + STATE_NAMES.index(name) * self.Lp[i])
+        return self.pool[o:o + int(self.L[i])].cpu().numpy()
 
 
 class BatchPipeline:
@@ -522,3 +571,74 @@ def frequency_sweep(V, P, domainSize, lowLimTim, highLimTim, Low=3e9, Interval=1
     Pi.freq_in = Pi.freq_in + Interval          # the reference leaves the last P advanced (:559)
     Exs, Hys = srcs.get(points - 1, (None, None))
     return freqs, measured, analytical, (Vi, Pi, CVi, CPi, Exs, Hys)
+
+
+def reflection_sweep(freqs, domainSize, lowLimTim, highLimTim, *, amps=1.0, periods=1.0, tfsf=True, chunk=256, rank=0,
+                     world_size=1, k_block=0, fma=False, fp32=False, nsteps=None, threads=0):
+    """Reflection coefficient of the Lorentz half-space at every frequency of ``freqs``: what the reference's sweep
+    (MasterController.LoopedSim, :543-563) computes per point -- ``Controller`` (two passes of IntegratorLinLor1D) and
+    ``results(RefCo=True)`` -- for grids ``envSetup(f, domainSize, lowLimTim, highLimTim, LorMed=True)``.
+
+    Everything per member is batched: the host setup is vectorised (sweep_setup), the CPML profiles and source tables are
+    built natively straight into pinned memory, all members of a chunk advance together (pf_run_batch), the reflection
+    figure is extracted on the device (batched FFT).  Chunks are pipelined: while the GPU steps chunk i the host builds the
+    inputs of chunk i+1.  Members are dealt round-robin over ranks (member % world_size == rank); no collective.
+
+    Returns a dict: ``index`` (positions in ``freqs`` this rank owns), ``freq``, ``measured`` (R per owned member),
+    ``analytical`` (BaseFDTD11.AnalyticalReflectionE with the medium as Controller leaves it), ``cell_steps`` and
+    ``timing`` (seconds: vectorised setup, native input building, total wall)."""
+    import time
+    from . import sweep_setup
+    torch = nat.require_cuda()
+    t_start = time.perf_counter()
+    freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+    tables = sweep_setup.lorentz_sweep_tables(freqs, amps, domainSize, lowLimTim, highLimTim, periods=periods, tfsf=tfsf,
+                                              nsteps=nsteps, fma=fma, fp32=fp32)
+    t_setup = time.perf_counter() - t_start
+    mine = np.arange(rank, len(freqs), world_size)
+    # analytical figure, medium as Controller leaves it (twice-corrected plasma frequency)
+    wp = tables[1].wp[mine]
+    med = sweep_setup.default_medium(1)
+    w0, gam = float(med["w0"][0]), float(med["gam"][0])
+    analytical = np.empty(len(mine))
+    for j in range(len(mine)):      # BaseFDTD11.AnalyticalReflectionE, Python-float / Python-complex arithmetic as there
+        wpj, wj = float(wp[j]), 2 * np.pi * float(freqs[mine[j]])
+        eps = 1 + (wpj * wpj) / (w0 * w0 - (wj * wj) + 1j * gam * wj)
+        n2 = np.real(np.sqrt(eps))
+        analytical[j] = abs((n2 - 1) / (1 + n2))
+    t_build = 0.0
+    out_R, out_bins, uploaded, cell_steps, keep = [], [], {}, 0, []
+    for c, lo in enumerate(range(0, len(mine), chunk)):
+        idx = mine[lo:lo + chunk]
+        t0c, t1c = tables[0].select(idx), tables[1].select(idx)
+        slot = f"sweep_in_{c % 2}"
+        if slot in uploaded:
+            uploaded[slot].synchronize()           # the H2D copy that last read this pinned slot has finished
+        tb = time.perf_counter()
+        batch = MemberBatch.from_table(t0c, "lorentz", pinned_tag=slot, threads=threads)
+        t_build += time.perf_counter() - tb
+        batch.upload()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        uploaded[slot] = ev
+        T = batch.T
+        batch.reset_state()
+        batch.run(do_pol=False, k_block=k_block)
+        p0, b0 = batch.probe_peaks(keep_to=np.trunc(T * 0.7).astype(np.int64), on_device=True)
+        batch.set_pass(t1c)
+        batch.reset_state()
+        batch.run(do_pol=True, k_block=k_block)
+        p1, b1 = batch.probe_peaks(keep_from=np.trunc(T * 0.05).astype(np.int64), on_device=True)
+        out_R.append(p1 / p0)
+        out_bins.append(torch.minimum(b0, b1))
+        cell_steps += 2 * batch.cell_steps
+        keep.append(batch)                          # descriptors / pools stay alive until the stream has drained
+    if out_R:
+        R = torch.cat(out_R).cpu().numpy()
+        if bool((torch.cat(out_bins) == 0).any()):
+            raise ValueError("Could not find non-DC freq")
+    else:
+        R = np.zeros(0)
+    del keep
+    return dict(index=mine, freq=freqs[mine], measured=R, analytical=analytical, cell_steps=cell_steps,
+                timing=dict(setup_s=t_setup, build_inputs_s=t_build, total_s=time.perf_counter() - t_start))
