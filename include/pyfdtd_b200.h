@@ -232,11 +232,17 @@ int pf_run_block(const PfGrid *src, const PfGrid *dst, int n_grids, int mode, in
                  int block_flags, void *scratch, size_t scratch_bytes, void *stream);
 size_t pf_run_block_scratch_bytes(const PfGrid *grids, int n_grids, int halo);
 
-/* Per-launch timing of the tile kernel (the dominant kernel): while enabled, every k_tile launch is
- * bracketed by CUDA events on its own stream; pf_profile_collect() waits for them, returns the summed
- * kernel time [ms] and the number of launches, and clears the list.                              */
+/* Per-launch timing of the dominant kernels (k_tile<...>, and the PIC step's k_pic_count / k_pic_move): while enabled,
+ * every such launch is bracketed by CUDA events on its own stream.  pf_profile_collect() waits for them, returns the
+ * summed kernel time [ms] and the number of launches, and clears the list; pf_profile_report() does the same but
+ * returns the figures per kernel name as text, "name|launches|ms;name|launches|ms;...".            */
 int pf_profile_enable(int on);
 int pf_profile_collect(double *ms_total, int *n_launches);
+int pf_profile_report(char *report, size_t report_bytes);
+/* What the FP64 pipe of the current device delivers, measured now (a few ms of GPU time): separately rounded
+ * DMUL + DADD instructions per second over all SMs (the roofline of the exact-arithmetic kernels) and DFMA per
+ * second (the contracted modes).  Either pointer may be NULL.                                           */
+int pf_probe_fp64(double *dmul_dadd_instr_per_s, double *dfma_per_s, void *stream);
 
 /* tile-engine introspection (bench / tests): tile width in cells, max k, threads per CTA       */
 int pf_tile_config(int *tile_cells, int *k_max, int *threads);

@@ -102,6 +102,8 @@ SYMBOLS = {
     "pf_run_block_scratch_bytes": (c_size_t, [_G, c_int, c_int]),
     "pf_profile_enable": (c_int, [c_int]),
     "pf_profile_collect": (c_int, [POINTER(c_double), POINTER(c_int)]),
+    "pf_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
+    "pf_probe_fp64": (c_int, [POINTER(c_double), POINTER(c_double), c_void_p]),
     "pf_tile_config": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "pf_halo_pack": (ctypes.c_longlong, [_G, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pf_halo_unpack": (ctypes.c_longlong, [_G, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -162,6 +164,25 @@ def require_cuda():
 def current_stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def profile_report():
+    """{kernel name: (launches, total ms)} of the launches timed since pf_profile_enable(1) / the last report."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().pf_profile_report(buf, len(buf)), "pf_profile_report")
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if item:
+            name, n, ms = item.rsplit("|", 2)
+            out[name] = (int(n), float(ms))
+    return out
+
+
+def probe_fp64():
+    """(separately rounded DMUL+DADD instructions/s, DFMA/s) of the current device, measured now."""
+    a, b = c_double(), c_double()
+    check(lib().pf_probe_fp64(a, b, current_stream_ptr()), "pf_probe_fp64")
+    return a.value, b.value
 
 
 def device_info():

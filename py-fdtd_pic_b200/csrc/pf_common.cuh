@@ -18,6 +18,16 @@ extern std::atomic<unsigned long long> g_launches; // pf_launch_count()
 int set_err(int code, const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 
+// Optional per-launch timing (pf_profile_enable / pf_profile_report): while enabled, a ProfScope brackets a kernel launch
+// with CUDA events on the launch's own stream and files them under the kernel's name.  Defined in pf_probe.cu.
+struct ProfScope {
+    cudaStream_t st;
+    const char *name;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(cudaStream_t s, const char *kernel_name);
+    ~ProfScope();
+};
+
 #define PF_CUDA(call)                                        \
     do {                                                     \
         int _rc = ::pf::check_cuda((call), #call);           \

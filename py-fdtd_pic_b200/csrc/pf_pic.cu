@@ -502,7 +502,10 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
     const int S = pic_sub_warps(p);
     int *tot = (int *)(s + pl.off_tot);
     unsigned wblocks = (unsigned)(((long long)p->L * S * 32 + PIC_THREADS - 1) / PIC_THREADS);
-    k_pic_count<<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, err, S);
+    {
+        ProfScope prof(st, "k_pic_count");
+        k_pic_count<<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, err, S);
+    }
     PF_LAUNCH_CHECK("k_pic_count");
     k_pic_cell_totals<<<(p->L + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(counts, p->L, S, tot);
     PF_LAUNCH_CHECK("k_pic_cell_totals");
@@ -510,12 +513,18 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
     PF_LAUNCH_CHECK("k_pic_scan");
     if (deposit) {
         double *part = (double *)(s + pl.off_part);
-        k_pic_move<true><<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S, part);
+        {
+            ProfScope prof(st, "k_pic_move<deposit>");
+            k_pic_move<true><<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S, part);
+        }
         PF_LAUNCH_CHECK("k_pic_move");
         k_pic_flush4<<<(p->L + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(*p, part, S);
         PF_LAUNCH_CHECK("k_pic_flush4");
     } else {
-        k_pic_move<false><<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S, nullptr);
+        {
+            ProfScope prof(st, "k_pic_move");
+            k_pic_move<false><<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S, nullptr);
+        }
         PF_LAUNCH_CHECK("k_pic_move");
     }
     return PF_OK;

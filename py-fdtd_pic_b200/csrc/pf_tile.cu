@@ -927,36 +927,27 @@ static TilePlan tile_plan(const PfGrid *grids, int n, int mode, int halo)
     return p;
 }
 
-// ---- optional per-launch timing of the dominant kernel (bench.py's roofline numerator) ----------
-static std::atomic<bool> g_prof_on{false};
-static std::mutex g_prof_mutex;   // guards g_prof_events (launches may come from one host thread per GPU)
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
-
-struct ProfScope {
-    cudaStream_t st;
-    cudaEvent_t a = nullptr, b = nullptr;
-    explicit ProfScope(cudaStream_t s) : st(s)
-    {
-        if (g_prof_on && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
-    }
-    ~ProfScope()
-    {
-        if (a && b) {
-            cudaEventRecord(b, st);
-            std::lock_guard<std::mutex> lk(g_prof_mutex);
-            g_prof_events.emplace_back(a, b);
-        }
-    }
-};
-
 enum { ARITH_EXACT = 0, ARITH_FUSED = 1, ARITH_FP32 = 2, ARITH_NEWTON = 3 };
+
+template <int MODE, bool POL, int C, class A>
+static const char *tile_kernel_name()
+{
+    static char name[64] = "";
+    if (!name[0]) {
+        const char *mode = MODE == PF_FREE ? "FREE" : MODE == PF_LORENTZ ? "LORENTZ" : MODE == PF_NL ? "NL" : "LORENTZ_NL";
+        const char *ar = std::is_same<A, Exact>::value ? "Exact" : std::is_same<A, Fused>::value ? "Fused"
+                         : std::is_same<A, Fast32>::value ? "Fast32" : "ExactNewton";
+        snprintf(name, sizeof(name), "k_tile<%s,POL=%d,C=%d,%s>", mode, (int)POL, C, ar);
+    }
+    return name;
+}
 
 template <int MODE, bool POL, int C, class A>
 static int launch_tile_a(int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
                          int n0, int ks, int halo, cudaStream_t st)
 {
     const size_t sm = TileSmem<MODE, C, typename A::real>::bytes;
-    ProfScope prof(st);
+    ProfScope prof(st, tile_kernel_name<MODE, POL, C, A>());
     static std::atomic<unsigned long long> attr_set{0};   // the attribute is per device; bit = device ordinal (idempotent, race-free)
     int dev = 0;
     PF_CUDA(cudaGetDevice(&dev));
@@ -1241,32 +1232,6 @@ size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine)
     if (engine != PF_ENGINE_TILE || !grids || n_grids <= 0) return 0;
     // sized for the largest state set (Lorentz) and the smallest tile interior (largest tile count)
     return tile_plan(grids, n_grids, PF_LORENTZ, TILE_KMAX).total;
-}
-
-int pf_profile_enable(int on)
-{
-    g_prof_on = on != 0;
-    return PF_OK;
-}
-
-int pf_profile_collect(double *ms_total, int *n_launches)
-{
-    double tot = 0.0;
-    int n = 0;
-    std::lock_guard<std::mutex> lk(g_prof_mutex);
-    for (auto &ev : g_prof_events) {
-        float ms = 0.f;
-        PF_CUDA(cudaEventSynchronize(ev.second));
-        PF_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
-        tot += ms;
-        ++n;
-        cudaEventDestroy(ev.first);
-        cudaEventDestroy(ev.second);
-    }
-    g_prof_events.clear();
-    if (ms_total) *ms_total = tot;
-    if (n_launches) *n_launches = n;
-    return PF_OK;
 }
 
 int pf_run_block(const PfGrid *src, const PfGrid *dst, int n_grids, int mode, int do_pol, int n0, int ksteps, int halo,

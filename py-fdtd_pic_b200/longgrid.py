@@ -237,6 +237,8 @@ class LongGrid:
         self.cur = 0
         self.n_done = 0
         self._tables_built = False    # the tile tables in self.scratch were written by this object's last pf_run_block
+        self.time_exchange = False    # True: every ghost exchange is bracketed by CUDA events (exchange_ms())
+        self._xch_events = []
         self.halo_bufs = {}
         self.cells_owned = sum(p["hi"] - p["lo"] for p in self.mine)
         self._local_of = {p["index"]: i for i, p in enumerate(self.mine)}
@@ -279,7 +281,14 @@ class LongGrid:
         while done < nsteps:
             ks = min(self.k, nsteps - done)
             if len(self.pieces) > 1:
-                self.exchange()
+                if self.time_exchange:
+                    ev = (self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
+                    self.exchange()
+                    ev[1].record()
+                    self._xch_events.append(ev)
+                else:
+                    self.exchange()
             # the tables hold buffer set 0 as `src`; this object owns the scratch, so after the first call they stay valid
             bflags = 0
             if self._tables_built:
@@ -292,6 +301,14 @@ class LongGrid:
             self.cur ^= 1
             self.n_done += ks
             done += ks
+
+    def exchange_ms(self):
+        """Summed device time [ms] of the ghost exchanges timed since time_exchange was switched on (pack kernels,
+        point-to-point messages, unpack kernels); clears the list."""
+        self.torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self._xch_events)
+        self._xch_events = []
+        return float(ms)
 
     def gather_owned(self, name):
         """Owned cells of one state array of this rank, concatenated in global order (host numpy)."""

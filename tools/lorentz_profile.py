@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A few launches of the bench's Lorentz sweep batch in one arithmetic mode, for ncu captures of k_tile.
-Usage: python tools/lorentz_profile.py [exact|fma|fp32] [members]"""
+Usage: python tools/lorentz_profile.py [exact|fma|fp32] [members] [steps]"""
 import os
 import sys
 
@@ -12,9 +12,8 @@ from pyfdtd_b200 import Solver_Engine as SE  # noqa: E402
 
 variant = sys.argv[1] if len(sys.argv) > 1 else "exact"
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
-SE.USE_FMA, SE.USE_FP32 = variant == "fma", variant == "fp32"
-wl = bench.ProductWorkload(M, 128, 64)
-b = wl.batch
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+b, table = bench.lorentz_sweep_batch(M, S, 64, fma=variant == "fma", fp32=variant == "fp32")
 b.upload()
 b.randomize_state(seed=1234)
 
@@ -24,5 +23,5 @@ def step():
     b.run(do_pol=True)
 
 
-sec = bench._time_cuda(torch, step, 2)
-print({"variant": variant, "members": M, "Gcell_updates_per_s": wl.cell_steps / sec / 1e9})
+sec = bench.time_cuda(torch, step, 2)
+print({"variant": variant, "members": M, "steps": S, "Gcell_updates_per_s": b.cell_steps / sec / 1e9})

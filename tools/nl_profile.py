@@ -12,10 +12,9 @@ import bench  # noqa: E402
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 variant = sys.argv[3] if len(sys.argv) > 3 else "closed"      # closed | newton | fp32
-from pyfdtd_b200 import Solver_Engine as SE  # noqa: E402
-SE.CUBIC = "newton" if variant == "newton" else "closed"
-SE.USE_FP32 = variant == "fp32"
-batch, members = bench.build_nl_batch(M, S)
+batch, table = bench.nl_sweep_batch(M, S, newton=variant == "newton", fp32=variant == "fp32")
+batch.upload()
+batch.randomize_state()
 
 
 def step():
@@ -23,6 +22,6 @@ def step():
     batch.run(do_pol=False)
 
 
-sec = bench._time_cuda(torch, step, 2)
-slab = sum(m.scalars["mr"] - m.scalars["mf"] for m in members)
+sec = bench.time_cuda(torch, step, 2)
+slab = int((table.mr - table.mf).sum())
 print({"variant": variant, "members": M, "steps": S, "Gcell_updates_per_s": batch.cell_steps / sec / 1e9, "cubic_solves_per_s": slab * S / sec})
