@@ -119,7 +119,11 @@ typedef struct PfGrid {
     double c2_pml;              /* C2 on the CPML ranges (delT/mu0)                              */
     /* state (read and written) */
     double *Ex, *Hy, *Dx, *P, *Pprev, *psiE, *psiH, *Acubic;
-    /* coefficients (read only); Jx may be NULL (= 0, the PIC current slot, BaseFDTD11.py:667)   */
+    /* coefficients (read only); Jx may be NULL (= 0): the PIC current slot, in units of J*dz.  ADE_ExUpdate subtracts it
+     * (BaseFDTD11.py:667: Ex += (Hy[nz]-Hy[nz-1]-Jx[nz])*UpExMat*den).  Inside the slab [mf, mr) the reference's loops
+     * overwrite Ex from Dx (ADE_ExCreate / NonLinExUpdate), so there the same bracket enters ADE_DxUpdate instead:
+     * Dx += (Hy[nz]-Hy[nz-1]-Jx[nz])*dt/dz*den (dD/dt = curl H - J) -- builder-defined, the reference has no particles;
+     * with Jx NULL or 0 both updates are the reference's bit for bit.                                                */
     const double *Jx, *UpExMat, *denE, *UpHySelf, *UpHyMat, *denH;
     const double *beX, *ceX, *Cb, *bmY, *cmY, *C2;
     /* per-step source terms, indexed by absolute step n:

@@ -98,10 +98,16 @@ void orc_source(OrcGrid *g, int n)
 }
 
 /* BaseFDTD11.py:750-760  ADE_DxUpdate */
+/* Current slot in material cells -- BUILDER-DEFINED (parity unpinned by the reference): the reference's only PIC contract
+ * is the Jx that ADE_ExUpdate subtracts (:667), but inside [mf, mr) ADE_ExCreate / NonLinExUpdate overwrite Ex from Dx, so
+ * a beam current there would drive nothing.  Ampere's law for the flux density is dD/dt = curl H - J, which in the
+ * reference's units (the slot holds J*dz, the bracket is multiplied by dt/dz) is the same bracket as in ADE_ExUpdate:
+ *     Dx += (Hy[nz] - Hy[nz-1] - Jx[nz]) * dt/dz * denE.
+ * With Jx = 0 (every reference run) this is ADE_DxUpdate bit for bit: x - 0.0 == x.                                   */
 void orc_dx_update(OrcGrid *g)
 {
     for (int nz = g->mf; nz < g->mr; ++nz)
-        g->Dx[nz] = g->Dx[nz] + (g->Hy[nz] - g->Hy[nz - 1]) * g->dt_over_dz * g->denE[nz];
+        g->Dx[nz] = g->Dx[nz] + (g->Hy[nz] - g->Hy[nz - 1] - g->Jx[nz]) * g->dt_over_dz * g->denE[nz];
 }
 
 /* BaseFDTD11.py:487-538 (history rotation) + :609-633 ADE_PolarisationCurrent_Ex.

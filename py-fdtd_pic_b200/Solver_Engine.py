@@ -126,7 +126,9 @@ def Sig_Mod(V, P, sig, AmpCarr=1, AmpMod=1, tau=14.6e-10):
 def _pick_engine(P, arrs, Jx, probe_idx):
     if ENGINE == "ops":
         return nat.PF_ENGINE_OPS, None
-    canon = dev.canonical_form(P, arrs, Jx)
+    canon = dev.canonical_form(P, arrs)
+    if Jx is not None and (USE_FMA or USE_FP32):
+        canon = None            # the tile engine carries a current slot in exact arithmetic only
     slab_src_clash = P.TFSF and (P.materialFrontEdge - 1 <= P.nzsrc - 1 < P.materialRearEdge)
     ok = canon is not None and dev.probes_ok_for_tiles(probe_idx) and not slab_src_clash
     if ENGINE == "tile" and not ok:

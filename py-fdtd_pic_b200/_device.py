@@ -24,8 +24,8 @@ def canonical_form(P, arrs, Jx=None):
     form, else None.  Every comparison is exact (bitwise for finite values)."""
     L = len(arrs["Ex"])
     pw, mf, mr = int(P.pmlWidth), int(P.materialFrontEdge), int(P.materialRearEdge)
-    if Jx is not None and np.any(Jx != 0.0):
-        return None
+    # (a current slot Jx does not affect the form of the coefficient arrays: the tile engine carries it as one more
+    #  per-cell input, see k_tile<..., JX>)
     for k in ("denE", "denH", "UpHySelf"):
         if not np.all(arrs[k] == 1.0):
             return None

@@ -93,6 +93,9 @@ __global__ void __launch_bounds__(OPS_THREADS) k_dx_update(PfGrid g)
     if (nz < 1 || nz >= g.L) return;
     if (!in_slab(g, PF_GZ(g, nz))) return;
     double dH = A::sub(g.Hy[nz], g.Hy[nz - 1]);
+    // current slot in material cells (builder-defined PIC coupling, dD/dt = curl H - J: the same bracket as ADE_ExUpdate;
+    // see include/pyfdtd_b200.h).  Jx == NULL in every reference run.
+    if (g.Jx) dH = A::sub(dH, g.Jx[nz]);
     g.Dx[nz] = A::add(g.Dx[nz], A::mul(A::mul(dH, g.dt_over_dz), g.denE[nz]));
 }
 

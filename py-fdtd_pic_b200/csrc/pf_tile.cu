@@ -245,11 +245,11 @@ __device__ __forceinline__ NlResultF nl_material_law_f32(float ca, float cb, flo
 // One full time step (E half-step, barrier, H half-step) on the thread's C cells.
 //   pc = P^n (current polarisation), pq = P^{n-1}: the new P^{n+1} is written over pq, so the
 //   caller alternates (pc,pq) <-> (pq,pc) instead of shifting the history (no register moves).
-template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, bool SP, class R = typename A::real>
+template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, bool SP, bool JX, class R = typename A::real>
 __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepConsts<R> &K, const CubicConsts *kcp, WarpLink &W, int tid, int s, bool more,
                                           R (&ex)[C], R (&hy)[C], R (&dx)[C], R (&pc)[C],
                                           R (&pq)[C], R (&pe)[C], R (&ph)[C], R (&acub)[C],
-                                          R (&rbe)[C], R (&rce)[C], R (&rcm)[C])
+                                          R (&rbe)[C], R (&rce)[C], R (&rcm)[C], const R (&jx)[C])
 {
     constexpr int NT = TILE_CELLS / C;
     constexpr bool F32 = std::is_same<R, float>::value;
@@ -268,6 +268,9 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
 #pragma unroll
     for (int j = 0; j < C; ++j) {
         const R dH = A::sub(hy[j], hl);
+        // JX: the current slot (PIC) enters the bracket of ADE_ExUpdate / ADE_DxUpdate, (Hy[nz] - Hy[nz-1] - Jx[nz]); the
+        // CPML convolution below keeps the plain difference (CPML_Psi_e_Update has no current term)
+        const R dHJ = JX ? A::sub(dH, jx[j]) : dH;
         hl = hy[j];
         R e = ex[j];
         R pnow = R(0);
@@ -297,7 +300,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
         }
         if (!ALL_MAT) {
             if constexpr (F32 && !GEN) e = A::add(e, A::mad(dH, K.cEs, A::mul(dH, K.cEs_lo)));
-            else e = A::mad(dH, GEN ? (R)S.cEu[j * NT + tid] : K.cEs, e);
+            else e = A::mad(dHJ, GEN ? (R)S.cEu[j * NT + tid] : K.cEs, e);
         }
         if (HAS_PML) {
             const R b = GEN ? (R)S.be[j * NT + tid] : rbe[j];
@@ -315,7 +318,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                     dx[j] = A::add(dx[j], A::sub(A::mad(dH, K.dtdz, A::mul(dH, K.dtdz_lo)), vnew));
                     em = dx[j];
                 } else {
-                    dx[j] = A::mad(dH, K.dtdz, dx[j]);
+                    dx[j] = A::mad(dHJ, K.dtdz, dx[j]);
                     em = div_const_fast(A::sub(dx[j], pnow), K.eps0, K.inv_eps0, divkey);
                 }
                 e = (!GEN || ((K.mSlab >> j) & 1)) ? em : e;
@@ -329,14 +332,14 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                 }
             } else if constexpr (A::newton) {   // PF_F_NEWTON: small enough to be inlined per cell
                 if (!GEN || ((K.mSlab >> j) & 1)) {
-                    dx[j] = A::mad(dH, K.dtdz, dx[j]);
+                    dx[j] = A::mad(dHJ, K.dtdz, dx[j]);
                     const R dn = LOR ? A::sub(dx[j], pnow) : dx[j];
                     nl_material_law_newton(NlNewtonConsts{K.ca, K.cb, K.cc, K.inv_cc}, dn, K.inv_eps0, K.den0, K.den1, acub[j], e);
                 }
             } else if (!GEN) {
-                dx[j] = A::mad(dH, K.dtdz, dx[j]);      // the material law of all C cells follows the loop
+                dx[j] = A::mad(dHJ, K.dtdz, dx[j]);      // the material law of all C cells follows the loop
             } else if ((K.mSlab >> j) & 1) {
-                dx[j] = A::mad(dH, K.dtdz, dx[j]);
+                dx[j] = A::mad(dHJ, K.dtdz, dx[j]);
                 const NlResult nl = nl_material_law(kcp, LOR ? A::sub(dx[j], pnow) : dx[j], K.eps0, K.inv_eps0, K.den0, K.den1);
                 acub[j] = nl.a;
                 e = nl.e;
@@ -445,7 +448,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
 //                 exactly 0 turns its term into an exact no-op (x + y*0 == x), so no per-cell branch
 //                 is needed; only the material law is selected per cell.
 // -------------------------------------------------------------------------------------------------
-template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, class R = typename A::real>
+template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, bool JX, class R = typename A::real>
 __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R> &S, const CellMasks &M, WarpLink W,
                                           int tid, int lz0, int ks, int src, int nabs0)
 {
@@ -460,7 +463,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
     // scaled variables of the fp32 mode (identity scales otherwise): H' = H sH, psi_E' = psi_E sH, D' = D sD, P' = P sD
     const double sH = F32 ? 1.0 / g.cH0 : 1.0, uH = F32 ? g.cH0 : 1.0;
     const double sD = F32 ? TG.d.inv_eps0 : 1.0, uD = F32 ? g.eps0 : 1.0;
-    R ex[C], hy[C], dx[C], pa[C], pb[C], pe[C], ph[C], acub[C], rbe[C], rce[C], rcm[C];
+    R ex[C], hy[C], dx[C], pa[C], pb[C], pe[C], ph[C], acub[C], rbe[C], rce[C], rcm[C], jx[C];
 
     // ---- load ---------------------------------------------------------------------------------
     {
@@ -471,6 +474,13 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
             bool v = !GEN || ((M.valid >> j) & 1);
             ex[j] = v ? inEx[lz0 + j] : 0.0;
             hy[j] = F32 ? (v ? inHy[lz0 + j] * sH : 0.0) : (v ? inHy[lz0 + j] : 0.0);
+        }
+        if (JX) {   // current slot: constant over the steps of a launch (a PIC-coupled run launches one step at a time)
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const bool v = (!GEN || ((M.valid >> j) & 1)) && g.Jx != nullptr;
+                jx[j] = v ? (R)g.Jx[lz0 + j] : R(0);
+            }
         }
         if (HAS_PML) {
             const double *__restrict__ inPe = TG.buf[src][S_PSIE];
@@ -584,16 +594,16 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 #define PF_STEP_SYNC() cta_sync()
 #endif
         for (; s + 1 < ks; s += 2) {
-            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s, true, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP, JX>(S, K, kc, W, tid, s, true, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm, jx);
             if (SP) probes(s);
             PF_STEP_SYNC();
-            if (SWAP) tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s + 1, s + 2 < ks, ex, hy, dx, pb, pa, pe, ph, acub, rbe, rce, rcm);
-            else tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s + 1, s + 2 < ks, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            if (SWAP) tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP, JX>(S, K, kc, W, tid, s + 1, s + 2 < ks, ex, hy, dx, pb, pa, pe, ph, acub, rbe, rce, rcm, jx);
+            else tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP, JX>(S, K, kc, W, tid, s + 1, s + 2 < ks, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm, jx);
             if (SP) probes(s + 1);
             PF_STEP_SYNC();
         }
         if (s < ks) {
-            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP>(S, K, kc, W, tid, s, false, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm);
+            tile_step<MODE, POL, C, A, GEN, SLAB, PML, SP, JX>(S, K, kc, W, tid, s, false, ex, hy, dx, pa, pb, pe, ph, acub, rbe, rce, rcm, jx);
             if (SP) probes(s);
             PF_STEP_SYNC();
             swapped = SWAP;
@@ -666,7 +676,7 @@ constexpr int tile_minblocks()
            : (A::newton ? PF_TILE_MINBLOCKS_NEWTON : (MODE == PF_FREE ? PF_TILE_MINBLOCKS_FREE : PF_TILE_MINBLOCKS));
 }
 
-template <int MODE, bool POL, int C, class A>
+template <int MODE, bool POL, int C, class A, bool JX = false>
 __global__ void __launch_bounds__(TILE_CELLS / C, tile_minblocks<MODE, A>())
 k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, int src, int n_done,
        int n0, int ksteps, int halo)
@@ -796,10 +806,10 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
 #endif
 
     switch (cls) {
-    case 0: tile_body<MODE, POL, C, A, false, false, false>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
-    case 1: tile_body<MODE, POL, C, A, false, true, false>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
-    case 2: tile_body<MODE, POL, C, A, false, false, true>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
-    case 3: tile_body<MODE, POL, C, A, false, true, true>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    case 0: tile_body<MODE, POL, C, A, false, false, false, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    case 1: tile_body<MODE, POL, C, A, false, true, false, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    case 2: tile_body<MODE, POL, C, A, false, false, true, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    case 3: tile_body<MODE, POL, C, A, false, true, true, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
     case 5:
         // nothing to compute: publish zero edges once, then only keep the CTA's barrier count
         S.edgeH[tid] = R(0);
@@ -807,7 +817,7 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
         cta_sync();
         for (int s = 0; s < ks; ++s) { cta_sync(); cta_sync(); }
         break;
-    default: tile_body<MODE, POL, C, A, true, true, true>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    default: tile_body<MODE, POL, C, A, true, true, true, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
     }
 }
 
@@ -886,7 +896,6 @@ static int tile_supported(const PfGrid &g, int mode)
     if (g.Lg >= (1LL << 31) - (1LL << 12) || g.z0 < -(1LL << 30) || g.z0 + g.L > g.Lg + (1LL << 12))
         return set_err(PF_E_UNSUPPORTED, "tile engine: global indices are evaluated in 32 bits (Lg = %lld)", (long long)g.Lg);
     if (!(g.flags & PF_F_CANONICAL)) return set_err(PF_E_UNSUPPORTED, "tile engine needs PF_F_CANONICAL coefficients");
-    if (g.Jx) return set_err(PF_E_UNSUPPORTED, "tile engine: Jx must be NULL");
     if (mode != PF_FREE && (g.flags & PF_F_TFSF) && g.nzsrc - 1 >= g.mf - 1 && g.nzsrc - 1 < g.mr)
         return set_err(PF_E_UNSUPPORTED, "tile engine: TF/SF point inside the slab");
     if (g.n_probes > 64) return set_err(PF_E_UNSUPPORTED, "tile engine: more than 64 probes");
@@ -927,7 +936,7 @@ static TilePlan tile_plan(const PfGrid *grids, int n, int mode, int halo)
     return p;
 }
 
-enum { ARITH_EXACT = 0, ARITH_FUSED = 1, ARITH_FP32 = 2, ARITH_NEWTON = 3 };
+enum { ARITH_EXACT = 0, ARITH_FUSED = 1, ARITH_FP32 = 2, ARITH_NEWTON = 3, ARITH_EXACT_JX = 4 };
 
 template <int MODE, bool POL, int C, class A>
 static const char *tile_kernel_name()
@@ -942,7 +951,7 @@ static const char *tile_kernel_name()
     return name;
 }
 
-template <int MODE, bool POL, int C, class A>
+template <int MODE, bool POL, int C, class A, bool JX = false>
 static int launch_tile_a(int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
                          int n0, int ks, int halo, cudaStream_t st)
 {
@@ -953,10 +962,10 @@ static int launch_tile_a(int n_tiles, const TileGrid *dg, const TileDesc *dt, in
     PF_CUDA(cudaGetDevice(&dev));
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(attr_set.load(std::memory_order_acquire) & bit)) {
-        PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        PF_CUDA(cudaFuncSetAttribute(k_tile<MODE, POL, C, A, JX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         attr_set.fetch_or(bit, std::memory_order_release);
     }
-    k_tile<MODE, POL, C, A><<<n_tiles, TILE_CELLS / C, sm, st>>>(dg, dt, src, n_done, n0, ks, halo);
+    k_tile<MODE, POL, C, A, JX><<<n_tiles, TILE_CELLS / C, sm, st>>>(dg, dt, src, n_done, n0, ks, halo);
     PF_LAUNCH_CHECK("k_tile");
     return 0;
 }
@@ -992,6 +1001,14 @@ constexpr int TILE_C_FREE = PF_TILE_C_FREE;
 static int launch_tile_mode(int mode, int do_pol, int fma, bool wide, int n_tiles, const TileGrid *dg, const TileDesc *dt,
                             int src, int n_done, int n0, int ks, int halo, cudaStream_t st)
 {
+    if (fma == ARITH_EXACT_JX) {   // a current slot (PIC coupling) is present: exact arithmetic, one geometry per mode
+        if (mode == PF_FREE) return launch_tile_a<PF_FREE, false, TILE_C_FREE, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        if (mode == PF_LORENTZ)
+            return do_pol ? launch_tile_a<PF_LORENTZ, true, TILE_C, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
+                          : launch_tile_a<PF_LORENTZ, false, TILE_C, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        if (mode == PF_NL) return launch_tile_a<PF_NL, false, TILE_C, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        return set_err(PF_E_UNSUPPORTED, "tile engine: a current slot (Jx) is supported in modes FREE, LORENTZ and NL");
+    }
     if (fma == ARITH_FP32) {   // PF_F_FP32: one geometry per mode
         if (mode == PF_FREE) return launch_tile_a<PF_FREE, false, PF_TILE_C_F32_FREE, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
         if (mode == PF_LORENTZ)
@@ -1036,6 +1053,13 @@ static int arith_of(const PfGrid *grids, int n, int mode, int *arith)
         } else if ((g.flags & PF_F_FMA) && a == ARITH_EXACT) {
             a = ARITH_FUSED;
         }
+    }
+    bool jx = false;
+    for (int m = 0; m < n; ++m) jx = jx || grids[m].Jx != nullptr;
+    if (jx) {
+        if (a != ARITH_EXACT) return set_err(PF_E_UNSUPPORTED, "tile engine: a current slot (Jx) needs exact arithmetic (no PF_F_FMA / PF_F_FP32)");
+        *arith = ARITH_EXACT_JX;      // (PF_F_NEWTON is ignored: the closed-form law runs)
+        return 0;
     }
     if (a == ARITH_EXACT && newton) a = ARITH_NEWTON;
     *arith = a;

@@ -137,13 +137,33 @@ class ParticleSet:
         return {k: v.cpu().numpy() for k, v in self.cur.items()} | {"cell": self.cell.cpu().numpy()}
 
 
+def coupled_grid(V, P, C_V, C_P, Exs, Hys, mode="free", probe_idx=()):
+    """DeviceGrid of one prepared pass (Solver_Engine.prepare_pass has run) for CoupledPIC: per-cell coefficient arrays for
+    the per-op engine plus, when they have the canonical piecewise form, the scalars and flag the fused tile engine needs."""
+    from . import BaseFDTD11, _device as dev
+    arrs = BaseFDTD11._host_arrays(V, C_V, V.tempVarPol)
+    scal = BaseFDTD11.grid_scalars(V, P, kerr_lorentz=(mode == "lorentz_nl"))
+    flags = BaseFDTD11.grid_flags(P)
+    canon = dev.canonical_form(P, arrs)
+    slab_src_clash = mode != "free" and P.TFSF and (P.materialFrontEdge - 1 <= P.nzsrc - 1 < P.materialRearEdge)
+    if canon is not None and not slab_src_clash and dev.probes_ok_for_tiles(list(probe_idx)):
+        scal.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
+        flags |= nat.PF_F_CANONICAL
+    return dev.DeviceGrid(L=len(V.Ex), T=int(P.timeSteps), arrays=arrs, scalars=scal, srcE=np.asarray(Exs) / P.courantNo,
+                          srcH=np.asarray(Hys) / P.courantNo, probe_idx=list(probe_idx), flags=flags)
+
+
 class CoupledPIC:
-    """PIC step coupled to one FDTD grid: deposit -> field step (Jx subtracted in ADE_ExUpdate) -> push.
+    """PIC step coupled to one FDTD grid: deposit -> field step -> push.
 
-    ``grid`` is a _device.DeviceGrid whose descriptor gets its Jx pointer from the particle set; the
-    field step runs through ENGINE_OPS (the engine that carries per-cell arrays, including Jx)."""
+    The deposited current enters the field step through the Jx slot: ADE_ExUpdate subtracts it (BaseFDTD11.py:667) and,
+    inside the slab [mf, mr) -- where the reference's loops overwrite Ex from Dx -- ADE_DxUpdate subtracts it the same way
+    (dD/dt = curl H - J; builder-defined, see include/pyfdtd_b200.h), so a beam inside the Lorentz / cubic medium drives
+    the fields there too.  ``grid`` is a _device.DeviceGrid (see ``coupled_grid``) whose descriptor gets its Jx pointer from
+    the particle set.  engine "auto": the fused tile kernel (one launch per field step, k_tile<..., JX>) when the grid
+    carries PF_F_CANONICAL and the mode is free / lorentz / nl, else the per-op engine (one kernel per leaf op)."""
 
-    def __init__(self, grid, particles, mode="free", fused=False):
+    def __init__(self, grid, particles, mode="free", fused=False, engine="auto"):
         from . import _device as dev
         self.grid, self.particles = grid, particles
         self.mode_id = dev.MODE_ID[mode]
@@ -151,6 +171,14 @@ class CoupledPIC:
         self.n = 0
         self.fused = fused          # True: push + re-sort + deposit in one pass over the particles (step_sorted)
         self._have_J = False
+        tile_ok = bool(grid.g.flags & nat.PF_F_CANONICAL) and mode in ("free", "lorentz", "nl")
+        if engine == "tile" and not tile_ok:
+            raise ValueError("CoupledPIC: engine='tile' needs a canonical grid (pic.coupled_grid) in mode free / lorentz / nl")
+        self.engine = nat.PF_ENGINE_TILE if (tile_ok and engine != "ops") else nat.PF_ENGINE_OPS
+        self.scratch, self.scratch_bytes = None, 0
+        if self.engine == nat.PF_ENGINE_TILE:
+            self.scratch_bytes = nat.lib().pf_run_scratch_bytes(grid.ref(), 1, nat.PF_ENGINE_TILE)
+            self.scratch = particles.torch.empty(self.scratch_bytes, dtype=particles.torch.uint8, device=particles.device)
 
     def step(self, do_pol=False):
         lib = nat.lib()
@@ -158,8 +186,9 @@ class CoupledPIC:
             raise ValueError(f"CoupledPIC.step: step {self.n} is past the grid's source tables (T = {self.grid.T})")
         if not (self.fused and self._have_J):
             self.particles.deposit()
-        nat.check(lib.pf_run_pass(self.grid.ref(), self.mode_id, int(do_pol), self.n, 1, nat.PF_ENGINE_OPS, None, 0, 0,
-                                  None, 0, nat.current_stream_ptr()), "pf_run_pass")
+        nat.check(lib.pf_run_pass(self.grid.ref(), self.mode_id, int(do_pol), self.n, 1, self.engine, None, 0, 0,
+                                  self.scratch.data_ptr() if self.scratch is not None else None, self.scratch_bytes,
+                                  nat.current_stream_ptr()), "pf_run_pass")
         if self.fused:               # the deposit of the pushed state is the current of the next field step
             self.particles.step_sorted(self.grid.tensor_view("Ex"), self.grid.tensor_view("Hy"))
             self._have_J = True

@@ -58,7 +58,7 @@ def test_table_batch_is_bit_identical_to_member_batch(pk):
         assert np.array_equal(ta[i], tb[i]), i
         for name in ("Ex", "Hy", "Dx", "P", "Pprev", "psiE", "psiH"):
             assert np.array_equal(a_batch.state(i, name), b_batch.state(i, name)), (i, name)
-    assert np.max(np.abs(ta[0])) > 0.1
+    assert np.max(np.abs(ta[0])) > 1e-3
 
 
 def test_reflection_sweep_equals_the_per_member_two_pass_batch(pk):
