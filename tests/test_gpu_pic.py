@@ -214,3 +214,77 @@ def test_coupled_fused_step_matches_unfused(pic):
     assert np.max(np.abs(ExA)) > 0
     assert rel(ExB, ExA) <= 1e-12 and rel(HyB, HyA) <= 1e-12
     assert rel(hB["z"], hA["z"]) <= 1e-12 and rel(hB["ux"], hA["ux"]) <= 1e-12 and rel(hB["uz"], hA["uz"]) <= 1e-12
+
+
+@pytest.mark.parametrize("engine", ["ops", "tile"])
+@pytest.mark.parametrize("mode", ["free", "lorentz", "nl"])
+def test_beam_inside_the_medium_drives_the_fields(pic, mode, engine):
+    """CoupledPIC with the beam overlapping the slab, every material mode, both engines, against the oracle chain
+    deposit -> one field step with that Jx (ADE_ExUpdate outside, ADE_DxUpdate inside the slab) -> push -> stable sort.
+    Bit-identical fields for the linear modes; the cubic mode is held to its 1e-10."""
+    import ctypes
+    import fdtd_oracle as fo
+    from pyfdtd_b200 import Solver_Engine as SE
+    from test_host_layer import build_objects
+    spec = dict(mode=mode, freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000, epsRe=1.0)
+    V, P, C_V, C_P = build_objects(spec)
+    C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=(mode == "lorentz"), nonlinear=(mode == "nl"))
+    L = len(V.Ex)
+    z, ux, uz, w, cell = po.make_beam(30_000, L, P.dz, seed=7)              # uniform over 5 % .. 95 % of the grid: most of it in the slab
+    ux = ux + 5e7
+    w = w * 1e3
+    assert np.sum((z / P.dz > P.materialFrontEdge) & (z / P.dz < P.materialRearEdge)) > 10_000
+    ps = pic.ParticleSet(z, ux, uz, w, L, P.dz, P.delT)
+    g = pic.coupled_grid(V, P, C_V, C_P, Exs, Hys, mode=mode)
+    sim = pic.CoupledPIC(g, ps, mode=mode, engine=engine)
+    do_pol = mode == "lorentz"
+    nsteps = 6
+    for _ in range(nsteps):
+        sim.step(do_pol=do_pol)
+    # oracle
+    c = fo.make_case(mode, 9e9, 0.15, 300, 320, source="sine", periods=1000, epsRe=1.0)
+    pa = fo.PassArrays(c, V.plasmaFreqE, np.asarray(Exs), np.asarray(Hys), [], False, Jx=np.zeros(L))
+    zo, uxo, uzo, wo, co = po.sort_by_cell(z, ux, uz, w, cell)
+    for n in range(nsteps):
+        pa.Jx[:] = po.deposit(zo, uxo, uzo, wo, co, L, dz=P.dz, c=C0, jx_scale=Q)
+        fo.lib().orc_run(ctypes.byref(pa.g), fo.MODE_ID[mode], int(do_pol), n, 1, c.T)
+        zo, uxo, uzo, co = po.push(zo, uxo, uzo, pa.Ex, pa.Hy, dz=P.dz, dt=P.delT, q_over_m=QM, c=C0, mu0=MU0)
+        zo, uxo, uzo, wo, co = po.sort_by_cell(zo, uxo, uzo, wo, co)
+    out = g.fetch(["Ex", "Hy", "Dx", "P"], probes=False)
+    slab = slice(P.materialFrontEdge, P.materialRearEdge)
+    assert np.max(np.abs(pa.Dx[slab])) > 0 and np.max(np.abs(pa.Ex[slab])) > 0          # the beam did drive the medium
+    if mode == "nl":
+        assert rel(out["Ex"], pa.Ex) <= 1e-10 and rel(out["Hy"], pa.Hy) <= 1e-10 and rel(out["Dx"], pa.Dx) <= 1e-10
+    else:
+        for name in ("Ex", "Hy", "Dx") + (("P",) if mode == "lorentz" else ()):
+            if mode == "free" and name == "Dx":
+                continue
+            assert np.array_equal(out[name], getattr(pa, name)), name
+    h = ps.host()
+    tol = 1e-12 if mode != "nl" else 1e-9
+    assert rel(h["z"], zo) <= tol and rel(h["ux"], uxo) <= tol and rel(h["uz"], uzo) <= tol
+    # without the builder-defined Dx term the slab would not feel the beam at all: Ex there would equal the beam-free run
+    assert (sim.engine == 1) == (engine == "tile")
+
+
+def test_tile_engine_with_a_static_current_equals_the_per_op_engine(pic):
+    """run_time_loop with a prescribed V.Jx (constant in time): the fused tile kernel (k = 64 steps per launch, Jx carried
+    as a per-cell input) against the per-op engine, Lorentz mode, bit for bit."""
+    from pyfdtd_b200 import Solver_Engine as SE
+    from test_host_layer import build_objects
+    outs = []
+    for engine in ("ops", "tile"):
+        SE.ENGINE = engine
+        try:
+            V, P, C_V, C_P = build_objects(dict(mode="lorentz", freq=9e9, dom=0.15, win=[300, 320], source="sine", periods=1000))
+            C_V, Exs, Hys = SE.prepare_pass(V, P, C_V, C_P, lorentz=True)
+            L = len(V.Ex)
+            V.Jx = 1e-3 * np.sin(np.arange(L) * 0.01) * (np.arange(L) > P.pmlWidth) * (np.arange(L) < L - P.pmlWidth)
+            tr = SE.run_time_loop(V, P, C_V, C_P, "lorentz", True, Exs, Hys, [P.x2Loc], nsteps=300)
+            assert SE.LAST_RUN_INFO["engine"] == engine
+            outs.append((V.Ex.copy(), V.Hy.copy(), V.Dx.copy(), V.polarisationCurr.copy(), tr.copy()))
+        finally:
+            SE.ENGINE = "auto"
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert np.max(np.abs(outs[0][0])) > 0

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Run under torchrun on N GPUs: sweep.reflection_sweep sharded over the ranks (member % N == rank, no data-path
+collective) must give exactly the numbers of the unsharded sweep (rank 0 runs that too and compares)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pyfdtd_b200  # noqa: E402,F401
+from pyfdtd_b200 import sweep  # noqa: E402
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+freqs = np.linspace(6e9, 10.5e9, 13)
+mine = sweep.reflection_sweep(freqs, 0.15, 300, 320, periods=1.0, rank=rank, world_size=world)
+parts = [None] * world
+dist.all_gather_object(parts, (mine["index"], mine["measured"]))
+ok = True
+if rank == 0:
+    full = sweep.reflection_sweep(freqs, 0.15, 300, 320, periods=1.0)
+    got = np.empty(len(freqs))
+    for idx, val in parts:
+        got[idx] = val
+    ok = bool(np.array_equal(got, full["measured"]))
+    print(f"world={world} sharded == unsharded: {ok}")
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
