@@ -370,6 +370,87 @@ static __device__ __noinline__ NlResultVec<C> nl_material_law_vec(const CubicCon
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The closed-form cubic material law of one cell, FAST PATH (tile engine, default cubic mode).  Same algorithm and
+// operation order as acubic_cell() + cubic_root0() above -- AcubicFinder / CubicEquationSolver.solve / NonLinExUpdate,
+// including the cancellation in T = -g/2 - sqrt(h) and in (S + U) - b/3a that parity has to reproduce -- but written
+// for the one-real-root branch only and without per-operation special cases:
+//   * the three divisions by run constants are the unguarded two-FMA Markstein form (exact for every operand the law
+//     can produce on this branch);
+//   * v ** (1/3.0) is cbrt by ONE Halley step from a single-precision seed ex2(lg2(v)/3) (the construction CUDA's cbrt
+//     uses, minus its denormal / zero / infinity handling), and the same lg2 feeds the exponent correction
+//     (1 + (double(1/3) - 1/3) ln v) that turns cbrt into the reference's pow(v, 1/3.0);
+//   * Dn / (den0 + den1 A) is a reciprocal refined by two Newton steps with a final residual correction (<= 1 ulp).
+// Anything outside the branch (a == 0, h <= 0, an operand outside the single-precision exponent range of the seed, a
+// non-finite result) returns ok = false and the caller redoes the cell with nl_material_law() -- never taken on the
+// nonlinear sweeps.  Accuracy class: ~1 ulp per elementary function, like the out-of-line law (whose cbrt / sqrt / div
+// are CUDA's); the mode's tolerances (Acubic 1e-10 absolute, Ex 1e-10 relative) are tested against the reference goldens.
+// ---------------------------------------------------------------------------------------------
+struct NlFastConsts {
+    double a, inv_a, g_ab, f3_27, b_3a;
+};
+__device__ __forceinline__ double pow_third_fast(double v, bool &ok)   // v != 0
+{
+    const double c_minus_third = -1.850371707708594e-17;   // double(1/3.0) - 1/3
+    const double x = fabs(v);
+    const float xf = (float)x;
+    ok = ok && (xf > 1e-30f) && (xf < 1e30f);
+    float lg, yf;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(lg * 0.333333343f));
+    const double y = (double)yf;
+    const double y2 = y * y;
+    const double den = fma(y, y2 + y2, x);      // 2 y^3 + x
+    const double num = fma(-y, y2, x);          // x - y^3
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double e = fma(-den, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    double s = fma(y, num * r, y);              // Halley step: cbrt(x) to rounding
+    const double lnx = (double)(lg * 0.693147182f);
+    s = fma(s, c_minus_third * lnx, s);         // -> x ** double(1/3)
+    return copysign(s, v);
+}
+__device__ __forceinline__ bool nl_material_law_fast(const NlFastConsts &k, double dn, double eps0, double inv_eps0,
+                                                     double den0, double den1, double &acub, double &e_out)
+{
+    bool ok = k.a != 0.0;
+    // AcubicFinder: q = |Dn/eps0|, d = -q^2
+    double q = __dmul_rn(dn, inv_eps0);
+    q = fabs(__fma_rn(__fma_rn(-q, eps0, dn), inv_eps0, q));
+    const double qq = __dmul_rn(q, q);
+    const double d = -qq;
+    double A = 0.0;
+    if (qq > 1e-8) {         // warp-divergent only while the wave front passes
+        const double x3 = __dmul_rn(27.0, d);
+        double t3 = __dmul_rn(x3, k.inv_a);                                // 27 d / a
+        t3 = __fma_rn(__fma_rn(-t3, k.a, x3), k.inv_a, t3);
+        const double xg = __dadd_rn(k.g_ab, t3);
+        double g = __dmul_rn(xg, 1.0 / 27.0);                              // findG
+        g = __fma_rn(__fma_rn(-g, 27.0, xg), 1.0 / 27.0, g);
+        const double h = __dadd_rn(__dmul_rn(__dmul_rn(g, g), 0.25), k.f3_27);   // findH
+        const double ghalf = __dmul_rn(g, 0.5);
+        ok = ok && (h > 0.0);
+        const double sh = sqrt(h);
+        const double S = pow_third_fast(__dadd_rn(-ghalf, sh), ok);
+        const double U = pow_third_fast(__dsub_rn(-ghalf, sh), ok);
+        A = __dsub_rn(__dadd_rn(S, U), k.b_3a);
+        ok = ok && (fabs(A) < 1e300);            // also false for NaN
+    }
+    const double den = __dadd_rn(den0, __dmul_rn(den1, A));
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    const double e0 = dn * r;
+    const double e = fma(fma(-den, e0, dn), r, e0);
+    ok = ok && (fabs(e) < 1e300) && (fabs(dn) > 1e-250 || dn == 0.0);
+    acub = A;
+    e_out = e;
+    return ok;
+}
+
 // Host-side constants, evaluated exactly as CubicEquationSolver.findF/findG/findH do in CPython
 // (float ** float -> libm pow).  Defined in pf_host.cu.
 CubicConsts cubic_consts_host(double a, double b, double c);

@@ -207,6 +207,7 @@ struct StepConsts {
     R cEs_lo, dtdz_lo;
     R pG, pK;            // fp32 mode: Lorentz ADE in difference form, G = 1 + B, K = 1 - A - B
     R ca, cb, cc, inv_cc;   // fp32 / Newton modes: cubic coefficients (and 1/c) in registers
+    NlFastConsts kf;        // closed-form cubic law, fast path (fp64 only)
     int jsrc, jtfsf;
     bool wSrc;
     unsigned mSlab;
@@ -265,6 +266,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
 #endif
     R hl = S.edgeH[tid - 1];
     unsigned divkey = 0;
+    unsigned nlbad = 0;   // closed-form cubic law: cells whose fast path has to be redone by the general law
 #pragma unroll
     for (int j = 0; j < C; ++j) {
         const R dH = A::sub(hy[j], hl);
@@ -336,17 +338,29 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                     const R dn = LOR ? A::sub(dx[j], pnow) : dx[j];
                     nl_material_law_newton(NlNewtonConsts{K.ca, K.cb, K.cc, K.inv_cc}, dn, K.inv_eps0, K.den0, K.den1, acub[j], e);
                 }
-            } else if (!GEN) {
-                dx[j] = A::mad(dHJ, K.dtdz, dx[j]);      // the material law of all C cells follows the loop
-            } else if ((K.mSlab >> j) & 1) {
-                dx[j] = A::mad(dHJ, K.dtdz, dx[j]);
-                const NlResult nl = nl_material_law(kcp, LOR ? A::sub(dx[j], pnow) : dx[j], K.eps0, K.inv_eps0, K.den0, K.den1);
-                acub[j] = nl.a;
-                e = nl.e;
+            } else {
+#ifdef PF_NL_OUT_OF_LINE     // round-1 arrangement: the closed-form law as an out-of-line call (kept for A/B timing)
+                if (!GEN) {
+                    dx[j] = A::mad(dHJ, K.dtdz, dx[j]);      // the material law of all C cells follows the loop
+                } else if ((K.mSlab >> j) & 1) {
+                    dx[j] = A::mad(dHJ, K.dtdz, dx[j]);
+                    const NlResult nl = nl_material_law(kcp, LOR ? A::sub(dx[j], pnow) : dx[j], K.eps0, K.inv_eps0, K.den0, K.den1);
+                    acub[j] = nl.a;
+                    e = nl.e;
+                }
+#else
+                if (!GEN || ((K.mSlab >> j) & 1)) {          // closed form, inlined fast path (pf_common.cuh)
+                    dx[j] = A::mad(dHJ, K.dtdz, dx[j]);
+                    const R dn = LOR ? A::sub(dx[j], pnow) : dx[j];
+                    const bool ok = nl_material_law_fast(K.kf, dn, K.eps0, K.inv_eps0, K.den0, K.den1, acub[j], e);
+                    nlbad |= (ok ? 0u : 1u) << j;
+                }
+#endif
             }
         }
         ex[j] = e;
     }
+#ifdef PF_NL_OUT_OF_LINE
     if constexpr ((MODE == PF_NL || MODE == PF_LORENTZ_NL) && ALL_MAT && !F32 && !A::newton) {
         NlVec<C> dv;
 #pragma unroll
@@ -355,6 +369,21 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
 #pragma unroll
         for (int j = 0; j < C; ++j) { acub[j] = nl.a[j]; ex[j] = nl.e[j]; }
     }
+#else
+    if constexpr ((MODE == PF_NL || MODE == PF_LORENTZ_NL) && HAS_MAT && !F32 && !A::newton) {
+        // cells the fast path declined (other branch of the cubic, out-of-range operand): the general out-of-line law
+        if (__any_sync(0xffffffffu, nlbad != 0u)) {
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                if ((nlbad >> j) & 1) {
+                    const NlResult nl = nl_material_law(kcp, LOR ? A::sub(dx[j], POL ? pq[j] : pc[j]) : dx[j], K.eps0, K.inv_eps0, K.den0, K.den1);
+                    acub[j] = nl.a;
+                    ex[j] = nl.e;
+                }
+            }
+        }
+    }
+#endif
     // warp-uniform test: a per-lane branch here opens a divergent region, which costs the uniform
     // registers holding the shared-memory window (re-read with S2UR after every step)
 #ifdef PF_EXPERIMENT_NO_GUARD   // timing experiment only: cost of the division-range guard
@@ -547,6 +576,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
     }
     K.pG = (R)(1.0 + g.polB); K.pK = (R)((1.0 - g.polA) - g.polB);
     K.ca = (R)g.cub_a; K.cb = (R)g.cub_b; K.cc = (R)g.cub_c; K.inv_cc = (R)TG.d.k.inv_c;
+    K.kf.a = TG.d.k.a; K.kf.inv_a = TG.d.k.inv_a; K.kf.g_ab = TG.d.k.g_ab; K.kf.f3_27 = TG.d.k.f3_27; K.kf.b_3a = TG.d.k.b_3a;
     K.jsrc = M.jsrc; K.jtfsf = M.jtfsf; K.mSlab = mSlab;
     K.wSrc = __any_sync(0xffffffffu, M.jsrc >= 0 || M.jtfsf >= 0);
     const CubicConsts *kc = &TG.d.k;

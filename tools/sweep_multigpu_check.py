@@ -26,6 +26,8 @@ if rank == 0:
     for idx, val in parts:
         got[idx] = val
     ok = bool(np.array_equal(got, full["measured"]))
-    print(f"world={world} sharded == unsharded: {ok}")
+    print(f"world={world} sharded == unsharded: {ok}  max |diff| = {np.max(np.abs(got - full['measured'])):.3e}", flush=True)
+    if not ok:
+        print("sharded  ", got, "\nunsharded", full["measured"], flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
