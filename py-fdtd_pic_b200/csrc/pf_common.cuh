@@ -415,7 +415,7 @@ __device__ __forceinline__ double pow_third_fast(double v, bool &ok)   // v != 0
 __device__ __forceinline__ bool nl_material_law_fast(const NlFastConsts &k, double dn, double eps0, double inv_eps0,
                                                      double den0, double den1, double &acub, double &e_out)
 {
-    bool ok = k.a != 0.0;
+    bool ok = true;          // (the caller has checked a != 0 once per launch)
     // AcubicFinder: q = |Dn/eps0|, d = -q^2
     double q = __dmul_rn(dn, inv_eps0);
     q = fabs(__fma_rn(__fma_rn(-q, eps0, dn), inv_eps0, q));
@@ -436,7 +436,6 @@ __device__ __forceinline__ bool nl_material_law_fast(const NlFastConsts &k, doub
         const double S = pow_third_fast(__dadd_rn(-ghalf, sh), ok);
         const double U = pow_third_fast(__dsub_rn(-ghalf, sh), ok);
         A = __dsub_rn(__dadd_rn(S, U), k.b_3a);
-        ok = ok && (fabs(A) < 1e300);            // also false for NaN
     }
     const double den = __dadd_rn(den0, __dmul_rn(den1, A));
     double r;
@@ -445,7 +444,12 @@ __device__ __forceinline__ bool nl_material_law_fast(const NlFastConsts &k, doub
     r = fma(r, fma(-den, r, 1.0), r);
     const double e0 = dn * r;
     const double e = fma(fma(-den, e0, dn), r, e0);
-    ok = ok && (fabs(e) < 1e300) && (fabs(dn) > 1e-250 || dn == 0.0);
+    // validity on the exponent fields (integer pipe): A and e finite (also catches NaN); Dn zero or inside the range in
+    // which the two-FMA divisions above are exact
+    const unsigned ea = (unsigned)__double2hiint(A) & 0x7ff00000u, ee = (unsigned)__double2hiint(e) & 0x7ff00000u;
+    const unsigned hd = (unsigned)__double2hiint(dn);
+    const bool dn_zero = ((hd << 1) | (unsigned)__double2loint(dn)) == 0u;
+    ok = ok && ea != 0x7ff00000u && ee != 0x7ff00000u && (dn_zero || ((hd & 0x7ff00000u) - DIVC_LO) < DIVC_RANGE);
     acub = A;
     e_out = e;
     return ok;

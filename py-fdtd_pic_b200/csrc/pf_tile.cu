@@ -208,6 +208,7 @@ struct StepConsts {
     R pG, pK;            // fp32 mode: Lorentz ADE in difference form, G = 1 + B, K = 1 - A - B
     R ca, cb, cc, inv_cc;   // fp32 / Newton modes: cubic coefficients (and 1/c) in registers
     NlFastConsts kf;        // closed-form cubic law, fast path (fp64 only)
+    bool kf_ok;             // the fast path applies to this grid (cub != 0: a genuine cubic)
     int jsrc, jtfsf;
     bool wSrc;
     unsigned mSlab;
@@ -352,7 +353,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
                 if (!GEN || ((K.mSlab >> j) & 1)) {          // closed form, inlined fast path (pf_common.cuh)
                     dx[j] = A::mad(dHJ, K.dtdz, dx[j]);
                     const R dn = LOR ? A::sub(dx[j], pnow) : dx[j];
-                    const bool ok = nl_material_law_fast(K.kf, dn, K.eps0, K.inv_eps0, K.den0, K.den1, acub[j], e);
+                    const bool ok = K.kf_ok && nl_material_law_fast(K.kf, dn, K.eps0, K.inv_eps0, K.den0, K.den1, acub[j], e);
                     nlbad |= (ok ? 0u : 1u) << j;
                 }
 #endif
@@ -576,6 +577,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
     }
     K.pG = (R)(1.0 + g.polB); K.pK = (R)((1.0 - g.polA) - g.polB);
     K.ca = (R)g.cub_a; K.cb = (R)g.cub_b; K.cc = (R)g.cub_c; K.inv_cc = (R)TG.d.k.inv_c;
+    K.kf_ok = TG.d.k.a != 0.0;
     K.kf.a = TG.d.k.a; K.kf.inv_a = TG.d.k.inv_a; K.kf.g_ab = TG.d.k.g_ab; K.kf.f3_27 = TG.d.k.f3_27; K.kf.b_3a = TG.d.k.b_3a;
     K.jsrc = M.jsrc; K.jtfsf = M.jtfsf; K.mSlab = mSlab;
     K.wSrc = __any_sync(0xffffffffu, M.jsrc >= 0 || M.jtfsf >= 0);

@@ -287,3 +287,76 @@ def test_builder_defined_models_have_not_drifted():
                 a, b = np.asarray(new[k], dtype=np.float64), np.asarray(old[k], dtype=np.float64)
                 scale = max(float(np.max(np.abs(b))), 1e-300)
                 assert float(np.max(np.abs(a - b))) <= 1e-11 * scale, (name, k)
+
+
+# ------------------------------------------------------------------------------------------------ PIC: external physics
+def _cold_plasma_run(wp_over_w, steps, record_from):
+    """The PIC model of oracle/pic_oracle.py coupled to the oracle's vacuum integrator through the Jx slot, driven by the
+    TF/SF sine source: a half-space of cold electrons (at rest, 4 per cell, quiet start) from the slab front into the right
+    CPML.  Returns (Ex samples [steps - record_from, L], case, first plasma cell)."""
+    import ctypes
+    import pic_oracle as po
+    C0, MU0, QM, Q = 299792458.0, 1.25663706127e-06, -1.75882001076e11, -1.602176634e-19
+    c = fo.make_case("free", 9e9, 0.15, 1500, 1600, source="sine", periods=1000, epsRe=1.0)
+    assert c.T >= steps
+    L, dz, dt = c.L, c.dz, c.dt
+    # continuous sine through the TF/SF point (SmoothTurnOn's tables without the free-space run's sech envelope),
+    # switched on over three periods
+    nn = np.arange(c.T)
+    ppw = C0 / (c.freq * dz)
+    ramp = np.minimum(1.0, nn * dt * c.freq / 3.0)
+    Exs = ramp * np.sin(2.0 * np.pi / ppw * (c.courantNo * nn)) * c.courantNo
+    Hys = ramp * np.sin(2.0 * np.pi / ppw * (c.courantNo * (nn + 1))) * c.courantNo * (1 / fo.CHAR_IMP)
+    pa = fo.PassArrays(c, 0.0, Exs, Hys, [], False, Jx=np.zeros(L))
+    a, b = c.mf, L - c.pw // 2
+    ppc = 4
+    cells = np.arange(a, b)
+    z = ((cells[:, None] + (np.arange(ppc)[None, :] + 0.5) / ppc) * dz).ravel()
+    w_src = 2 * np.pi * c.freq
+    n_e = (wp_over_w * w_src) ** 2 * fo.EPS0 * (Q / QM) / Q ** 2            # wp^2 = n q^2 / (eps0 m)
+    wgt = np.full(len(z), n_e * dz / ppc)                                   # slot = J dz  (pic.py: weights per unit area)
+    ux, uz = np.zeros(len(z)), np.zeros(len(z))
+    cell = np.clip(np.floor(z / dz).astype(np.int64), 0, L - 2).astype(np.int32)
+
+    def deposit(z, ux, uz, cell):           # pic_oracle.deposit's CIC definition, summed by bincount (order-free)
+        g = np.sqrt(1.0 + (ux * ux + uz * uz) / (C0 * C0))
+        wv = wgt * (ux / g)
+        f = z * (1.0 / dz) - cell
+        return Q * (np.bincount(cell, wv * (1.0 - f), L) + np.bincount(cell + 1, wv * f, L))
+    uxt = 1e3 * np.sin(np.arange(len(z)))   # the bincount deposit IS the oracle's deposit up to summation order
+    ref = po.deposit(z, uxt, uz, wgt, cell, L, dz=dz, c=C0, jx_scale=Q)      # (z is generated cell by cell: already sorted)
+    assert np.allclose(deposit(z, uxt, uz, cell), ref, rtol=0, atol=1e-14 * np.max(np.abs(ref)))
+    rec = np.zeros((steps - record_from, L))
+    for n in range(steps):
+        pa.Jx[:] = deposit(z, ux, uz, cell)
+        fo.lib().orc_run(ctypes.byref(pa.g), fo.MODE_ID["free"], 0, n, 1, c.T)
+        z, ux, uz, cell = po.push(z, ux, uz, pa.Ex, pa.Hy, dz=dz, dt=dt, q_over_m=QM, c=C0, mu0=MU0)
+        if n >= record_from:
+            rec[n - record_from] = pa.Ex
+    return rec, c, a
+
+
+def test_pic_model_reproduces_cold_plasma_dispersion():
+    """External cross-check of the builder-defined PIC model (push + CIC gather + CIC deposit + the Jx coupling): an
+    electromagnetic wave entering a cold electron plasma must obey the textbook dispersion relation
+    w^2 = wp^2 + c^2 k^2 -- not a property any single piece of the model has by construction.
+    Underdense (wp = 0.6 w): the wave number inside the plasma is k = (w/c) sqrt(1 - wp^2/w^2) = 0.8 w/c.
+    Overdense (wp = 1.5 w): the field is evanescent with decay constant kappa = (w/c) sqrt(wp^2/w^2 - 1)."""
+    steps, rec0 = 4200, 3000
+    # --- underdense: phase advance between two cells inside the plasma (forward wave only: half-space, absorbed in the CPML)
+    rec, c, a = _cold_plasma_run(0.6, steps, rec0)
+    w = 2 * np.pi * c.freq
+    t = (np.arange(rec0, steps) + 1) * c.dt
+    demod = np.exp(-1j * w * t) @ rec                    # complex amplitude of exp(+i w t) in every cell
+    phase = np.unwrap(np.angle(demod[a + 100: a + 600])) # forward wave exp(i(wt - kz)): the phase falls linearly with z
+    k_meas = -np.polyfit(np.arange(500) * c.dz, phase, 1)[0]
+    k_theory = (w / 299792458.0) * np.sqrt(1 - 0.36)
+    assert abs(k_meas / k_theory - 1) < 0.01, (k_meas, k_theory)
+    assert abs(k_meas / (w / 299792458.0) - 1) > 0.15    # ... and it is NOT the vacuum wave number
+    # --- overdense: exponential decay inside the plasma
+    rec, c, a = _cold_plasma_run(1.5, steps, rec0)
+    demod = np.abs(np.exp(-1j * w * t) @ rec)
+    q1, q2 = a + 40, a + 140
+    kappa_meas = np.log(demod[q1] / demod[q2]) / ((q2 - q1) * c.dz)
+    kappa_theory = (w / 299792458.0) * np.sqrt(2.25 - 1)
+    assert abs(kappa_meas / kappa_theory - 1) < 0.01, (kappa_meas, kappa_theory)
