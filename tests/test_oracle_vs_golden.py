@@ -360,3 +360,42 @@ def test_pic_model_reproduces_cold_plasma_dispersion():
     kappa_meas = np.log(demod[q1] / demod[q2]) / ((q2 - q1) * c.dz)
     kappa_theory = (w / 299792458.0) * np.sqrt(2.25 - 1)
     assert abs(kappa_meas / kappa_theory - 1) < 0.01, (kappa_meas, kappa_theory)
+
+
+def test_kerr_lorentz_composition_has_the_textbook_nonlinear_index():
+    """External cross-check of the builder-defined PF_LORENTZ_NL composition (Lorentz ADE + instantaneous Kerr law on
+    Dx - P): for a monochromatic field E0 cos(wt) the Kerr polarisation eps0 chi3 E^3 has the component
+    (3/4) eps0 chi3 E0^2 at w, i.e. the medium's effective permittivity is eps_L(w) + (3/4) chi3 |E|^2 -- the standard n2
+    result, which nothing in the cell-wise law states.  Measured: the extra phase lag a strong wave accumulates along the
+    slab relative to a weak one, against (w/c)^2 (3/4) chi3 / (2 k) * integral |E(z)|^2 dz with the measured amplitude."""
+    import ctypes
+    c = fo.make_case("lorentz_nl", 9e9, 0.3, 2500, 2600, source="sine", periods=1000)
+    wp = c.medium["wp"]
+    for _ in range(2):
+        wp, _ = fo.spatial_stab(c.Nz, c.dz, c.freq, c.dt, wp, c.medium["w0"], c.medium["gam"])
+    Exs, Hys = fo.sources(c)
+    probes = list(range(c.mf + 50, c.mf + 1900, 50))
+    assert probes[-1] < c.L - c.pw - 100
+    w = 2 * np.pi * c.freq
+    n0, N = c.T - 2600, 2527                                  # six periods (421.05 steps each), after the transient
+    win = np.hanning(N)
+    tt = (np.arange(n0, n0 + N) + 1) * c.dt
+    amps = {}
+    for amp in (0.01, 8.0):
+        pa = fo.PassArrays(c, wp, Exs * amp, Hys * amp, probes, False)
+        fo.lib().orc_run(ctypes.byref(pa.g), fo.MODE_ID["lorentz_nl"], 1, 0, c.T, c.T)
+        amps[amp] = (pa.probe_out[:, n0:n0 + N] * win) @ np.exp(-1j * w * tt) * (2.0 / win.sum())
+    lo, hi = amps[0.01] / 0.01, amps[8.0]
+    z = np.asarray(probes) * c.dz
+    k_lo = -np.polyfit(z, np.unwrap(np.angle(lo)), 1)[0]
+    assert 1.5 < k_lo / (w / 299792458.0) < 1.9                # Re n of the Lorentz medium at 9 GHz: ~1.70
+    E2 = np.abs(hi) ** 2
+    assert 25.0 < E2[0] < 60.0 and E2[-1] < 0.6 * E2[0]        # chi3 |E|^2 ~ 4 %, decaying with the linear absorption
+    dphi = np.unwrap(np.angle(hi / (lo * 8.0)))
+    lag = -(dphi - dphi[0])                                    # extra phase lag of the strong wave, from the first probe on
+    chi3 = c.medium["chi3"]
+    dk = (w / 299792458.0) ** 2 * 0.75 * chi3 * E2 / (2.0 * k_lo)
+    theory = np.concatenate([[0.0], np.cumsum(0.5 * (dk[1:] + dk[:-1]) * np.diff(z))])
+    assert lag[-1] > 0.05
+    assert abs(lag[-1] / theory[-1] - 1) < 0.02, (lag[-1], theory[-1])          # measured here: 0.9989
+    assert np.max(np.abs(lag - theory)) < 0.05 * theory[-1]
