@@ -81,8 +81,14 @@ enum {
     PF_F_FP32 = 32      /* optional single-precision mode of the tile engine: the on-chip state is
                            advanced in fp32 (contracted; Lorentz ADE in difference form, cubic root by
                            Newton iteration); the arrays in device memory stay fp64 and are converted at
-                           tile load / store.  Not a parity mode: stated tolerance 1e-5 of the trace
-                           peak.  PF_ENGINE_OPS rejects it (PF_E_UNSUPPORTED).                    */
+                           tile load / store.  Not a parity mode.  Stated tolerance: 1e-5 of the peak
+                           (fields: of their own peak; probe traces: of the peak of the probe traces)
+                           for runs of up to 8192 time steps, growing like sqrt(steps) beyond -- the
+                           single-precision rounding of the running fields is a random walk -- i.e.
+                           1.7e-5 at the reference's default 23997 steps (measured there: 5.6e-6 to
+                           1.3e-5), 2e-5 at its maximum 2^15.  Carrying the fields as float pairs would
+                           hold 1e-5 at any length but costs more than fp64 on this GPU (FP32 : FP64
+                           issue rate is 2 : 1).  PF_ENGINE_OPS rejects the flag (PF_E_UNSUPPORTED).  */
 };
 
 /* One 1-D grid: a single simulation, one sweep member, or one rank's slab of a long grid.
@@ -196,6 +202,38 @@ int pf_cubic_root0_newton(const double *coeffs, double *root0, int n, void *stre
 /* every root, as CubicEquationSolver.solve returns them: roots = [n][3][2] (re, im) device,
  * nroots = [n] device (1 linear, 2 quadratic, 3 cubic)                                          */
 int pf_cubic_solve(const double *coeffs, double *roots, int *nroots, int n, void *stream);
+
+/* ---- dormant models of the reference: leaf functions no reference integrator calls ------------
+ * One call = one reference leaf function on one grid, bit-identical to the Python / numba original.  Pointers are device
+ * arrays of length L (Nz+1 here; the reference allocates these members with Nz entries and only touches [mf, mr)).     */
+typedef struct PfDormant {
+    int32_t L, mf, mr, reserved0;
+    double eps0, dt;
+    double chi1, chi3, alpha3, one_minus_alpha3;  /* V.chi1Stat, V.chi3Stat, V.alpha3 (float32 member), 1 - V.alpha3        */
+    double lin_AoverD, lin_BoverD;   /* (1-G)/(1+G), w0^2 dt/(1+G), G = gammaE dt/2          BaseFDTD11.py:583-586       */
+    double ram_eoverf, ram_hoverf;   /* same with nonLin3gammaE / nonLin3Omega_0E            BaseFDTD11.py:598-601       */
+    double kerr_coef;                /* (alpha3 eps0 chi3)/dt                                BaseFDTD11.py:765           */
+    double mur_mult;                 /* (c0 dt - dz)/(c0 dt + dz)                            BaseFDTD11.py:771           */
+    double *Ex;                      /* V.Ex            (MUR1DEx writes it)                                             */
+    const double *Eold;              /* V.tempTempVarE  (KerrNonlin, MUR1DEx)                                           */
+    double *Jx, *P, *Pbar3, *Qx3, *Gx3, *JxKerr;   /* V.Jx, V.polarisationCurr, V.Pbar3, V.Qx3, V.Gx3, V.JxKerr         */
+} PfDormant;
+int pf_varin_pbar(const PfDormant *d, void *stream);          /* BaseFDTD11.py:567-577  ADE_NonLin_Pol_Ex_Pbar       */
+int pf_varin_lin_curr_pol(const PfDormant *d, void *stream);  /* BaseFDTD11.py:580-594  ADE_Lin_Curr_And_Pol_Varin   */
+int pf_varin_q_and_g(const PfDormant *d, void *stream);       /* BaseFDTD11.py:596-609  ADE_Nonlin_Q_and_G           */
+int pf_kerr_nonlin(const PfDormant *d, void *stream);         /* BaseFDTD11.py:762-766  KerrNonlin                   */
+int pf_mur1d_ex(const PfDormant *d, void *stream);            /* BaseFDTD11.py:769-788  MUR1DEx                      */
+
+/* The Drude medium in current (J) form as the reference steps it in its scratch script (TESTBOXDIPSERSE.py:79-94): vacuum
+ * H update, J update inside [mat_front, mat_rear), E update of every cell with the J term (Hy[-1] wraps for cell 0, as the
+ * Python does), hard source Ex[src] = Hys[i]; no PML.  Steps i0 .. i0+nsteps-1.                                        */
+typedef struct PfDrudeJ {
+    int32_t n, src, mat_front, mat_rear, n_src, reserved0;
+    double inv_cour, kapE, betaE, c_self, c_curl, half_one_plus_kap;
+    double *Ex, *Hy, *Jx, *tempE, *tempEOld;
+    const double *Hys;
+} PfDrudeJ;
+int pf_drude_j_run(const PfDrudeJ *d, int i0, int nsteps, void *stream);
 
 /* ---- integrator passes ------------------------------------------------------------------ */
 /* One pass of `nsteps` steps starting at absolute step n0 on ONE grid: the body of the

@@ -326,3 +326,67 @@ int orc_run_batch(OrcGrid *grids, int n_members, int mode, int do_pol, int n0, i
 }
 
 size_t orc_sizeof_grid(void) { return sizeof(OrcGrid); }
+
+/* ---- dormant models: leaf functions of the reference that no integrator calls -------------------- */
+/* BaseFDTD11.py:567-577  ADE_NonLin_Pol_Ex_Pbar (Varin: linear + instantaneous Kerr + Raman polarisation target) */
+void orc_varin_pbar(int mf, int mr, double eps0, double chi1, double chi3, double alpha3, const double *Ex, const double *Qx3,
+                    double *Pbar3)
+{
+    for (int nz = mf; nz < mr; ++nz)
+        Pbar3[nz] = eps0 * (chi1 * Ex[nz] + chi3 * (alpha3 * Ex[nz] * Ex[nz] * Ex[nz] + (1 - alpha3) * Qx3[nz] * Ex[nz]));
+}
+/* BaseFDTD11.py:580-594  ADE_Lin_Curr_And_Pol_Varin */
+void orc_varin_lin(int mf, int mr, double gammaE, double omega0, double dt, double *Jx, double *P, const double *Pbar3)
+{
+    double Gamma = (gammaE * dt) / 2, A = 1 - Gamma, D = 1 + Gamma, B = omega0 * omega0 * dt;
+    for (int nz = mf; nz < mr; ++nz) {
+        Jx[nz] = (A / D) * Jx[nz] + (B / D) * (Pbar3[nz] - P[nz]);
+        P[nz] = P[nz] + dt * Jx[nz];
+    }
+}
+/* BaseFDTD11.py:596-609  ADE_Nonlin_Q_and_G (Raman oscillator) */
+void orc_varin_qg(int mf, int mr, double gamma3, double omega3, double dt, const double *Ex, double *Gx3, double *Qx3)
+{
+    double Gamma = (gamma3 * dt) / 2, e = 1 - Gamma, f = 1 + Gamma, h = omega3 * omega3 * dt;
+    for (int nz = mf; nz < mr; ++nz) {
+        Gx3[nz] = (e / f) * Gx3[nz] + (h / f) * (Ex[nz] * Ex[nz] - Qx3[nz]);
+        Qx3[nz] = Qx3[nz] + dt * Gx3[nz];
+    }
+}
+/* BaseFDTD11.py:762-766  KerrNonlin */
+void orc_kerr_nonlin(int n, double alpha3, double eps0, double chi3, double dt, const double *Ex, const double *Eold, double *JxKerr)
+{
+    double coef = (alpha3 * eps0 * chi3) / dt;
+    for (int nz = 0; nz < n; ++nz) {
+        double ae = fabs(Ex[nz]), ao = fabs(Eold[nz]);
+        JxKerr[nz] = coef * (ae * ae * Ex[nz] - ao * ao * Eold[nz]);
+    }
+}
+/* BaseFDTD11.py:769-788  MUR1DEx */
+void orc_mur1d(int Nz, double c0, double dt, double dz, double *Ex, const double *Eold)
+{
+    double m = (c0 * dt - dz) / (c0 * dt + dz);
+    for (int nz = 1; nz < 5; ++nz)
+        Ex[nz] = Eold[nz + 1] + m * (Ex[nz + 1] - Eold[nz]);
+    for (int nz = Nz - 1; nz > Nz - 6; --nz)
+        Ex[nz] = Eold[nz - 1] + m * (Ex[nz - 1] - Eold[nz]);
+}
+/* TESTBOXDIPSERSE.py:79-94: the Drude J-form loop as written (Hy[nz-1] of cell 0 is Python's Hy[-1]) */
+void orc_drude_j(int n, int tim, int src, int mat_front, int mat_rear, double cour, double kapE, double betaE, double perm0,
+                 double dt, const double *Hys, double *Ex, double *Hy, double *Jx, double *tempE, double *tempEOld)
+{
+    for (int i = 0; i < tim; ++i) {
+        for (int nz = 0; nz < n - 1; ++nz)
+            Hy[nz] = Hy[nz] + (Ex[nz + 1] - Ex[nz]) * (1 / cour);
+        for (int nz = mat_front; nz < mat_rear; ++nz)
+            Jx[nz] = (kapE * Jx[nz] + betaE * (Ex[nz] + tempEOld[nz])) * (1 / cour);
+        for (int nz = 0; nz < n; ++nz) {
+            tempEOld[nz] = tempE[nz];
+            tempE[nz] = Ex[nz];
+            double hl = Hy[nz == 0 ? n - 1 : nz - 1];
+            Ex[nz] = ((2 * perm0 - betaE * dt) / (2 * perm0 + betaE * dt)) * Ex[nz]
+                     + (Hy[nz] - hl - 0.5 * (1 + kapE) * Jx[nz]) * ((2 * dt) / (2 * perm0 + betaE * dt)) * (1 / cour);
+        }
+        Ex[src] = Hys[i];
+    }
+}

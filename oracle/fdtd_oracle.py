@@ -452,3 +452,61 @@ def analytical_reflection(freq, wp, w0, gam):
     """BaseFDTD11.AnalyticalReflectionE :882-923 (returned value only)."""
     refr2 = np.real(np.sqrt(lorentz_eps(wp, w0, gam, freq)))
     return float(abs((refr2 - 1) / (1 + refr2)))
+
+
+# ----------------------------------------------------------------------------- dormant models (SURVEY 8(f) row 4)
+def _cd(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def varin_pbar(mf, mr, eps0, chi1, chi3, alpha3, Ex, Qx3, Pbar3):
+    """BaseFDTD11.py:567-577 ADE_NonLin_Pol_Ex_Pbar (in place on Pbar3)."""
+    f = lib().orc_varin_pbar
+    f.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 4 + [ctypes.POINTER(ctypes.c_double)] * 3
+    f.restype = None
+    f(int(mf), int(mr), eps0, chi1, chi3, alpha3, _cd(Ex), _cd(Qx3), _cd(Pbar3))
+
+
+def varin_lin(mf, mr, gammaE, omega0, dt, Jx, P, Pbar3):
+    """BaseFDTD11.py:580-594 ADE_Lin_Curr_And_Pol_Varin (in place on Jx, P)."""
+    f = lib().orc_varin_lin
+    f.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 3 + [ctypes.POINTER(ctypes.c_double)] * 3
+    f.restype = None
+    f(int(mf), int(mr), gammaE, omega0, dt, _cd(Jx), _cd(P), _cd(Pbar3))
+
+
+def varin_qg(mf, mr, gamma3, omega3, dt, Ex, Gx3, Qx3):
+    """BaseFDTD11.py:596-609 ADE_Nonlin_Q_and_G (in place on Gx3, Qx3)."""
+    f = lib().orc_varin_qg
+    f.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 3 + [ctypes.POINTER(ctypes.c_double)] * 3
+    f.restype = None
+    f(int(mf), int(mr), gamma3, omega3, dt, _cd(Ex), _cd(Gx3), _cd(Qx3))
+
+
+def kerr_nonlin(alpha3, eps0, chi3, dt, Ex, Eold, JxKerr):
+    """BaseFDTD11.py:762-766 KerrNonlin (in place on JxKerr)."""
+    f = lib().orc_kerr_nonlin
+    f.argtypes = [ctypes.c_int] + [ctypes.c_double] * 4 + [ctypes.POINTER(ctypes.c_double)] * 3
+    f.restype = None
+    f(len(Ex), alpha3, eps0, chi3, dt, _cd(Ex), _cd(Eold), _cd(JxKerr))
+
+
+def mur1d(Nz, c0, dt, dz, Ex, Eold):
+    """BaseFDTD11.py:769-788 MUR1DEx (in place on Ex)."""
+    f = lib().orc_mur1d
+    f.argtypes = [ctypes.c_int] + [ctypes.c_double] * 3 + [ctypes.POINTER(ctypes.c_double)] * 2
+    f.restype = None
+    f(int(Nz), c0, dt, dz, _cd(Ex), _cd(Eold))
+
+
+def drude_j(k):
+    """TESTBOXDIPSERSE.py:79-94 for the constants dict of pyfdtd_b200.drude_sandbox.constants(); returns (Ex, Hy, Jx)."""
+    n = int(k["domain"])
+    Ex, Hy, Jx, tE, tEo = (np.zeros(n) for _ in range(5))
+    Hys = np.ascontiguousarray(k["Hys"], dtype=np.float64)
+    f = lib().orc_drude_j
+    f.argtypes = [ctypes.c_int] * 5 + [ctypes.c_double] * 5 + [ctypes.POINTER(ctypes.c_double)] * 6
+    f.restype = None
+    f(n, int(k["tim"]), int(k["src"]), int(k["matFront"]), int(k["matRear"]), k["cour"], k["kapE"], k["betaE"], k["perm0"],
+      k["dt"], _cd(Hys), _cd(Ex), _cd(Hy), _cd(Jx), _cd(tE), _cd(tEo))
+    return Ex, Hy, Jx

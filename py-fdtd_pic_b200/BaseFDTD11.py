@@ -406,3 +406,68 @@ class _NullCpml:
         z = np.zeros(L)
         self.psi_Ex = self.psi_Hy = self.beX = self.ceX = self.Cb = self.bmY = self.cmY = self.C2 = z
         self.den_Exdz = self.den_Hydz = np.ones(L)
+
+
+# ------------------------------------------------------------------------------------------------ dormant models
+# Leaf functions the reference defines but none of its integrators calls: Varin's explicit Kerr + Raman
+# ADE, the Kerr current, the first-order Mur boundary.  Same names, arguments and return values; each is one sm_100a kernel
+# (csrc/pf_dormant.cu) through the C-ABI, bit-identical to the reference function (tests/golden/dormant_leaf_ops.npz).
+_DORMANT_ARRAYS = (("Ex", "Ex"), ("Eold", "tempTempVarE"), ("Jx", "Jx"), ("P", "polarisationCurr"), ("Pbar3", "Pbar3"),
+                   ("Qx3", "Qx3"), ("Gx3", "Gx3"), ("JxKerr", "JxKerr"))
+
+
+def _dormant(V, P, fn_name, out_fields):
+    torch = nat.require_cuda()
+    L = len(V.Ex)
+    d = nat.PfDormant()
+    d.L, d.mf, d.mr = L, int(P.materialFrontEdge), int(P.materialRearEdge)
+    d.eps0, d.dt = P.permit_0, P.delT
+    d.chi1, d.chi3, d.alpha3, d.one_minus_alpha3 = V.chi1Stat, V.chi3Stat, V.alpha3, 1 - V.alpha3
+    Gamma = (V.gammaE * P.delT) / 2
+    d.lin_AoverD, d.lin_BoverD = (1 - Gamma) / (1 + Gamma), (V.omega_0E * V.omega_0E * P.delT) / (1 + Gamma)
+    Gamma3 = (V.nonLin3gammaE * P.delT) / 2
+    d.ram_eoverf = (1 - Gamma3) / (1 + Gamma3)
+    d.ram_hoverf = (V.nonLin3Omega_0E * V.nonLin3Omega_0E * P.delT) / (1 + Gamma3)
+    d.kerr_coef = (V.alpha3 * P.permit_0 * V.chi3Stat) / P.delT
+    d.mur_mult = (P.c0 * P.delT - P.dz) / (P.c0 * P.delT + P.dz)
+    keep = {}
+    for field, attr in _DORMANT_ARRAYS:
+        a = np.zeros(L)
+        src = np.asarray(getattr(V, attr), dtype=np.float64)
+        a[: min(L, len(src))] = src[:L]
+        keep[field] = torch.as_tensor(a, device="cuda")
+        setattr(d, field, keep[field].data_ptr())
+    import ctypes
+    nat.check(getattr(nat.lib(), fn_name)(ctypes.byref(d), nat.current_stream_ptr()), fn_name)
+    out = []
+    for field, attr in _DORMANT_ARRAYS:
+        if attr in out_fields:
+            n = len(getattr(V, attr))
+            setattr(V, attr, keep[field].cpu().numpy()[:n].copy())
+    return tuple(getattr(V, a) for a in out_fields)
+
+
+def ADE_NonLin_Pol_Ex_Pbar(V, P):
+    """BaseFDTD11.py:567-577 (Varin: explicit second/third-order nonlinearity) -> pf_varin_pbar."""
+    return _dormant(V, P, "pf_varin_pbar", ("Pbar3",))[0]
+
+
+def ADE_Lin_Curr_And_Pol_Varin(V, P):
+    """BaseFDTD11.py:580-594 -> pf_varin_lin_curr_pol."""
+    return _dormant(V, P, "pf_varin_lin_curr_pol", ("Jx", "polarisationCurr"))
+
+
+def ADE_Nonlin_Q_and_G(V, P):
+    """BaseFDTD11.py:596-609 (Raman oscillator) -> pf_varin_q_and_g."""
+    G, Q = _dormant(V, P, "pf_varin_q_and_g", ("Gx3", "Qx3"))
+    return G, Q, V.Ex
+
+
+def KerrNonlin(V, P, counts=0):
+    """BaseFDTD11.py:762-766 -> pf_kerr_nonlin."""
+    return _dormant(V, P, "pf_kerr_nonlin", ("JxKerr",))[0]
+
+
+def MUR1DEx(V, P, C_V=None, C_P=None):
+    """BaseFDTD11.py:769-788 (first-order Mur absorbing boundary on both ends) -> pf_mur1d_ex."""
+    return _dormant(V, P, "pf_mur1d_ex", ("Ex",))[0]

@@ -55,6 +55,28 @@ class PfPic(ctypes.Structure):
     ]
 
 
+class PfDormant(ctypes.Structure):
+    """Mirror of ``struct PfDormant``."""
+    _fields_ = [
+        ("L", c_int32), ("mf", c_int32), ("mr", c_int32), ("reserved0", c_int32),
+        ("eps0", c_double), ("dt", c_double),
+        ("chi1", c_double), ("chi3", c_double), ("alpha3", c_double), ("one_minus_alpha3", c_double),
+        ("lin_AoverD", c_double), ("lin_BoverD", c_double), ("ram_eoverf", c_double), ("ram_hoverf", c_double),
+        ("kerr_coef", c_double), ("mur_mult", c_double),
+        ("Ex", _dp), ("Eold", _dp), ("Jx", _dp), ("P", _dp), ("Pbar3", _dp), ("Qx3", _dp), ("Gx3", _dp), ("JxKerr", _dp),
+    ]
+
+
+class PfDrudeJ(ctypes.Structure):
+    """Mirror of ``struct PfDrudeJ``."""
+    _fields_ = [
+        ("n", c_int32), ("src", c_int32), ("mat_front", c_int32), ("mat_rear", c_int32), ("n_src", c_int32), ("reserved0", c_int32),
+        ("inv_cour", c_double), ("kapE", c_double), ("betaE", c_double), ("c_self", c_double), ("c_curl", c_double),
+        ("half_one_plus_kap", c_double),
+        ("Ex", _dp), ("Hy", _dp), ("Jx", _dp), ("tempE", _dp), ("tempEOld", _dp), ("Hys", _dp),
+    ]
+
+
 class PfSetupMember(ctypes.Structure):
     """Mirror of ``struct PfSetupMember``."""
     _fields_ = [
@@ -95,6 +117,12 @@ SYMBOLS = {
     "pf_cubic_root0": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "pf_cubic_root0_newton": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "pf_cubic_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pf_varin_pbar": (c_int, [POINTER(PfDormant), c_void_p]),
+    "pf_varin_lin_curr_pol": (c_int, [POINTER(PfDormant), c_void_p]),
+    "pf_varin_q_and_g": (c_int, [POINTER(PfDormant), c_void_p]),
+    "pf_kerr_nonlin": (c_int, [POINTER(PfDormant), c_void_p]),
+    "pf_mur1d_ex": (c_int, [POINTER(PfDormant), c_void_p]),
+    "pf_drude_j_run": (c_int, [POINTER(PfDrudeJ), c_int, c_int, c_void_p]),
     "pf_run_pass": (c_int, [_G, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_batch": (c_int, [_G, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_size_t, c_void_p]),
     "pf_run_scratch_bytes": (c_size_t, [_G, c_int, c_int]),

@@ -593,6 +593,34 @@ def test_fp32_mode_within_stated_tolerance(pk, name):
     assert not np.array_equal(V.Ex, g["Ex"])      # it really is a different arithmetic
 
 
+def fp32_tol(steps):
+    """The tolerance PF_F_FP32 is stated with (include/pyfdtd_b200.h): 1e-5 of the peak up to 8192 time steps, growing like
+    sqrt(steps) beyond (single-precision rounding of the running fields is a random walk)."""
+    return FP32_TOL * max(1.0, (steps / 8192.0) ** 0.5)
+
+
+@pytest.mark.parametrize("name", ["lorentz_default_full", "free_default_full"])
+def test_fp32_mode_full_length_default_geometry(pk, name):
+    """PF_F_FP32 on the reference's default geometry (Nz = 13193, 2 x 23997 steps): fields within the stated tolerance of
+    their own peak, probe traces within it of the peak of the probe traces (x1ColAf is a scattered-field trace a third the
+    size of the incident one).  Measured: Ex / Hy 5.6e-6 (Lorentz), 9.8e-6 / 1.3e-5 (free); bound at 23997 steps 1.7e-5."""
+    g = load_golden(name)
+    pk.SE.USE_FP32 = True
+    try:
+        V, P, C_V, C_P = pk.build_objects(g["spec"])
+        V, P, C_V, C_P, Exs, Hys = pk.MC.Controller(V, P, C_V, C_P)
+    finally:
+        pk.SE.USE_FP32 = False
+    tol = fp32_tol(P.timeSteps)
+    assert 1.5e-5 < tol < 2e-5
+    for nm, got in (("Ex", V.Ex), ("Hy", V.Hy)):
+        assert rel_err(got, g[nm]) <= tol, (nm, rel_err(got, g[nm]))
+    trace_peak = max(np.max(np.abs(g["x1ColBe"])), np.max(np.abs(g["x1ColAf"])))
+    for nm, got in (("x1ColBe", V.x1ColBe), ("x1ColAf", V.x1ColAf)):
+        err = float(np.max(np.abs(got - g[nm])) / trace_peak)
+        assert err <= tol, (nm, err)
+
+
 def test_fp32_mode_is_rejected_by_the_per_op_engine(pk):
     g = load_golden("lorentz_sine")
     pk.SE.USE_FP32, pk.SE.ENGINE = True, "ops"

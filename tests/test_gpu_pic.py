@@ -232,7 +232,8 @@ def test_beam_inside_the_medium_drives_the_fields(pic, mode, engine):
     L = len(V.Ex)
     z, ux, uz, w, cell = po.make_beam(30_000, L, P.dz, seed=7)              # uniform over 5 % .. 95 % of the grid: most of it in the slab
     ux = ux + 5e7
-    w = w * 1e3
+    w = w * 1e-2            # beam-driven |Ex| ~ 10 V/m in the slab: the amplitude range of the nonlinear sweeps (at 1e6 V/m the
+                            # closed-form cubic is ill-conditioned at 1e-9 between any two libm implementations)
     assert np.sum((z / P.dz > P.materialFrontEdge) & (z / P.dz < P.materialRearEdge)) > 10_000
     ps = pic.ParticleSet(z, ux, uz, w, L, P.dz, P.delT)
     g = pic.coupled_grid(V, P, C_V, C_P, Exs, Hys, mode=mode)

@@ -63,7 +63,10 @@ def test_table_batch_is_bit_identical_to_member_batch(pk):
 
 def test_reflection_sweep_equals_the_per_member_two_pass_batch(pk):
     freqs = np.linspace(6e9, 10.5e9, 7)
-    objs = _objs(pk, freqs, 1.0)
+    DOM, WIN = 0.3, (2000, 2200)          # the geometry of the reference's sweep golden: long enough for the reflection to return
+    objs = []
+    for f in freqs:
+        objs.append(pk.build_objects(dict(mode="lorentz", freq=float(f), dom=DOM, win=WIN, source="sine", periods=1.0)))
     _, _, want = pk.sweep.run_two_pass_batch(objs, lorentz=True, device_reflection=True)
     got = pk.sweep.reflection_sweep(freqs, DOM, *WIN, periods=1.0, chunk=3)       # 3 chunks: 3 + 3 + 1 members
     assert np.array_equal(got["measured"], want)

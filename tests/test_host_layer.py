@@ -152,13 +152,17 @@ def test_library_exports_every_header_symbol():
 def test_ctypes_structs_match_header(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pyfdtd_b200.h"\n'
-                   'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(PfGrid), offsetof(PfGrid, Ex), '
-                   'offsetof(PfGrid, probe_out), sizeof(PfPic), offsetof(PfPic, z), offsetof(PfPic, Jx));return 0;}\n')
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PfGrid), offsetof(PfGrid, Ex), '
+                   'offsetof(PfGrid, probe_out), sizeof(PfPic), offsetof(PfPic, z), offsetof(PfPic, Jx), '
+                   'sizeof(PfSetupMember), offsetof(PfSetupMember, off_srcH), sizeof(PfDormant), offsetof(PfDormant, JxKerr), '
+                   'sizeof(PfDrudeJ), offsetof(PfDrudeJ, Hys));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = list(map(int, subprocess.check_output([str(exe)]).split()))
     want = [ctypes.sizeof(nat.PfGrid), nat.PfGrid.Ex.offset, nat.PfGrid.probe_out.offset,
-            ctypes.sizeof(nat.PfPic), nat.PfPic.z.offset, nat.PfPic.Jx.offset]
+            ctypes.sizeof(nat.PfPic), nat.PfPic.z.offset, nat.PfPic.Jx.offset,
+            ctypes.sizeof(nat.PfSetupMember), nat.PfSetupMember.off_srcH.offset, ctypes.sizeof(nat.PfDormant),
+            nat.PfDormant.JxKerr.offset, ctypes.sizeof(nat.PfDrudeJ), nat.PfDrudeJ.Hys.offset]
     assert got == want
 
 

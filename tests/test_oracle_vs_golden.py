@@ -399,3 +399,48 @@ def test_kerr_lorentz_composition_has_the_textbook_nonlinear_index():
     assert lag[-1] > 0.05
     assert abs(lag[-1] / theory[-1] - 1) < 0.02, (lag[-1], theory[-1])          # measured here: 0.9989
     assert np.max(np.abs(lag - theory)) < 0.05 * theory[-1]
+
+
+# ------------------------------------------------------------------------------------------------ dormant models
+def _dormant_golden():
+    import ast
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dormant_leaf_ops.npz"), allow_pickle=False)
+    return g, ast.literal_eval(str(g["scalars"]))
+
+
+def test_oracle_reproduces_the_reference_dormant_leaf_functions():
+    """Varin Kerr + Raman ADE, Kerr current and Mur ABC (BaseFDTD11.py:567-609, 762-788): the C restatement against the
+    outputs of the unmodified reference functions (oracle/make_dormant_golden.py), three chained rounds, bit for bit."""
+    g, k = _dormant_golden()
+    Ex, Eold = g["in_Ex"].copy(), g["in_tempTempVarE"].copy()
+    Q, G, J, Pol, Pbar = (g[f"in_{n}"].copy() for n in ("Qx3", "Gx3", "Jx", "polarisationCurr", "Pbar3"))
+    for r in range(3):
+        fo.varin_pbar(k["mf"], k["mr"], k["permit_0"], k["chi1Stat"], k["chi3Stat"], k["alpha3"], Ex, Q, Pbar)
+        assert np.array_equal(Pbar, g[f"r{r}_Pbar3"]), r
+        fo.varin_lin(k["mf"], k["mr"], k["gammaE"], k["omega_0E"], k["delT"], J, Pol, Pbar)
+        assert np.array_equal(J, g[f"r{r}_Jx"]) and np.array_equal(Pol, g[f"r{r}_P"]), r
+        fo.varin_qg(k["mf"], k["mr"], k["nonLin3gammaE"], k["nonLin3Omega_0E"], k["delT"], Ex, G, Q)
+        assert np.array_equal(G, g[f"r{r}_Gx3"]) and np.array_equal(Q, g[f"r{r}_Qx3"]), r
+        JK = np.zeros(len(Ex))
+        fo.kerr_nonlin(k["alpha3"], k["permit_0"], k["chi3Stat"], k["delT"], Ex, Eold, JK)
+        assert np.array_equal(JK, g[f"r{r}_JxKerr"]), r
+        fo.mur1d(k["Nz"], k["c0"], k["delT"], k["dz"], Ex, Eold)
+        assert np.array_equal(Ex, g[f"r{r}_Ex"]), r
+        Eold = Eold * 0.5 + 0.25 * Ex
+        assert np.array_equal(Eold, g[f"r{r}_Eold_next"])
+    assert np.max(np.abs(g["r2_Pbar3"])) > 0 and np.max(np.abs(g["r2_JxKerr"])) > 0
+
+
+def test_oracle_reproduces_the_reference_drude_scratch_script():
+    """TESTBOXDIPSERSE.py:79-94 (Drude medium in J form, hard source, no PML) stepped as written: the C restatement against
+    the arrays the unmodified script text leaves behind (sizes substituted; the scheme is unstable, see make_dormant_golden)."""
+    import pyfdtd_b200  # noqa: F401
+    from pyfdtd_b200 import drude_sandbox
+    g = np.load(os.path.join(ROOT, "tests", "golden", "drude_sandbox.npz"), allow_pickle=False)
+    k = drude_sandbox.constants(int(g["domain"]), int(g["tim"]), float(g["freq"]), int(g["nl"]), int(g["src"]), int(g["matFront"]))
+    for name in ("dz", "dt", "cour", "betaE", "kapE", "perm0"):
+        assert k[name] == float(g[name]), name                      # the host mirror of the script's constants
+    assert np.array_equal(k["Hys"], g["Hys"])
+    Ex, Hy, Jx = fo.drude_j(k)
+    assert np.array_equal(Ex, g["Ex"]) and np.array_equal(Hy, g["Hy"]) and np.array_equal(Jx, g["Jx"])
+    assert np.all(np.isfinite(Ex)) and np.max(np.abs(Jx)) > 0

@@ -16,12 +16,12 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 freqs = np.linspace(6e9, 10.5e9, 13)
-mine = sweep.reflection_sweep(freqs, 0.15, 300, 320, periods=1.0, rank=rank, world_size=world)
+mine = sweep.reflection_sweep(freqs, 0.3, 2000, 2200, periods=1.0, rank=rank, world_size=world)
 parts = [None] * world
 dist.all_gather_object(parts, (mine["index"], mine["measured"]))
 ok = True
 if rank == 0:
-    full = sweep.reflection_sweep(freqs, 0.15, 300, 320, periods=1.0)
+    full = sweep.reflection_sweep(freqs, 0.3, 2000, 2200, periods=1.0)
     got = np.empty(len(freqs))
     for idx, val in parts:
         got[idx] = val
