@@ -69,7 +69,9 @@ def test_reflection_sweep_equals_the_per_member_two_pass_batch(pk):
         objs.append(pk.build_objects(dict(mode="lorentz", freq=float(f), dom=DOM, win=WIN, source="sine", periods=1.0)))
     _, _, want = pk.sweep.run_two_pass_batch(objs, lorentz=True, device_reflection=True)
     got = pk.sweep.reflection_sweep(freqs, DOM, *WIN, periods=1.0, chunk=3)       # 3 chunks: 3 + 3 + 1 members
-    assert np.array_equal(got["measured"], want)
+    # the time stepping is bit-identical (test above); the reflection figure goes through a batched cuFFT whose plan -- and with
+    # it the last bit of the peak magnitude -- depends on the batch size and stride, so the two routes agree to an ulp
+    np.testing.assert_allclose(got["measured"], want, rtol=1e-13, atol=0)
     assert list(got["index"]) == list(range(7)) and got["cell_steps"] > 0
     # the analytical figure is results(AnalRefCo=True) with the medium as the two passes leave it
     for i, (V, P, C_V, C_P) in enumerate(objs):
@@ -77,7 +79,8 @@ def test_reflection_sweep_equals_the_per_member_two_pass_batch(pk):
     # sharded over two ranks: same numbers, dealt round-robin
     r0 = pk.sweep.reflection_sweep(freqs, DOM, *WIN, periods=1.0, rank=0, world_size=2)
     r1 = pk.sweep.reflection_sweep(freqs, DOM, *WIN, periods=1.0, rank=1, world_size=2)
-    assert np.array_equal(r0["measured"], want[0::2]) and np.array_equal(r1["measured"], want[1::2])
+    np.testing.assert_allclose(r0["measured"], want[0::2], rtol=1e-13, atol=0)
+    np.testing.assert_allclose(r1["measured"], want[1::2], rtol=1e-13, atol=0)
     assert 0.0 < got["measured"].min() and got["measured"].max() < 1.0
 
 

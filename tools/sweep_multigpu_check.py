@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run under torchrun on N GPUs: sweep.reflection_sweep sharded over the ranks (member % N == rank, no data-path
-collective) must give exactly the numbers of the unsharded sweep (rank 0 runs that too and compares)."""
+collective) must give the numbers of the unsharded sweep (to an ulp of the cuFFT reduction) (rank 0 runs that too and compares)."""
 import os
 import sys
 
@@ -25,7 +25,8 @@ if rank == 0:
     got = np.empty(len(freqs))
     for idx, val in parts:
         got[idx] = val
-    ok = bool(np.array_equal(got, full["measured"]))
+    # (cuFFT's plan depends on the batch size: the reflection figure agrees to an ulp, the time stepping is bit-identical)
+    ok = bool(np.allclose(got, full["measured"], rtol=1e-13, atol=0))
     print(f"world={world} sharded == unsharded: {ok}  max |diff| = {np.max(np.abs(got - full['measured'])):.3e}", flush=True)
     if not ok:
         print("sharded  ", got, "\nunsharded", full["measured"], flush=True)
