@@ -105,17 +105,28 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_push(PfPic p, PicDerived D)
 }
 
 // ------------------------------------------------------------------------------------------------ fused push + re-sort
-// A particle moves less than one cell per step (|v| dt < c dt = 0.95 dz), so a cell-sorted set stays
-// sorted up to exchanges between neighbouring cells.  The stable sort by new cell is then a counting
-// problem: the new population of cell c is [right-movers of c-1][stayers of c][left-movers of c+1], each
-// group in its old order.  Two passes, one warp per (old) cell, no radix sort, no gather:
-//   count : push the cell's particles, store them in place (old order), count left / stay / right
-//                                                                                      (reads 24 B, writes 24 B)
-//   scan  : new_start = exclusive scan of nR[c-1] + nS[c] + nL[c+1]
-//   move  : re-derive each pushed particle's cell from its z, rank by ballot in index order, write it
-//           straight to its final slot of the alternate arrays                         (reads 32 B, writes 36 B)
-// (pushing twice instead of storing saves 24 B of traffic per particle but doubles the fp64 work of the
-//  push, ~190 instructions with its two square roots and three divisions: measured slower)
+// A particle moves less than one cell per step (|v| dt < c dt = 0.95 dz), so a cell-sorted set stays sorted up to
+// exchanges between neighbouring cells.  The stable sort by new cell is then a LOCAL problem: the new population of cell c
+// is [right-movers of c-1][stayers of c][left-movers of c+1], each group in its old order, and with L(c), R(c) the numbers
+// of left- / right-movers of old cell c the new offsets follow from the old ones by boundary flows alone,
+//     new_start[c] = start[c] - R(c-1) + L(c),
+// so the first slot of each group needs only the counts of the cells c-1, c, c+1 -- no global scan:
+//     stayers of c      : start[c] + L(c)                   left-movers of c : start[c] - R(c-1)
+//     right-movers of c : start[c+1] - R(c) + L(c+1)        (plus, inside a cell, the counts of its earlier pieces).
+//
+// ONE pass over the particles (k_pic_step1).  A cell is cut into S contiguous pieces (sub_range), one warp per piece:
+//   1. push the piece's particles and keep them in REGISTERS (PIC_K = 8 per lane: z, ux, uz, w), counting
+//      left / stay / right by ballot;
+//   2. publish the three counts as one 64-bit word (valid bit + 3 x 20 bits; the words are zeroed before the launch);
+//   3. wait for the words of every piece of the cells c-1, c, c+1 (lanes poll in parallel), derive the offsets;
+//   4. write every particle straight to its final slot of the alternate arrays -- and, DEP = true, accumulate its CIC
+//      shares (pf_pic_step_sorted: deposition of the new state while it is in registers).
+// HBM traffic: 32 B read + 36 B written per particle-step (the two-pass version of round 1 stored the pushed state between
+// its passes: 116 B).  Pieces longer than 32 PIC_K particles (a cell far above the average population) keep the old
+// behaviour inside the same kernel: pushed state stored in place, re-read for placement.
+// The grid is persistent (every CTA resident, pieces dealt round-robin to warps): a warp waits only for publications, and
+// every warp publishes before it waits, so the wait graph has no cycle (a piece's neighbours are at most 2 S pieces away,
+// far less than the number of warps in flight, so no warp ever waits for a piece of its own next round).
 __global__ void __launch_bounds__(PIC_THREADS) k_pic_cell_start(const int *__restrict__ cell, long long n, int L,
                                                                 long long *__restrict__ start)
 {
@@ -137,173 +148,191 @@ __device__ __forceinline__ void sub_range(long long a, long long b, int S, int s
     hi = min(b, lo + q);
 }
 
-// sum of one of the three counters of cell c over its S sub-warps
-__device__ __forceinline__ int cell_count(const int *__restrict__ counts, int S, int c, int k)
+constexpr int PIC_K = 8;                      // particles per lane a piece holds in registers
+constexpr unsigned long long PUB_VALID = 1ull << 63;
+constexpr int PUB_BITS = 20, PUB_MASK = (1 << PUB_BITS) - 1;
+
+__device__ __forceinline__ unsigned long long pub_load(const unsigned long long *p)
 {
-    int t = 0;
-    for (int s = 0; s < S; ++s) t += counts[((size_t)c * S + s) * 3 + k];
-    return t;
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pub_store(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(PIC_THREADS) k_pic_count(PfPic p, PicDerived D, const long long *__restrict__ start,
-                                                           int *__restrict__ counts, int *__restrict__ err, int S)
-{
-    const long long wid = ((long long)blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int c = (int)(wid / S), sub = (int)(wid % S);
-    if (c >= p.L) return;
-    long long a, b;
-    sub_range(start[c], start[c + 1], S, sub, a, b);
-    int nl = 0, ns = 0, nr = 0;
-    for (long long i0 = a; i0 < b; i0 += 32) {
-        const long long i = i0 + lane;
-        int d = 2;                        // 2 = no particle in this lane
-        if (i < b) {
-            Pushed r = pic_push_one(p, D, p.z[i], p.ux[i], p.uz[i]);
-            p.z[i] = r.z;               // pushed state, still in the old order: the move pass only re-ranks it
-            p.ux[i] = r.ux;
-            p.uz[i] = r.uz;
-            d = r.cell - c;
-            if (d < -1 || d > 1) { atomicExch(err, 1); d = max(-1, min(1, d)); }
-        }
-        nl += __popc(__ballot_sync(0xffffffffu, d == -1));
-        ns += __popc(__ballot_sync(0xffffffffu, d == 0));
-        nr += __popc(__ballot_sync(0xffffffffu, d == 1));
-    }
-    if (lane == 0) {
-        int *o = counts + ((size_t)c * S + sub) * 3;
-        o[0] = nl;
-        o[1] = ns;
-        o[2] = nr;
-    }
-}
-
-// per-cell totals of the sub-warp counters (tot[3c+k]); one thread per cell
-__global__ void __launch_bounds__(PIC_THREADS) k_pic_cell_totals(const int *__restrict__ counts, int L, int S,
-                                                                 int *__restrict__ tot)
-{
-    const int c = blockIdx.x * PIC_THREADS + threadIdx.x;
-    if (c >= L) return;
-    for (int k = 0; k < 3; ++k) tot[3 * c + k] = cell_count(counts, S, c, k);
-}
-
-// single CTA: new_start[c] = sum_{c' < c} (nR[c'-1] + nS[c'] + nL[c'+1])   (counts = per-cell totals)
-__global__ void __launch_bounds__(1024) k_pic_scan(const int *__restrict__ counts, int L, long long *__restrict__ new_start)
-{
-    __shared__ long long part[1024];
-    const int t = threadIdx.x;
-    const int per = (L + 1023) / 1024;
-    const int c0 = t * per, c1 = min(L, c0 + per);
-    long long sum = 0;
-    for (int c = c0; c < c1; ++c)
-        sum += (c > 0 ? counts[3 * (c - 1) + 2] : 0) + counts[3 * c + 1] + (c + 1 < L ? counts[3 * (c + 1)] : 0);
-    part[t] = sum;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {     // inclusive Hillis-Steele scan of the 1024 partials
-        long long v = (t >= off) ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    long long run = part[t] - sum;                 // exclusive prefix of this thread's chunk
-    for (int c = c0; c < c1; ++c) {
-        new_start[c] = run;
-        run += (c > 0 ? counts[3 * (c - 1) + 2] : 0) + counts[3 * c + 1] + (c + 1 < L ? counts[3 * (c + 1)] : 0);
-    }
-    if (t == 1023) new_start[L] = part[1023];
-}
-
-// DEP = true additionally deposits while the particles are in registers (pf_pic_step_sorted): lane l of sub-warp
-// (c, s) accumulates, in chunk order, the CIC shares of its particles at the four nodes c-1 .. c+2 a particle of old
-// cell c can touch; the 32 lanes are combined by the fixed xor butterfly and the four sums go to part[(c*S+s)*4 + k].
-// k_pic_flush4 then adds the partial sums of every node in a fixed order.  Deterministic (no atomics), but a
-// different summation tree from pf_pic_deposit's -- oracle/pic_oracle.py: deposit_fused().
-#ifndef PF_PIC_MOVE_MINBLOCKS
-#define PF_PIC_MOVE_MINBLOCKS 4   // 62 instead of 78 registers for the depositing variant: 0.589 vs 0.616 ms per 2e7-particle step
-#endif
+// DEP = true additionally deposits while the particles are in registers (pf_pic_step_sorted): lane l of piece (c, s)
+// accumulates, in chunk order, the CIC shares of its particles at the four nodes c-1 .. c+2 a particle of old cell c can
+// touch; the 32 lanes are combined by the fixed xor butterfly and the four sums go to part[(c*S+s)*4 + k].  k_pic_flush4
+// then adds the partial sums of every node in a fixed order.  Deterministic (no atomics), but a different summation tree
+// from pf_pic_deposit's -- oracle/pic_oracle.py: deposit_fused().
 template <bool DEP>
-__global__ void __launch_bounds__(PIC_THREADS, DEP ? PF_PIC_MOVE_MINBLOCKS : 1) k_pic_move(PfPic p, PicDerived D, const long long *__restrict__ start,
-                                                          const int *__restrict__ counts, const int *__restrict__ tot,
-                                                          const long long *__restrict__ new_start, int S,
-                                                          double *__restrict__ part)
+__global__ void __launch_bounds__(PIC_THREADS, 2) k_pic_step1(PfPic p, PicDerived D, const long long *__restrict__ start,
+                                                             long long *__restrict__ new_start, unsigned long long *pub,
+                                                             int *__restrict__ err, int S, long long n_pieces,
+                                                             double *__restrict__ part)
 {
-    const long long wid = ((long long)blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int c = (int)(wid / S), sub = (int)(wid % S);
-    if (c >= p.L) return;
-    long long a, b;
-    sub_range(start[c], start[c + 1], S, sub, a, b);
-    if (a == b) {
-        if (DEP && lane < 4) part[((size_t)c * S + sub) * 4 + lane] = 0.0;
-        return;
-    }
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     const unsigned lt = (1u << lane) - 1u;
-    // first slot of each group in the new order (tot = per-cell totals), advanced past the cell's earlier sub-warps
-    long long posL = 0, posS, posR = 0;
-    if (c > 0) posL = new_start[c - 1] + (c > 1 ? tot[3 * (c - 2) + 2] : 0) + tot[3 * (c - 1) + 1];
-    posS = new_start[c] + (c > 0 ? tot[3 * (c - 1) + 2] : 0);
-    if (c + 1 < p.L) posR = new_start[c + 1];
-    for (int s2 = 0; s2 < sub; ++s2) {
-        const int *o = counts + ((size_t)c * S + s2) * 3;
-        posL += o[0];
-        posS += o[1];
-        posR += o[2];
-    }
-    for (long long i0 = a; i0 < b; i0 += 32) {
-        const long long i = i0 + lane;
-        int d = 2;
-        Pushed r;
-        double w = 0.0;
-        if (i < b) {
-            r.z = p.z[i];               // already pushed by the count pass
-            r.ux = p.ux[i];
-            r.uz = p.uz[i];
-            w = p.w[i];
-            const int cn = (int)floor(r.z * D.inv_dz);     // same expression as pic_push_one's cell
-            d = max(-1, min(1, max(0, min(cn, p.L - 2)) - c));
+    const long long warp0 = ((long long)blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * PIC_THREADS) >> 5;
+    for (long long piece = warp0; piece < n_pieces; piece += n_warps) {
+        const int c = (int)(piece / S), sub = (int)(piece % S);
+        long long a, b;
+        sub_range(start[c], start[c + 1], S, sub, a, b);
+        const long long n = b - a;
+        const bool fast = n <= 32 * PIC_K;
+        if (n > PUB_MASK) atomicExch(err, 2);            // a piece of more than 2^20 particles: counts would not fit their field
+        double rz[PIC_K], rux[PIC_K], ruz[PIC_K], rw[PIC_K];
+        unsigned dbits = 0;                               // 2 bits per held particle: d + 1 (0..2), 3 = no particle
+        int nl = 0, ns = 0, nr = 0;
+        // ---- 1. push + count ------------------------------------------------------------------------------------
+        if (fast) {
+#pragma unroll
+            for (int k = 0; k < PIC_K; ++k) {
+                const long long i = a + 32 * k + lane;
+                int d = 2;
+                rz[k] = rux[k] = ruz[k] = rw[k] = 0.0;
+                if (32 * k < n) {                         // warp-uniform
+                    if (i < b) {
+                        Pushed r = pic_push_one(p, D, p.z[i], p.ux[i], p.uz[i]);
+                        rz[k] = r.z; rux[k] = r.ux; ruz[k] = r.uz; rw[k] = p.w[i];
+                        d = r.cell - c;
+                        if (d < -1 || d > 1) { atomicExch(err, 1); d = max(-1, min(1, d)); }
+                    }
+                    nl += __popc(__ballot_sync(0xffffffffu, d == -1));
+                    ns += __popc(__ballot_sync(0xffffffffu, d == 0));
+                    nr += __popc(__ballot_sync(0xffffffffu, d == 1));
+                }
+                dbits |= (unsigned)(d + 1) << (2 * k);
+            }
+        } else {
+            for (long long i0 = a; i0 < b; i0 += 32) {
+                const long long i = i0 + lane;
+                int d = 2;
+                if (i < b) {
+                    Pushed r = pic_push_one(p, D, p.z[i], p.ux[i], p.uz[i]);
+                    p.z[i] = r.z;                         // pushed state, still in the old order: re-read for placement below
+                    p.ux[i] = r.ux;
+                    p.uz[i] = r.uz;
+                    d = r.cell - c;
+                    if (d < -1 || d > 1) { atomicExch(err, 1); d = max(-1, min(1, d)); }
+                }
+                nl += __popc(__ballot_sync(0xffffffffu, d == -1));
+                ns += __popc(__ballot_sync(0xffffffffu, d == 0));
+                nr += __popc(__ballot_sync(0xffffffffu, d == 1));
+            }
         }
-        const unsigned bl = __ballot_sync(0xffffffffu, d == -1);
-        const unsigned bs = __ballot_sync(0xffffffffu, d == 0);
-        const unsigned br = __ballot_sync(0xffffffffu, d == 1);
-        if (i < b) {
-            long long dst = (d == -1) ? posL + __popc(bl & lt) : (d == 0) ? posS + __popc(bs & lt) : posR + __popc(br & lt);
-            p.z_alt[dst] = r.z;
-            p.ux_alt[dst] = r.ux;
-            p.uz_alt[dst] = r.uz;
-            p.w_alt[dst] = w;
-            p.cell_alt[dst] = c + d;
+        // ---- 2. publish --------------------------------------------------------------------------------------------
+        if (lane == 0)
+            pub_store(pub + piece, PUB_VALID | (unsigned long long)(nl & PUB_MASK) | ((unsigned long long)(ns & PUB_MASK) << PUB_BITS) |
+                                       ((unsigned long long)(nr & PUB_MASK) << (2 * PUB_BITS)));
+        // ---- 3. counts of the cells c-1, c, c+1 -> first slots of the three groups -------------------------------
+        int Lc = 0, Rc = 0, preL = 0, preS = 0, preR = 0, Rm = 0, Lp = 0;
+        {
+            const long long jlo = (long long)max(0, c - 1) * S, jhi = (long long)min(p.L, c + 2) * S;
+            for (long long j0 = jlo; j0 < jhi; j0 += 32) {
+                const long long j = j0 + lane;
+                if (j < jhi) {
+                    unsigned long long v;
+                    do { v = pub_load(pub + j); } while (!(v & PUB_VALID));
+                    const int l = (int)(v & PUB_MASK), st = (int)((v >> PUB_BITS) & PUB_MASK), r = (int)((v >> (2 * PUB_BITS)) & PUB_MASK);
+                    const int cj = (int)(j / S), sj = (int)(j % S);
+                    if (cj == c) {
+                        Lc += l; Rc += r;
+                        if (sj < sub) { preL += l; preS += st; preR += r; }
+                    } else if (cj < c) {
+                        Rm += r;
+                    } else {
+                        Lp += l;
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                Lc += __shfl_xor_sync(0xffffffffu, Lc, off);
+                Rc += __shfl_xor_sync(0xffffffffu, Rc, off);
+                preL += __shfl_xor_sync(0xffffffffu, preL, off);
+                preS += __shfl_xor_sync(0xffffffffu, preS, off);
+                preR += __shfl_xor_sync(0xffffffffu, preR, off);
+                Rm += __shfl_xor_sync(0xffffffffu, Rm, off);
+                Lp += __shfl_xor_sync(0xffffffffu, Lp, off);
+            }
+        }
+        const long long sc = start[c], sc1 = start[c + 1];
+        long long posS = sc + Lc + preS, posL = sc - Rm + preL, posR = sc1 - Rc + Lp + preR;
+        if (sub == 0 && lane == 0) {                      // the offsets of the NEW order (the next step's start[])
+            new_start[c] = sc - Rm + Lc;
+            if (c == p.L - 1) new_start[p.L] = sc1;
+        }
+        // ---- 4. place (+ deposit) ----------------------------------------------------------------------------------
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        auto place = [&](bool have, int d, double z, double ux, double uz, double w) {
+            const unsigned bl = __ballot_sync(0xffffffffu, d == -1);
+            const unsigned bs = __ballot_sync(0xffffffffu, d == 0);
+            const unsigned br = __ballot_sync(0xffffffffu, d == 1);
+            if (have) {
+                const long long dst = (d == -1) ? posL + __popc(bl & lt) : (d == 0) ? posS + __popc(bs & lt) : posR + __popc(br & lt);
+                p.z_alt[dst] = z;
+                p.ux_alt[dst] = ux;
+                p.uz_alt[dst] = uz;
+                p.w_alt[dst] = w;
+                p.cell_alt[dst] = c + d;
+            }
+            if (DEP) {
+                double t0 = 0.0, t1 = 0.0;
+                if (have) {
+                    const double g = sqrt(1.0 + (ux * ux + uz * uz) * D.inv_c2);
+                    const double wv = w * (ux / g);
+                    const double f = z * D.inv_dz - (double)(c + d);
+                    t0 = wv * (1.0 - f);
+                    t1 = wv * f;
+                }
+                // shares at nodes c-1, c, c+1, c+2 (adding 0.0 is exact, so absent lanes / other nodes do not perturb the sums)
+                acc0 = acc0 + (d == -1 ? t0 : 0.0);
+                acc1 = acc1 + (d == -1 ? t1 : (d == 0 ? t0 : 0.0));
+                acc2 = acc2 + (d == 0 ? t1 : (d == 1 ? t0 : 0.0));
+                acc3 = acc3 + (d == 1 ? t1 : 0.0);
+            }
+            posL += __popc(bl);
+            posS += __popc(bs);
+            posR += __popc(br);
+        };
+        if (fast) {
+#pragma unroll
+            for (int k = 0; k < PIC_K; ++k) {
+                if (32 * k < n) {                         // warp-uniform
+                    const int d = (int)((dbits >> (2 * k)) & 3u) - 1;     // 2 = no particle in this lane
+                    place(d != 2, d, rz[k], rux[k], ruz[k], rw[k]);
+                }
+            }
+        } else {
+            for (long long i0 = a; i0 < b; i0 += 32) {
+                const long long i = i0 + lane;
+                int d = 2;
+                double z = 0.0, ux = 0.0, uz = 0.0, w = 0.0;
+                if (i < b) {
+                    z = p.z[i]; ux = p.ux[i]; uz = p.uz[i]; w = p.w[i];
+                    const int cn = (int)floor(z * D.inv_dz);     // same expression as pic_push_one's cell
+                    d = max(-1, min(1, max(0, min(cn, p.L - 2)) - c));
+                }
+                place(i < b, d, z, ux, uz, w);
+            }
         }
         if (DEP) {
-            double t0 = 0.0, t1 = 0.0;
-            if (i < b) {
-                const double g = sqrt(1.0 + (r.ux * r.ux + r.uz * r.uz) * D.inv_c2);
-                const double wv = w * (r.ux / g);
-                const double f = r.z * D.inv_dz - (double)(c + d);
-                t0 = wv * (1.0 - f);
-                t1 = wv * f;
-            }
-            // shares at nodes c-1, c, c+1, c+2 (adding 0.0 is exact, so absent lanes / other nodes do not perturb the sums)
-            acc0 = acc0 + (d == -1 ? t0 : 0.0);
-            acc1 = acc1 + (d == -1 ? t1 : (d == 0 ? t0 : 0.0));
-            acc2 = acc2 + (d == 0 ? t1 : (d == 1 ? t0 : 0.0));
-            acc3 = acc3 + (d == 1 ? t1 : 0.0);
-        }
-        posL += __popc(bl);
-        posS += __popc(bs);
-        posR += __popc(br);
-    }
-    if (DEP) {
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, off);
-            acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, off);
-            acc2 = acc2 + __shfl_xor_sync(0xffffffffu, acc2, off);
-            acc3 = acc3 + __shfl_xor_sync(0xffffffffu, acc3, off);
-        }
-        if (lane == 0) {
-            double *o = part + ((size_t)c * S + sub) * 4;
-            o[0] = acc0; o[1] = acc1; o[2] = acc2; o[3] = acc3;
+            for (int off = 16; off >= 1; off >>= 1) {
+                acc0 = acc0 + __shfl_xor_sync(0xffffffffu, acc0, off);
+                acc1 = acc1 + __shfl_xor_sync(0xffffffffu, acc1, off);
+                acc2 = acc2 + __shfl_xor_sync(0xffffffffu, acc2, off);
+                acc3 = acc3 + __shfl_xor_sync(0xffffffffu, acc3, off);
+            }
+            if (lane == 0) {
+                double *o = part + ((size_t)c * S + sub) * 4;
+                o[0] = acc0; o[1] = acc1; o[2] = acc2; o[3] = acc3;
+            }
         }
     }
 }
@@ -341,11 +370,13 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_permute(PfPic p, const int 
 }
 
 // the fused push + re-sort runs up to this many warps per cell (each on a contiguous piece of the cell's particles)
-constexpr int PIC_SUB_MAX = 8;
+// (sized so that a piece of an average cell is 3/4 of what a warp holds in registers: cells up to a third above the
+//  average population still take the register path)
+constexpr int PIC_SUB_MAX = 64;
 static inline int pic_sub_warps(const PfPic *p)
 {
     long long per_cell = p->n / std::max(1, p->L);
-    return (int)std::min<long long>(PIC_SUB_MAX, std::max<long long>(1, (per_cell + 255) / 256));
+    return (int)std::min<long long>(PIC_SUB_MAX, std::max<long long>(1, (per_cell + 191) / 192));
 }
 
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
@@ -375,7 +406,7 @@ static PicPlan pic_plan(const PfPic *p)
     pl.off_start = pl.off_acc + al256(sizeof(double) * 2 * (size_t)p->L);
     pl.off_new_start = pl.off_start + al256(sizeof(long long) * ((size_t)p->L + 1));
     pl.off_counts = pl.off_new_start + al256(sizeof(long long) * ((size_t)p->L + 1));
-    pl.off_tot = pl.off_counts + al256(sizeof(int) * 3 * (size_t)p->L * PIC_SUB_MAX);
+    pl.off_tot = pl.off_counts + al256(sizeof(unsigned long long) * (size_t)p->L * PIC_SUB_MAX);   // publication words
     pl.off_part = pl.off_tot + al256(sizeof(int) * 3 * (size_t)p->L);
     pl.off_err = pl.off_part + al256(sizeof(double) * 4 * (size_t)p->L * PIC_SUB_MAX);
     pl.total = pl.off_err + 256;
@@ -489,7 +520,7 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
     cudaStream_t st = (cudaStream_t)stream;
     char *s = (char *)scratch;
     long long *start = (long long *)(s + pl.off_start), *new_start = (long long *)(s + pl.off_new_start);
-    int *counts = (int *)(s + pl.off_counts), *err = (int *)(s + pl.off_err);
+    int *err = (int *)(s + pl.off_err);
     PF_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
     if (p->flags & PF_PIC_F_OFFSETS_VALID) {
         // the previous fused call's new offsets ARE this call's offsets (caller's promise): 8 (L+1) bytes instead of a
@@ -500,32 +531,35 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
         PF_LAUNCH_CHECK("k_pic_cell_start");
     }
     const int S = pic_sub_warps(p);
-    int *tot = (int *)(s + pl.off_tot);
-    unsigned wblocks = (unsigned)(((long long)p->L * S * 32 + PIC_THREADS - 1) / PIC_THREADS);
-    {
-        ProfScope prof(st, "k_pic_count");
-        k_pic_count<<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, err, S);
-    }
-    PF_LAUNCH_CHECK("k_pic_count");
-    k_pic_cell_totals<<<(p->L + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(counts, p->L, S, tot);
-    PF_LAUNCH_CHECK("k_pic_cell_totals");
-    k_pic_scan<<<1, 1024, 0, st>>>(tot, p->L, new_start);
-    PF_LAUNCH_CHECK("k_pic_scan");
+    unsigned long long *pub = (unsigned long long *)(s + pl.off_counts);
+    const long long n_pieces = (long long)p->L * S;
+    PF_CUDA(cudaMemsetAsync(pub, 0, sizeof(unsigned long long) * (size_t)n_pieces, st));
+    // persistent grid: every CTA resident (the kernel's warps wait for one another's publications)
+    int dev = 0, sms = 0, per_sm = 0;
+    PF_CUDA(cudaGetDevice(&dev));
+    PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (deposit) PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pic_step1<true>, PIC_THREADS, 0));
+    else PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pic_step1<false>, PIC_THREADS, 0));
+    if (per_sm < 1) return set_err(PF_E_CUDA, "k_pic_step1 does not fit on an SM");
+    const long long need = (n_pieces * 32 + PIC_THREADS - 1) / PIC_THREADS;
+    const unsigned blocks = (unsigned)std::min<long long>(need, (long long)sms * per_sm);
+    if ((long long)blocks < need && (long long)blocks * (PIC_THREADS / 32) <= 4LL * S)
+        return set_err(PF_E_UNSUPPORTED, "pf_pic_step_sorted: too few resident warps for %d pieces per cell", S);
+    double *part = (double *)(s + pl.off_part);
     if (deposit) {
-        double *part = (double *)(s + pl.off_part);
         {
-            ProfScope prof(st, "k_pic_move<deposit>");
-            k_pic_move<true><<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S, part);
+            ProfScope prof(st, "k_pic_step1<deposit>");
+            k_pic_step1<true><<<blocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, part);
         }
-        PF_LAUNCH_CHECK("k_pic_move");
+        PF_LAUNCH_CHECK("k_pic_step1");
         k_pic_flush4<<<(p->L + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(*p, part, S);
         PF_LAUNCH_CHECK("k_pic_flush4");
     } else {
         {
-            ProfScope prof(st, "k_pic_move");
-            k_pic_move<false><<<wblocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, counts, tot, new_start, S, nullptr);
+            ProfScope prof(st, "k_pic_step1");
+            k_pic_step1<false><<<blocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, nullptr);
         }
-        PF_LAUNCH_CHECK("k_pic_move");
+        PF_LAUNCH_CHECK("k_pic_step1");
     }
     return PF_OK;
 }
