@@ -115,8 +115,10 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_push(PfPic p, PicDerived D)
 //     right-movers of c : start[c+1] - R(c) + L(c+1)        (plus, inside a cell, the counts of its earlier pieces).
 //
 // ONE pass over the particles (k_pic_step1).  A cell is cut into S contiguous pieces (sub_range), one warp per piece:
-//   1. push the piece's particles and keep them in REGISTERS (PIC_K = 8 per lane: z, ux, uz, w), counting
-//      left / stay / right by ballot;
+//   1. push the piece's particles and keep them ON CHIP (32 PIC_K = 128 per piece: z, ux, uz, w in the warp's own
+//      4 KB of shared memory -- registers would cost the occupancy the latency-bound push lives on: a first version with
+//      8 particles per lane in registers ran at 128 registers / 16 warps per SM and 1.33 ms per 2e7-particle step),
+//      counting left / stay / right by ballot;
 //   2. publish the three counts as one 64-bit word (valid bit + 3 x 20 bits; the words are zeroed before the launch);
 //   3. wait for the words of every piece of the cells c-1, c, c+1 (lanes poll in parallel), derive the offsets;
 //   4. write every particle straight to its final slot of the alternate arrays -- and, DEP = true, accumulate its CIC
@@ -148,7 +150,11 @@ __device__ __forceinline__ void sub_range(long long a, long long b, int S, int s
     hi = min(b, lo + q);
 }
 
-constexpr int PIC_K = 8;                      // particles per lane a piece holds in registers
+constexpr int PIC_K = 4;                      // particles per lane a piece keeps on chip (32 PIC_K per piece, in shared memory)
+#ifndef PF_PIC_STEP_MINBLOCKS
+#define PF_PIC_STEP_MINBLOCKS 5
+#endif
+constexpr int PIC_STEP_MINBLOCKS = PF_PIC_STEP_MINBLOCKS;   // 40 warps / SM: the push is fp64-latency bound and lives on thread-level parallelism
 constexpr unsigned long long PUB_VALID = 1ull << 63;
 constexpr int PUB_BITS = 20, PUB_MASK = (1 << PUB_BITS) - 1;
 
@@ -169,13 +175,15 @@ __device__ __forceinline__ void pub_store(unsigned long long *p, unsigned long l
 // then adds the partial sums of every node in a fixed order.  Deterministic (no atomics), but a different summation tree
 // from pf_pic_deposit's -- oracle/pic_oracle.py: deposit_fused().
 template <bool DEP>
-__global__ void __launch_bounds__(PIC_THREADS, 2) k_pic_step1(PfPic p, PicDerived D, const long long *__restrict__ start,
+__global__ void __launch_bounds__(PIC_THREADS, PIC_STEP_MINBLOCKS) k_pic_step1(PfPic p, PicDerived D, const long long *__restrict__ start,
                                                              long long *__restrict__ new_start, unsigned long long *pub,
                                                              int *__restrict__ err, int S, long long n_pieces,
                                                              double *__restrict__ part)
 {
+    __shared__ double stage[PIC_THREADS / 32][4][32 * PIC_K];      // [warp][z, ux, uz, w][particle of the piece]
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
+    double(*my)[32 * PIC_K] = stage[threadIdx.x >> 5];
     const long long warp0 = ((long long)blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * PIC_THREADS) >> 5;
     for (long long piece = warp0; piece < n_pieces; piece += n_warps) {
@@ -185,7 +193,6 @@ __global__ void __launch_bounds__(PIC_THREADS, 2) k_pic_step1(PfPic p, PicDerive
         const long long n = b - a;
         const bool fast = n <= 32 * PIC_K;
         if (n > PUB_MASK) atomicExch(err, 2);            // a piece of more than 2^20 particles: counts would not fit their field
-        double rz[PIC_K], rux[PIC_K], ruz[PIC_K], rw[PIC_K];
         unsigned dbits = 0;                               // 2 bits per held particle: d + 1 (0..2), 3 = no particle
         int nl = 0, ns = 0, nr = 0;
         // ---- 1. push + count ------------------------------------------------------------------------------------
@@ -194,11 +201,11 @@ __global__ void __launch_bounds__(PIC_THREADS, 2) k_pic_step1(PfPic p, PicDerive
             for (int k = 0; k < PIC_K; ++k) {
                 const long long i = a + 32 * k + lane;
                 int d = 2;
-                rz[k] = rux[k] = ruz[k] = rw[k] = 0.0;
                 if (32 * k < n) {                         // warp-uniform
                     if (i < b) {
                         Pushed r = pic_push_one(p, D, p.z[i], p.ux[i], p.uz[i]);
-                        rz[k] = r.z; rux[k] = r.ux; ruz[k] = r.uz; rw[k] = p.w[i];
+                        my[0][32 * k + lane] = r.z; my[1][32 * k + lane] = r.ux; my[2][32 * k + lane] = r.uz;
+                        my[3][32 * k + lane] = p.w[i];
                         d = r.cell - c;
                         if (d < -1 || d > 1) { atomicExch(err, 1); d = max(-1, min(1, d)); }
                     }
@@ -305,7 +312,9 @@ __global__ void __launch_bounds__(PIC_THREADS, 2) k_pic_step1(PfPic p, PicDerive
             for (int k = 0; k < PIC_K; ++k) {
                 if (32 * k < n) {                         // warp-uniform
                     const int d = (int)((dbits >> (2 * k)) & 3u) - 1;     // 2 = no particle in this lane
-                    place(d != 2, d, rz[k], rux[k], ruz[k], rw[k]);
+                    const bool have = d != 2;                             // (each lane reads back only what it wrote itself)
+                    place(have, d, have ? my[0][32 * k + lane] : 0.0, have ? my[1][32 * k + lane] : 0.0,
+                          have ? my[2][32 * k + lane] : 0.0, have ? my[3][32 * k + lane] : 0.0);
                 }
             }
         } else {
@@ -370,13 +379,13 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_permute(PfPic p, const int 
 }
 
 // the fused push + re-sort runs up to this many warps per cell (each on a contiguous piece of the cell's particles)
-// (sized so that a piece of an average cell is 3/4 of what a warp holds in registers: cells up to a third above the
-//  average population still take the register path)
-constexpr int PIC_SUB_MAX = 64;
+// (sized so that a piece of an average cell is 3/4 of what a warp keeps on chip, 128 particles: cells up to a third above
+//  the average population still take the on-chip path)
+constexpr int PIC_SUB_MAX = 128;
 static inline int pic_sub_warps(const PfPic *p)
 {
     long long per_cell = p->n / std::max(1, p->L);
-    return (int)std::min<long long>(PIC_SUB_MAX, std::max<long long>(1, (per_cell + 191) / 192));
+    return (int)std::min<long long>(PIC_SUB_MAX, std::max<long long>(1, (per_cell + 95) / 96));
 }
 
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }

@@ -527,14 +527,76 @@ def nonlinear_sweep(freqs, amplitudes, domainSize, lowLimTim, highLimTim, *, nst
     return out
 
 
+def _sweep_chain_env(V, P, domainSize, lowLimTim, highLimTim, Interval, points):
+    """The sizing chain of the reference's sweep (MasterController.py:543-563) without the objects: member i's points per
+    wavelength come from member i-1's medium AS ITS TWO PASSES LEAVE IT (twice dispersion-corrected plasma frequency; the
+    first member is sized from the V that was passed in), every member then starts from the default medium again.
+    Returns (freqs, env dict of arrays, twice-corrected plasma frequency per member)."""
+    from . import sweep_setup, genericStability as gStab
+    med = sweep_setup.default_medium(1)
+    wp0, w0d, gamd = float(med["wp"][0]), float(med["w0"][0]), float(med["gam"][0])
+    prev = (float(V.plasmaFreqE), float(V.omega_0E), float(V.gammaE))
+    freq = float(P.freq_in)
+    freqs, envs, wps = [], [], []
+    for _ in range(points):
+        w = 2 * np.pi * freq                                        # Environment_Setup.py:23-46 with VExists=True
+        eps = 1 + (prev[0] * prev[0]) / (prev[1] * prev[1] - (w * w) + 1j * prev[2] * w)
+        Nlam = int(60 * (np.real(eps)) ** 1.05)
+        env = sweep_setup.envSetup_many(np.array([freq]), domainSize, lowLimTim, highLimTim, LorMed=True, Nlam=np.array([Nlam]))
+        wp = wp0
+        for _k in range(2):                                         # Solver_Engine.py:286, once per pass
+            wp = float(gStab.spatialStab(int(env["timeSteps"][0]), int(env["Nz"][0]), float(env["dz"][0]), freq,
+                                         float(env["delT"][0]), wp, w0d, gamd)[3])
+        freqs.append(freq)
+        envs.append(env)
+        wps.append(wp)
+        prev = (wp, w0d, gamd)
+        freq = freq + Interval
+    env = {k: np.concatenate([e[k] for e in envs]) for k in envs[0]}
+    return np.array(freqs), env, np.array(wps)
+
+
 def frequency_sweep(V, P, domainSize, lowLimTim, highLimTim, Low=3e9, Interval=1e8, points=20, batched=True,
                     device_postproc=True):
     """MasterController.LoopedSim(loop=True) :533-569.  Returns (freqs, measured R, analytical R,
-    (V,P,C_V,C_P,Exs,Hys) of the last member).  With ``batched`` and ``device_postproc`` the reflection
-    extraction (results(RefCo=True) -> RefTester) runs on the device too and only the last member's traces
-    come back to the host."""
+    (V,P,C_V,C_P,Exs,Hys) of the last member).
+
+    batched + device_postproc (default) with a Lorentz medium and the sine source: the whole sweep runs through the
+    vectorised path -- the reference's sizing chain on scalars (``_sweep_chain_env``), tables, native input building, one
+    batch, reflection extraction on the device; only the LAST member is also built as objects (the tuple the reference
+    returns), with its traces and final fields copied back.  Otherwise: per-member objects, batched (``run_two_pass_batch``)
+    or one Controller call after another like the reference."""
     from . import MasterController as MC
     freqs = np.arange(Low, points * Interval + Low, Interval)[:points]
+    fast = (batched and device_postproc and bool(P.LorentzMed) and bool(P.SineCont) and not bool(P.Gaussian)
+            and not SE.KERR_LORENTZ and points > 0)
+    if fast:
+        from . import sweep_setup
+        _, env, wp2 = _sweep_chain_env(V, P, domainSize, lowLimTim, highLimTim, Interval, points)
+        fr = np.empty(points)                       # member frequencies as the reference accumulates them (freq_in += Interval)
+        f = float(P.freq_in)
+        for i in range(points):
+            fr[i] = f
+            f = f + Interval
+        tables = sweep_setup.lorentz_sweep_tables(fr, 1.0, domainSize, lowLimTim, highLimTim, periods=P.Periods,
+                                                  tfsf=bool(P.TFSF), fma=SE.USE_FMA, fp32=SE.USE_FP32, env=env)
+        assert np.array_equal(tables[1].wp, wp2)
+        measured, _, _, last = _run_reflection_tables(tables, np.arange(points), keep_last=True)
+        analytical = _analytical_reflection(fr, wp2)
+        # the last member as objects: sized from the previous member's medium exactly like the chain above
+        prevV, prevP = V, P
+        if points > 1:
+            prevV = MC.Variables(1, 1, 1, 1)
+            prevV.plasmaFreqE = float(wp2[points - 2])
+        Vi, Pi, CVi, CPi = new_member_objects(float(fr[-1]), domainSize, lowLimTim, highLimTim, prevV, prevP, P)
+        for _k in range(2):
+            CVi, Exs, Hys = SE.prepare_pass(Vi, Pi, CVi, CPi, True)
+        n = np.arange(Pi.timeSteps)
+        Vi.x1ColBe = np.where(n <= int(Pi.timeSteps * 0.7), last[0], 0.0)
+        Vi.x1ColAf = np.where(n >= int(Pi.timeSteps * 0.05), last[1], 0.0)
+        Vi.Ex, Vi.Hy = last[2], last[3]
+        Pi.freq_in = Pi.freq_in + Interval          # the reference leaves the last P advanced (:559)
+        return freqs, measured, analytical, (Vi, Pi, CVi, CPi, Exs, Hys)
     # -- setup chain (sequential by construction: member i is sized from member i-1's corrected medium;
     #    the correction itself is host-side setup, so it does not need member i-1's fields)
     objs = []
@@ -573,6 +635,67 @@ def frequency_sweep(V, P, domainSize, lowLimTim, highLimTim, Low=3e9, Interval=1
     return freqs, measured, analytical, (Vi, Pi, CVi, CPi, Exs, Hys)
 
 
+def _run_reflection_tables(tables, mine, *, chunk=256, k_block=0, threads=0, keep_last=False):
+    """Two passes of IntegratorLinLor1D + results(RefCo=True) for the rows ``mine`` of a (pass 0, pass 1) table pair, chunk by
+    chunk, pipelined (while the GPU steps chunk i the host builds the inputs of chunk i+1).  Returns (R per member,
+    cell-updates, seconds spent building inputs, and -- keep_last -- the last member's (x1ColBe trace, x1ColAf trace, Ex, Hy))."""
+    import time
+    torch = nat.require_cuda()
+    t_build = 0.0
+    out_R, out_bins, uploaded, cell_steps, keep, last = [], [], {}, 0, [], None
+    for c, lo in enumerate(range(0, len(mine), chunk)):
+        idx = mine[lo:lo + chunk]
+        t0c, t1c = tables[0].select(idx), tables[1].select(idx)
+        slot = f"sweep_in_{c % 2}"
+        if slot in uploaded:
+            uploaded[slot].synchronize()           # the H2D copy that last read this pinned slot has finished
+        tb = time.perf_counter()
+        batch = MemberBatch.from_table(t0c, "lorentz", pinned_tag=slot, threads=threads)
+        t_build += time.perf_counter() - tb
+        batch.upload()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        uploaded[slot] = ev
+        T = batch.T
+        is_last = keep_last and lo + chunk >= len(mine)
+        batch.reset_state()
+        batch.run(do_pol=False, k_block=k_block)
+        p0, b0 = batch.probe_peaks(keep_to=np.trunc(T * 0.7).astype(np.int64), on_device=True)
+        tr0 = batch.download_probe(batch.M - 1)[0] if is_last else None
+        batch.set_pass(t1c)
+        batch.reset_state()
+        batch.run(do_pol=True, k_block=k_block)
+        p1, b1 = batch.probe_peaks(keep_from=np.trunc(T * 0.05).astype(np.int64), on_device=True)
+        if is_last:
+            last = (tr0, batch.download_probe(batch.M - 1)[0], batch.state(batch.M - 1, "Ex"), batch.state(batch.M - 1, "Hy"))
+        out_R.append(p1 / p0)
+        out_bins.append(torch.minimum(b0, b1))
+        cell_steps += 2 * batch.cell_steps
+        keep.append(batch)                          # descriptors / pools stay alive until the stream has drained
+    if out_R:
+        R = torch.cat(out_R).cpu().numpy()
+        if bool((torch.cat(out_bins) == 0).any()):
+            raise ValueError("Could not find non-DC freq")
+    else:
+        R = np.zeros(0)
+    del keep
+    return R, cell_steps, t_build, last
+
+
+def _analytical_reflection(freqs, wp):
+    """BaseFDTD11.AnalyticalReflectionE per member (Python-float / Python-complex arithmetic as there), default medium."""
+    from . import sweep_setup
+    med = sweep_setup.default_medium(1)
+    w0, gam = float(med["w0"][0]), float(med["gam"][0])
+    out = np.empty(len(freqs))
+    for j in range(len(freqs)):
+        wpj, wj = float(wp[j]), 2 * np.pi * float(freqs[j])
+        eps = 1 + (wpj * wpj) / (w0 * w0 - (wj * wj) + 1j * gam * wj)
+        n2 = np.real(np.sqrt(eps))
+        out[j] = abs((n2 - 1) / (1 + n2))
+    return out
+
+
 def reflection_sweep(freqs, domainSize, lowLimTim, highLimTim, *, amps=1.0, periods=1.0, tfsf=True, chunk=256, rank=0,
                      world_size=1, k_block=0, fma=False, fp32=False, nsteps=None, threads=0):
     """Reflection coefficient of the Lorentz half-space at every frequency of ``freqs``: what the reference's sweep
@@ -589,56 +712,14 @@ def reflection_sweep(freqs, domainSize, lowLimTim, highLimTim, *, amps=1.0, peri
     ``timing`` (seconds: vectorised setup, native input building, total wall)."""
     import time
     from . import sweep_setup
-    torch = nat.require_cuda()
+    nat.require_cuda()
     t_start = time.perf_counter()
     freqs = np.ascontiguousarray(freqs, dtype=np.float64)
     tables = sweep_setup.lorentz_sweep_tables(freqs, amps, domainSize, lowLimTim, highLimTim, periods=periods, tfsf=tfsf,
                                               nsteps=nsteps, fma=fma, fp32=fp32)
     t_setup = time.perf_counter() - t_start
     mine = np.arange(rank, len(freqs), world_size)
-    # analytical figure, medium as Controller leaves it (twice-corrected plasma frequency)
-    wp = tables[1].wp[mine]
-    med = sweep_setup.default_medium(1)
-    w0, gam = float(med["w0"][0]), float(med["gam"][0])
-    analytical = np.empty(len(mine))
-    for j in range(len(mine)):      # BaseFDTD11.AnalyticalReflectionE, Python-float / Python-complex arithmetic as there
-        wpj, wj = float(wp[j]), 2 * np.pi * float(freqs[mine[j]])
-        eps = 1 + (wpj * wpj) / (w0 * w0 - (wj * wj) + 1j * gam * wj)
-        n2 = np.real(np.sqrt(eps))
-        analytical[j] = abs((n2 - 1) / (1 + n2))
-    t_build = 0.0
-    out_R, out_bins, uploaded, cell_steps, keep = [], [], {}, 0, []
-    for c, lo in enumerate(range(0, len(mine), chunk)):
-        idx = mine[lo:lo + chunk]
-        t0c, t1c = tables[0].select(idx), tables[1].select(idx)
-        slot = f"sweep_in_{c % 2}"
-        if slot in uploaded:
-            uploaded[slot].synchronize()           # the H2D copy that last read this pinned slot has finished
-        tb = time.perf_counter()
-        batch = MemberBatch.from_table(t0c, "lorentz", pinned_tag=slot, threads=threads)
-        t_build += time.perf_counter() - tb
-        batch.upload()
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        uploaded[slot] = ev
-        T = batch.T
-        batch.reset_state()
-        batch.run(do_pol=False, k_block=k_block)
-        p0, b0 = batch.probe_peaks(keep_to=np.trunc(T * 0.7).astype(np.int64), on_device=True)
-        batch.set_pass(t1c)
-        batch.reset_state()
-        batch.run(do_pol=True, k_block=k_block)
-        p1, b1 = batch.probe_peaks(keep_from=np.trunc(T * 0.05).astype(np.int64), on_device=True)
-        out_R.append(p1 / p0)
-        out_bins.append(torch.minimum(b0, b1))
-        cell_steps += 2 * batch.cell_steps
-        keep.append(batch)                          # descriptors / pools stay alive until the stream has drained
-    if out_R:
-        R = torch.cat(out_R).cpu().numpy()
-        if bool((torch.cat(out_bins) == 0).any()):
-            raise ValueError("Could not find non-DC freq")
-    else:
-        R = np.zeros(0)
-    del keep
+    analytical = _analytical_reflection(freqs[mine], tables[1].wp[mine])     # medium as Controller leaves it
+    R, cell_steps, t_build, _ = _run_reflection_tables(tables, mine, chunk=chunk, k_block=k_block, threads=threads)
     return dict(index=mine, freq=freqs[mine], measured=R, analytical=analytical, cell_steps=cell_steps,
                 timing=dict(setup_s=t_setup, build_inputs_s=t_build, total_s=time.perf_counter() - t_start))

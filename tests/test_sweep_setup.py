@@ -140,3 +140,29 @@ def test_member_table_select_rebases_sharing():
     assert list(t.share) == [0, 0, 2, 2, 2]
     s = t.select([1, 3, 4])          # owners 0 and 2 are not selected: the first selected member of each group owns
     assert list(s.share) == [0, 1, 1] and s.n == 3 and list(s.L) == [t.L[1], t.L[3], t.L[4]]
+
+
+def test_reference_sweep_sizing_chain_without_objects():
+    """LoopedSim's quirk (MasterController.py:547): member i is sized from member i-1's twice-corrected medium.  The scalar
+    chain of sweep._sweep_chain_env against the per-member object chain (new_member_objects + spatialStab)."""
+    _lib_or_skip()
+    from pyfdtd_b200 import genericStability as gStab
+    from test_host_layer import build_objects
+    V, P, C_V, C_P = build_objects(dict(mode="lorentz", freq=6e9, dom=0.3, win=[2000, 2200], source="sine", periods=1.0))
+    fr, env, wp2 = sweep._sweep_chain_env(V, P, 0.3, 2000, 2200, 5e8, 6)
+    prevV, prevP, freq = V, P, P.freq_in
+    for i in range(6):
+        Vi, Pi, CVi, CPi = sweep.new_member_objects(freq, 0.3, 2000, 2200, prevV, prevP, P)
+        wp = Vi.plasmaFreqE
+        for _ in range(2):
+            wp = gStab.spatialStab(Pi.timeSteps, Pi.Nz, Pi.dz, Pi.freq_in, Pi.delT, wp, Vi.omega_0E, Vi.gammaE)[3]
+        assert (Pi.Nz, Pi.timeSteps, Pi.pmlWidth, Pi.nzsrc, Pi.materialFrontEdge, Pi.x1Loc, Pi.x2Loc, Pi.dz, Pi.delT) == (
+            env["Nz"][i], env["timeSteps"][i], env["pmlWidth"][i], env["nzsrc"][i], env["materialFrontEdge"][i],
+            env["x1Loc"][i], env["x2Loc"][i], env["dz"][i], env["delT"][i]), i
+        assert wp == wp2[i] and freq == fr[i]
+        sh = MC.Variables(Pi.Nz, 1, 1, 1)
+        sh.plasmaFreqE = wp
+        prevV, prevP, freq = sh, Pi, Pi.freq_in + 5e8
+    assert len(set(env["Nlam"])) > 1                       # the chain really does change the resolution from member to member
+    t = sweep_setup.lorentz_sweep_tables(fr, 1.0, 0.3, 2000, 2200, periods=1.0, env=env)
+    assert np.array_equal(t[1].wp, wp2)
