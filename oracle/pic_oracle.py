@@ -91,10 +91,10 @@ def deposit(z, ux, uz, w, cell, L, *, dz, c, jx_scale):
     return jx_scale * J
 
 
-def sub_warps(n, L, sub_max=128):
+def sub_warps(n, L, sub_max=8):
     """pic_sub_warps() of csrc/pf_pic.cu: pieces (warps) per cell of the fused push + re-sort (+ deposit)."""
     per_cell = n // max(1, L)
-    return int(min(sub_max, max(1, (per_cell + 95) // 96)))
+    return int(min(sub_max, max(1, (per_cell + 255) // 256)))
 
 
 def deposit_fused(z, ux, uz, w, cell_old, cell_new, L, S, *, dz, c, jx_scale):

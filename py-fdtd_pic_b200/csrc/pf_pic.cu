@@ -178,8 +178,11 @@ template <bool DEP>
 __global__ void __launch_bounds__(PIC_THREADS, PIC_STEP_MINBLOCKS) k_pic_step1(PfPic p, PicDerived D, const long long *__restrict__ start,
                                                              long long *__restrict__ new_start, unsigned long long *pub,
                                                              int *__restrict__ err, int S, long long n_pieces,
-                                                             double *__restrict__ part)
+                                                             double *__restrict__ part, int pass)
 {
+    // pass 0: the whole step in one launch (pieces wait for their neighbours' publications);
+    // pass 1 / pass 2: the same step as two launches -- 1 = push + count + publish with the pushed state stored in place,
+    // 2 = offsets + placement from the stored state (every word is published by then: no waiting)
     __shared__ double stage[PIC_THREADS / 32][4][32 * PIC_K];      // [warp][z, ux, uz, w][particle of the piece]
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -191,12 +194,14 @@ __global__ void __launch_bounds__(PIC_THREADS, PIC_STEP_MINBLOCKS) k_pic_step1(P
         long long a, b;
         sub_range(start[c], start[c + 1], S, sub, a, b);
         const long long n = b - a;
-        const bool fast = n <= 32 * PIC_K;
+        const bool fast = pass == 0 && n <= 32 * PIC_K;
         if (n > PUB_MASK) atomicExch(err, 2);            // a piece of more than 2^20 particles: counts would not fit their field
         unsigned dbits = 0;                               // 2 bits per held particle: d + 1 (0..2), 3 = no particle
         int nl = 0, ns = 0, nr = 0;
         // ---- 1. push + count ------------------------------------------------------------------------------------
-        if (fast) {
+        if (pass == 2) {
+            // already pushed, counted and published by the first launch
+        } else if (fast) {
 #pragma unroll
             for (int k = 0; k < PIC_K; ++k) {
                 const long long i = a + 32 * k + lane;
@@ -233,9 +238,10 @@ __global__ void __launch_bounds__(PIC_THREADS, PIC_STEP_MINBLOCKS) k_pic_step1(P
             }
         }
         // ---- 2. publish --------------------------------------------------------------------------------------------
-        if (lane == 0)
+        if (lane == 0 && pass != 2)
             pub_store(pub + piece, PUB_VALID | (unsigned long long)(nl & PUB_MASK) | ((unsigned long long)(ns & PUB_MASK) << PUB_BITS) |
                                        ((unsigned long long)(nr & PUB_MASK) << (2 * PUB_BITS)));
+        if (pass == 1) continue;
         // ---- 3. counts of the cells c-1, c, c+1 -> first slots of the three groups -------------------------------
         int Lc = 0, Rc = 0, preL = 0, preS = 0, preR = 0, Rm = 0, Lp = 0;
         {
@@ -243,8 +249,8 @@ __global__ void __launch_bounds__(PIC_THREADS, PIC_STEP_MINBLOCKS) k_pic_step1(P
             for (long long j0 = jlo; j0 < jhi; j0 += 32) {
                 const long long j = j0 + lane;
                 if (j < jhi) {
-                    unsigned long long v;
-                    do { v = pub_load(pub + j); } while (!(v & PUB_VALID));
+                    unsigned long long v = 0;
+                    while (!((v = pub_load(pub + j)) & PUB_VALID)) __nanosleep(200);
                     const int l = (int)(v & PUB_MASK), st = (int)((v >> PUB_BITS) & PUB_MASK), r = (int)((v >> (2 * PUB_BITS)) & PUB_MASK);
                     const int cj = (int)(j / S), sj = (int)(j % S);
                     if (cj == c) {
@@ -379,6 +385,7 @@ __global__ void __launch_bounds__(PIC_THREADS) k_pic_permute(PfPic p, const int 
 }
 
 // the fused push + re-sort runs up to this many warps per cell (each on a contiguous piece of the cell's particles)
+#ifdef PF_PIC_SINGLE_PASS
 // (sized so that a piece of an average cell is 3/4 of what a warp keeps on chip, 128 particles: cells up to a third above
 //  the average population still take the on-chip path)
 constexpr int PIC_SUB_MAX = 128;
@@ -387,6 +394,14 @@ static inline int pic_sub_warps(const PfPic *p)
     long long per_cell = p->n / std::max(1, p->L);
     return (int)std::min<long long>(PIC_SUB_MAX, std::max<long long>(1, (per_cell + 95) / 96));
 }
+#else
+constexpr int PIC_SUB_MAX = 8;
+static inline int pic_sub_warps(const PfPic *p)
+{
+    long long per_cell = p->n / std::max(1, p->L);
+    return (int)std::min<long long>(PIC_SUB_MAX, std::max<long long>(1, (per_cell + 255) / 256));
+}
+#endif
 
 static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -555,20 +570,27 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
     if ((long long)blocks < need && (long long)blocks * (PIC_THREADS / 32) <= 4LL * S)
         return set_err(PF_E_UNSUPPORTED, "pf_pic_step_sorted: too few resident warps for %d pieces per cell", S);
     double *part = (double *)(s + pl.off_part);
-    if (deposit) {
+    // PF_PIC_SINGLE_PASS: one launch (pass 0).  Default: two launches of the same kernel (pass 1, pass 2) -- measured on a B200
+    // at 2e7 particles the single launch is slower (1.28 ms against ~0.6 ms): its warps spend their time polling for the
+    // neighbours' publications instead of hiding the push's fp64 latency (profiles/r2_pic.md)
+#ifdef PF_PIC_SINGLE_PASS
+    const int passes[2] = {0, -1};
+#else
+    const int passes[2] = {1, 2};
+#endif
+    for (int k = 0; k < 2 && passes[k] >= 0; ++k) {
+        const int pass = passes[k];
+        const unsigned grid = pass == 0 ? blocks : (unsigned)need;
         {
-            ProfScope prof(st, "k_pic_step1<deposit>");
-            k_pic_step1<true><<<blocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, part);
+            ProfScope prof(st, pass == 1 ? "k_pic_step1<count>" : (deposit ? "k_pic_step1<place+deposit>" : "k_pic_step1<place>"));
+            if (deposit) k_pic_step1<true><<<grid, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, part, pass);
+            else k_pic_step1<false><<<grid, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, nullptr, pass);
         }
         PF_LAUNCH_CHECK("k_pic_step1");
+    }
+    if (deposit) {
         k_pic_flush4<<<(p->L + PIC_THREADS - 1) / PIC_THREADS, PIC_THREADS, 0, st>>>(*p, part, S);
         PF_LAUNCH_CHECK("k_pic_flush4");
-    } else {
-        {
-            ProfScope prof(st, "k_pic_step1");
-            k_pic_step1<false><<<blocks, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, nullptr);
-        }
-        PF_LAUNCH_CHECK("k_pic_step1");
     }
     return PF_OK;
 }

@@ -242,7 +242,7 @@ def test_pic_oracle_fused_summation_tree_agrees_with_the_plain_one():
         Jf = po.deposit_fused(zp, uxp, uzp, wo, co, cp, L, S, dz=dz, c=299792458.0, jx_scale=-1.6e-19)
         Jp = po.deposit(*po.sort_by_cell(zp, uxp, uzp, wo, cp), L, dz=dz, c=299792458.0, jx_scale=-1.6e-19)
         assert np.max(np.abs(Jf - Jp)) <= 1e-13 * np.max(np.abs(Jp))
-    assert po.sub_warps(20_000_000, 13194) == 16 and po.sub_warps(1000, 4097) == 1 and po.sub_warps(100_000_000, 13194) == 79
+    assert po.sub_warps(20_000_000, 13194) == 6 and po.sub_warps(1000, 4097) == 1 and po.sub_warps(100_000_000, 13194) == 8
 
 
 def test_python_constants_match_header_enums(tmp_path):
