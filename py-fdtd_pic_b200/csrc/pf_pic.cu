@@ -174,19 +174,26 @@ __device__ __forceinline__ void pub_store(unsigned long long *p, unsigned long l
 // touch; the 32 lanes are combined by the fixed xor butterfly and the four sums go to part[(c*S+s)*4 + k].  k_pic_flush4
 // then adds the partial sums of every node in a fixed order.  Deterministic (no atomics), but a different summation tree
 // from pf_pic_deposit's -- oracle/pic_oracle.py: deposit_fused().
-template <bool DEP>
-__global__ void __launch_bounds__(PIC_THREADS, PIC_STEP_MINBLOCKS) k_pic_step1(PfPic p, PicDerived D, const long long *__restrict__ start,
+#ifndef PF_PIC_COUNT_MINBLOCKS
+#define PF_PIC_COUNT_MINBLOCKS 1
+#endif
+#ifndef PF_PIC_PLACE_MINBLOCKS
+#define PF_PIC_PLACE_MINBLOCKS 4   // round 1: 62 instead of 78 registers for the depositing placement, 0.589 vs 0.616 ms per 2e7-particle step
+#endif
+template <bool DEP, int PASS>
+__global__ void __launch_bounds__(PIC_THREADS, PASS == 0 ? PIC_STEP_MINBLOCKS : (PASS == 1 ? PF_PIC_COUNT_MINBLOCKS : PF_PIC_PLACE_MINBLOCKS)) k_pic_step1(PfPic p, PicDerived D, const long long *__restrict__ start,
                                                              long long *__restrict__ new_start, unsigned long long *pub,
                                                              int *__restrict__ err, int S, long long n_pieces,
-                                                             double *__restrict__ part, int pass)
+                                                             double *__restrict__ part)
 {
+    constexpr int pass = PASS;
     // pass 0: the whole step in one launch (pieces wait for their neighbours' publications);
     // pass 1 / pass 2: the same step as two launches -- 1 = push + count + publish with the pushed state stored in place,
     // 2 = offsets + placement from the stored state (every word is published by then: no waiting)
-    __shared__ double stage[PIC_THREADS / 32][4][32 * PIC_K];      // [warp][z, ux, uz, w][particle of the piece]
+    __shared__ double stage[PASS == 0 ? PIC_THREADS / 32 : 1][4][PASS == 0 ? 32 * PIC_K : 1];   // [warp][z, ux, uz, w][particle of the piece]
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    double(*my)[32 * PIC_K] = stage[threadIdx.x >> 5];
+    double(*my)[PASS == 0 ? 32 * PIC_K : 1] = stage[PASS == 0 ? (threadIdx.x >> 5) : 0];
     const long long warp0 = ((long long)blockIdx.x * PIC_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * PIC_THREADS) >> 5;
     for (long long piece = warp0; piece < n_pieces; piece += n_warps) {
@@ -562,8 +569,8 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
     int dev = 0, sms = 0, per_sm = 0;
     PF_CUDA(cudaGetDevice(&dev));
     PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (deposit) PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pic_step1<true>, PIC_THREADS, 0));
-    else PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pic_step1<false>, PIC_THREADS, 0));
+    if (deposit) PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pic_step1<true, 0>, PIC_THREADS, 0));
+    else PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pic_step1<false, 0>, PIC_THREADS, 0));
     if (per_sm < 1) return set_err(PF_E_CUDA, "k_pic_step1 does not fit on an SM");
     const long long need = (n_pieces * 32 + PIC_THREADS - 1) / PIC_THREADS;
     const unsigned blocks = (unsigned)std::min<long long>(need, (long long)sms * per_sm);
@@ -583,8 +590,11 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
         const unsigned grid = pass == 0 ? blocks : (unsigned)need;
         {
             ProfScope prof(st, pass == 1 ? "k_pic_step1<count>" : (deposit ? "k_pic_step1<place+deposit>" : "k_pic_step1<place>"));
-            if (deposit) k_pic_step1<true><<<grid, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, part, pass);
-            else k_pic_step1<false><<<grid, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, nullptr, pass);
+#define PF_PIC_LAUNCH(DEPV, PASSV) k_pic_step1<DEPV, PASSV><<<grid, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, DEPV ? part : nullptr)
+            if (pass == 0) { if (deposit) PF_PIC_LAUNCH(true, 0); else PF_PIC_LAUNCH(false, 0); }
+            else if (pass == 1) PF_PIC_LAUNCH(false, 1);          // (the count pass does not deposit)
+            else { if (deposit) PF_PIC_LAUNCH(true, 2); else PF_PIC_LAUNCH(false, 2); }
+#undef PF_PIC_LAUNCH
         }
         PF_LAUNCH_CHECK("k_pic_step1");
     }

@@ -35,3 +35,17 @@ tot, ts = sum(c.values()), max(1, sum(s.values()))
 print(f"executed warp-instructions: {tot}")
 for op, n in c.most_common(16):
     print(f"  {op:8s} {100*n/tot:5.1f}% of instructions, {100*s[op]/ts:5.1f}% of stall samples")
+
+# optional: python tools/ncu_summary.py REP --traffic-json KEY  -> merges the capture's DRAM bytes per launch into
+# profiles/ncu_traffic.json under KEY (bench.py's roofline.traffic reads it for the matching workload)
+if len(sys.argv) > 3 and sys.argv[2] == "--traffic-json":
+    import json, os
+    key = sys.argv[3]
+    get = lambda name: float(vals[hdr.index(name)].replace(",", "")) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[units[hdr.index(name)]]
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[key] = {"dram_bytes_read": get("dram__bytes_read.sum"), "dram_bytes_write": get("dram__bytes_write.sum"),
+                 "kernel": vals[hdr.index("Kernel Name")], "duration_ms_under_ncu": vals[hdr.index("gpu__time_duration.sum")],
+                 "source": "ncu --set full --clock-control none, one launch: " + os.path.basename(rep)}
+    json.dump(data, open(path, "w"), indent=1)
+    print("wrote", path, key, data[key])
