@@ -71,9 +71,10 @@ def dp_instr_per_step(L, pw, mf, mr, mode="lorentz"):
     """Separately rounded fp64 instructions of the reference's OWN arithmetic per time step, summed over members (exact
     mode): vacuum cell 6 (Ex 3 + Hy 3); CPML cell +10 (psi_E 3 + correction 2 + psi_H 3 + correction 2); Lorentz slab cell 15
     (P 5, dH 1, Dx 2, Dx-P 1, /eps0 3, Hy 3; its Ex += ... is dead because ADE_ExCreate overwrites it) and +6 where the slab
-    lies inside the CPML.  Cubic slab cell (mode "nl"): 72, the fp64 instructions the closed-form law executes per slab
-    cell-step (ncu, profiles/r1g_k_tile_nl_closed_ncu.txt: sqrt, two cbrt and four divisions expanded) -- an EXECUTED count,
-    the reference's own expression has ~20 simple operations + 4 divisions + 1 sqrt + 2 pow."""
+    lies inside the CPML.  Cubic slab cell (mode "nl"): 50, the DADD / DMUL / DFMA instructions the closed-form law executes
+    per slab cell-step (ncu, profiles/r2e_k_tile_nl_closed_ncu.txt: 2.78e8 fp64 warp-instructions per 256-member x 64-step
+    launch, halo recomputation and the non-slab cells taken out; sqrt, two cube roots and four divisions expanded) -- an
+    EXECUTED count: the reference's own expression has ~20 simple operations + 4 divisions + 1 sqrt + 2 pow."""
     L, pw, mf, mr = (np.asarray(x, dtype=np.float64) for x in (L, pw, mf, mr))
     cpml_left = np.maximum(0, pw - 1)
     slab = np.maximum(0, mr - mf)
@@ -81,7 +82,7 @@ def dp_instr_per_step(L, pw, mf, mr, mode="lorentz"):
     vac = L - slab
     if mode == "free":
         return float(np.sum(6 * L + 10 * (cpml_left + pw)))
-    per_slab = 72.0 if mode == "nl" else 15.0
+    per_slab = 50.0 if mode == "nl" else 15.0
     return float(np.sum(6 * vac + 10 * (cpml_left + 2) + per_slab * slab + 6 * slab_in_cpml))
 
 
@@ -405,7 +406,7 @@ def other_configs(torch, nat, dist, rank, world, args, fp64_peak, hbm_peak):
                       "cubic_solves_per_s": slab * S * world / sec_max,
                       "cubic": "Newton root (PF_F_NEWTON; <= 1e-10 absolute on Acubic)" if kw else "closed form (the reference's algorithm)",
                       "rank0_roofline": roofline_entry(kern, 2, dp, ab, 64, tile_cells, fp64_peak, hbm_peak,
-                                                       "slab cells counted at 72 EXECUTED fp64 instructions per cell-step (closed form)")}
+                                                       "slab cells counted at 50 EXECUTED fp64 instructions per cell-step (closed-form law, ncu r2e); Newton variant executes fewer")}
         del batch
         torch.cuda.empty_cache()
 
