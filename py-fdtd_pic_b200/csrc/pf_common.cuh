@@ -17,8 +17,6 @@ extern std::atomic<unsigned long long> g_launches; // pf_launch_count()
 
 int set_err(int code, const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
-// n0 .. n0+nsteps-1 inside the caller's source tables / probe rows? (pf_tile.cu)
-int check_step_range(const PfGrid &g, int n0, int nsteps, const char *who);
 
 // Optional per-launch timing (pf_profile_enable / pf_profile_report): while enabled, a ProfScope brackets a kernel launch
 // with CUDA events on the launch's own stream and files them under the kernel's name.  Defined in pf_probe.cu.

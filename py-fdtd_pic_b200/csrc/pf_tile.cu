@@ -36,15 +36,7 @@
 #include <vector>
 #include "pf_common.cuh"
 
-// This file is compiled twice: as itself (1024-cell tiles, the throughput engine) and, included by pf_tile_small.cu with
-// PF_TILE_SECONDARY defined, as namespace pf::small with 256-cell tiles -- the LATENCY variant for a single short grid
-// (one default-geometry Controller() run is 15 tiles of 1024 cells: 15 of 148 SMs, every step paced by one CTA's 16 warps
-// queueing on an SM's FP64 pipe; as 100+ tiles of 128 threads the same run spreads over the whole chip and a step costs one
-// warp per SM sub-partition).  The extern "C" entry points exist once (primary build) and pick the engine per call.
 namespace pf {
-#ifdef PF_TILE_SECONDARY
-namespace small {
-#endif
 
 #ifndef PF_TILE_CELLS
 #define PF_TILE_CELLS 1024
@@ -59,10 +51,7 @@ namespace small {
 #define PF_TILE_KDEF 64
 #endif
 constexpr int TILE_CELLS = PF_TILE_CELLS;   // cells per tile (interior + 2 halos)
-#ifndef PF_TILE_KMAX
-#define PF_TILE_KMAX (PF_TILE_CELLS / 8)
-#endif
-constexpr int TILE_KMAX = PF_TILE_KMAX;   // halo <= TILE_KMAX per side
+constexpr int TILE_KMAX = TILE_CELLS / 8;   // halo <= TILE_KMAX per side
 constexpr int TILE_KDEF = PF_TILE_KDEF;     // default steps per launch
 
 struct TileGrid {
@@ -922,9 +911,6 @@ static inline bool piece_has_pml(const PfGrid &g)
 static inline bool piece_has_slab(const PfGrid &g) { return g.z0 < g.mr && g.z0 + g.L > g.mf; }
 
 // n0 .. n0+nsteps-1 must lie inside the caller's source tables and probe rows (PfGrid.n_src / probe_stride)
-#ifdef PF_TILE_SECONDARY
-using ::pf::check_step_range;
-#else
 int check_step_range(const PfGrid &g, int n0, int nsteps, const char *who)
 {
     if (n0 < 0 || nsteps < 0) return set_err(PF_E_ARG, "%s: negative step range", who);
@@ -936,8 +922,6 @@ int check_step_range(const PfGrid &g, int n0, int nsteps, const char *who)
         return set_err(PF_E_ARG, "%s: steps %d..%lld run past the probe rows (probe_stride = %d)", who, n0, end - 1, g.probe_stride);
     return 0;
 }
-
-#endif
 
 static int tile_supported(const PfGrid &g, int mode)
 {
@@ -994,11 +978,7 @@ static const char *tile_kernel_name()
         const char *mode = MODE == PF_FREE ? "FREE" : MODE == PF_LORENTZ ? "LORENTZ" : MODE == PF_NL ? "NL" : "LORENTZ_NL";
         const char *ar = std::is_same<A, Exact>::value ? "Exact" : std::is_same<A, Fused>::value ? "Fused"
                          : std::is_same<A, Fast32>::value ? "Fast32" : "ExactNewton";
-#ifdef PF_TILE_SECONDARY
-        snprintf(name, sizeof(name), "small::k_tile<%s,POL=%d,C=%d,%s>", mode, (int)POL, C, ar);
-#else
         snprintf(name, sizeof(name), "k_tile<%s,POL=%d,C=%d,%s>", mode, (int)POL, C, ar);
-#endif
     }
     return name;
 }
@@ -1294,33 +1274,8 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
     return launch_tile_mode(mode, do_pol, fma, wide, (int)ht.size(), dg, dt, 0, 0, n0, ks, halo, st);
 }
 
-size_t tile_scratch_bytes(const PfGrid *grids, int n_grids)
-{
-    // sized for the largest state set (Lorentz) and the smallest tile interior (largest tile count)
-    return tile_plan(grids, n_grids, PF_LORENTZ, TILE_KMAX).total;
-}
-
-#ifdef PF_TILE_SECONDARY
-}  // namespace small
-}  // namespace pf
-#else
 int ops_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, double *snap_out,
                  int snap_interval, int snap_rows, cudaStream_t st);
-namespace small {   // pf_tile_small.cu
-int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int *nsteps, int k_block,
-             double *snap_out, int snap_interval, int snap_rows, void *scratch, size_t scratch_bytes, cudaStream_t st);
-size_t tile_scratch_bytes(const PfGrid *grids, int n_grids);
-}
-
-// A single grid that does not even fill half the SMs with 1024-cell tiles is latency-bound: the small-tile engine wins.
-static bool prefer_small_tiles(const PfGrid *grids, int n)
-{
-    if (n != 1) return false;
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles = (grids[0].L + (TILE_CELLS - 2 * TILE_KDEF) - 1) / (TILE_CELLS - 2 * TILE_KDEF);
-    return tiles * 2 <= sms && !(grids[0].flags & PF_F_FP32);
-}
 
 }  // namespace pf
 
@@ -1331,7 +1286,8 @@ extern "C" {
 size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine)
 {
     if (engine != PF_ENGINE_TILE || !grids || n_grids <= 0) return 0;
-    return std::max(tile_scratch_bytes(grids, n_grids), n_grids == 1 ? small::tile_scratch_bytes(grids, n_grids) : (size_t)0);
+    // sized for the largest state set (Lorentz) and the smallest tile interior (largest tile count)
+    return tile_plan(grids, n_grids, PF_LORENTZ, TILE_KMAX).total;
 }
 
 int pf_run_block(const PfGrid *src, const PfGrid *dst, int n_grids, int mode, int do_pol, int n0, int ksteps, int halo,
@@ -1373,11 +1329,8 @@ int pf_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, int e
         if (rc) return rc;
     }
     if (engine == PF_ENGINE_OPS) return ops_run_pass(g, mode, do_pol, n0, nsteps, snap_out, snap_interval, snap_rows, st);
-    if (engine == PF_ENGINE_TILE) {
-        if (prefer_small_tiles(g, 1))
-            return small::tile_run(g, 1, mode, do_pol, n0, &nsteps, 0, snap_out, snap_interval, snap_rows, scratch, scratch_bytes, st);
+    if (engine == PF_ENGINE_TILE)
         return tile_run(g, 1, mode, do_pol, n0, &nsteps, 0, snap_out, snap_interval, snap_rows, scratch, scratch_bytes, st);
-    }
     return set_err(PF_E_ARG, "pf_run_pass: bad engine %d", engine);
 }
 
@@ -1391,4 +1344,3 @@ int pf_run_batch(const PfGrid *grids, int n_grids, int mode, int do_pol, int n0,
 }
 
 }  // extern "C"
-#endif   // PF_TILE_SECONDARY

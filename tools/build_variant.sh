@@ -9,7 +9,7 @@ cd "$(dirname "$0")/../py-fdtd_pic_b200/csrc"
 make -s -j4 >/dev/null
 mkdir -p ../variants /tmp/pfv_$name
 objs=""
-for f in pf_host.cu pf_setup.cu pf_probe.cu pf_ops.cu pf_tile.cu pf_tile_small.cu pf_pic.cu pf_halo.cu pf_dormant.cu; do
+for f in pf_host.cu pf_setup.cu pf_probe.cu pf_ops.cu pf_tile.cu pf_pic.cu pf_halo.cu pf_dormant.cu; do
   if [[ " $files " == *" $f "* ]]; then
     nvcc $flags -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -ffp-contract=off -Xptxas -v --fmad=false -c $f -o /tmp/pfv_$name/${f%.cu}.o 2> /tmp/pfv_$name/${f%.cu}.log
     objs="$objs /tmp/pfv_$name/${f%.cu}.o"
