@@ -101,9 +101,18 @@ class Variables(_TypedStruct):
         self.chi3Stat = 1e-3
         self.roots = np.zeros(4, dtype=np.complex128)
 
+    def _build_ex_history(self):
+        """Ex_History on first touch: zeros, plus the snapshot rows the integrators left ON THE DEVICE (Solver_Engine
+        run_time_loop parks them there: a default run's history is 50 MB that most callers never read)."""
+        h = np.zeros((self._rows, self._L))
+        for t, lo, hi in self.__dict__.pop("_pending_history", []):
+            h[lo:hi] = t[lo:hi].cpu().numpy()
+        return h
+
     _lazy = {
+        "Ex_History": lambda self: self._build_ex_history(),
         **{k: (lambda self: np.zeros((self._rows, self._L)))
-           for k in "Ex_History Hy_History Jx_History polCurr_History Dx_History Psi_e_History".split()},
+           for k in "Hy_History Jx_History polCurr_History Dx_History Psi_e_History".split()},
         "cubPoly": lambda self: np.zeros((self._L, 4), dtype=np.complex128),
     }
 

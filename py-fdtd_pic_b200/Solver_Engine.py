@@ -198,14 +198,18 @@ def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=F
     if mode in ("nl", "lorentz_nl"):
         V.Acubic = out["Acubic"]
     if snap_t is not None:
-        stage = dev.pinned_buffer(rows * L, tag="history").view(rows, L)
-        stage.copy_(snap_t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        hist = stage.numpy()
         n_abs = np.arange(rows) * int(P.vidInterval)
         done = np.flatnonzero((n_abs > 0) & (n_abs >= n0) & (n_abs < n0 + nsteps))
-        if len(done):                               # a contiguous block of rows: one memcpy, no mask temporaries
-            V.Ex_History[done[0]:done[-1] + 1] = hist[done[0]:done[-1] + 1]
+        if len(done):                               # a contiguous block of rows
+            lo, hi = int(done[0]), int(done[-1]) + 1
+            if "Ex_History" in V.__dict__ or not hasattr(V, "_build_ex_history") or getattr(V, "_rows", rows) != rows:
+                stage = dev.pinned_buffer(rows * L, tag="history").view(rows, L)     # already materialised: update it now
+                stage.copy_(snap_t, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                V.Ex_History[lo:hi] = stage.numpy()[lo:hi]
+            else:
+                # leave the rows on the device; V.Ex_History downloads them when it is first read (vidMake / VideoMaker)
+                V.__dict__.setdefault("_pending_history", []).append((snap_t, lo, hi))
     LAST_RUN_INFO.update(engine="tile" if engine == nat.PF_ENGINE_TILE else "ops", h2d_bytes=g.h2d_bytes,
                          d2h_bytes=g.d2h_bytes, launches=lib.pf_launch_count() - launches0, cells=L, steps=nsteps)
     return out["probe_out"]
