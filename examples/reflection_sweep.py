@@ -39,3 +39,17 @@ print(f"{a.points} sweep members in {dt:.2f} s")
 print("  f [GHz]   measured   analytical (Fresnel)")
 for f, m, an in zip(freqs, measured, analytical):
     print(f"  {f / 1e9:6.2f}    {m:.4f}     {an:.4f}")
+
+# The same physics for MANY frequencies at once -- the product call behind bench.py's `e2e_full_sweep`: every grid is
+# envSetup(f, ...) on its own (no member-to-member sizing chain), setup vectorised over members, inputs built natively,
+# reflection extracted on the device.
+import numpy as np  # noqa: E402
+from pyfdtd_b200 import sweep  # noqa: E402
+
+fr = np.linspace(a.low, a.low + a.interval * (a.points - 1), 256)
+t0 = time.perf_counter()
+res = sweep.reflection_sweep(fr, a.domain, 7000, 8000, periods=1000)
+dt = time.perf_counter() - t0
+print(f"sweep.reflection_sweep: {len(fr)} distinct grids, {res['cell_steps'] / 1e9:.0f} Gcell-updates in {dt:.2f} s "
+      f"(host setup {res['timing']['setup_s'] * 1e3:.0f} ms + input building {res['timing']['build_inputs_s'] * 1e3:.0f} ms)")
+print("  R(f) first / last:", res["measured"][0], res["measured"][-1], " Fresnel:", res["analytical"][0], res["analytical"][-1])

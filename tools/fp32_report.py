@@ -52,10 +52,8 @@ def speed(only=None):
                                     ("fp64_newton", False, False, "newton"), ("fp32", True, False, "closed")):
         if only and label not in only:
             continue
-        SE.USE_FP32, SE.USE_FMA, SE.CUBIC = fp32, fma, cubic
         try:
-            wl = bench.ProductWorkload(1024, 512, 64)
-            b = wl.batch
+            b, table = bench.lorentz_sweep_batch(1024, 512, 64, fma=fma, fp32=fp32)
             b.upload()
             b.randomize_state(seed=1234)
 
@@ -63,20 +61,22 @@ def speed(only=None):
                 b.reset_state(template=True)
                 b.run(do_pol=True)
             sec = bench._time_cuda(torch, step, 3)
-            out["lorentz_sweep_" + label] = wl.cell_steps / sec / 1e9
-            del b, wl
+            out["lorentz_sweep_" + label] = b.cell_steps / sec / 1e9
+            del b
             torch.cuda.empty_cache()
-            nb, members = bench.build_nl_batch(256, 128)
+            nb, table = bench.nl_sweep_batch(256, 128, fp32=fp32, newton=(cubic == "newton"))
+            nb.upload()
+            nb.randomize_state()
 
             def nstep():
                 nb.reset_state(template=True)
                 nb.run(do_pol=False)
             sec = bench._time_cuda(torch, nstep, 2)
             out["nl_sweep_" + label] = nb.cell_steps / sec / 1e9
-            del nb, members
+            del nb
             torch.cuda.empty_cache()
         finally:
-            SE.USE_FP32, SE.USE_FMA, SE.CUBIC = False, False, "closed"
+            pass
         print(label, {k: round(v, 1) for k, v in out.items() if k.endswith(label)}, flush=True)
     return out
 
