@@ -254,7 +254,14 @@ def cpu_port_rate(n_members, steps, threads, n_freq=64, warmup=1, reps=1):
 
 def workload_text(members, steps, n_freq):
     return (f"batched Lorentz-ADE+CPML 1D FDTD sweep (IntegratorLinLor1D pass-1 loop), {members} members/GPU "
-            f"({n_freq} frequencies 6-10.5 GHz x amplitudes) x {steps} time steps per step, Nz~10-15k cells/member")
+            f"({n_freq} frequencies 6-10.5 GHz x amplitudes) x {steps} time steps per step, Nz~10-15k cells/member, "
+            "probes recorded every step, synthetic non-zero state")
+
+
+def workload_config(args, arithmetic="exact (bit-identical to reference order)"):
+    """The `config` object: the WORKLOAD only, identical for both arms (how an arm runs it goes under `run`)."""
+    return {"workload": workload_text(args.members, args.pass_steps, args.n_freq), "members_per_gpu": args.members,
+            "time_steps_per_step": args.pass_steps, "n_freq": args.n_freq, "arithmetic": arithmetic}
 
 
 def run_reference_arm(args, rank):
@@ -266,8 +273,9 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.members, args.pass_steps, args.n_freq) + f" ({cells/1e9:.2f} Gcell-updates/step)",
-                   "members_per_gpu": args.members, "time_steps_per_step": args.pass_steps, "same_workload_as_gpu_arm": True},
+        "config": workload_config(args),
+        "run": {"cell_updates_per_step": cells, "host_threads": threads, "what": "C port of the reference loop (oracle/fdtd_oracle.c), "
+                "one member per thread, the same members, steps, sources and synthetic state as the GPU arm"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"the full bench step: {args.members} members x {args.pass_steps} steps "
                                    f"({cells/1e9:.2f} Gcell-updates), C port of the reference loop (oracle/fdtd_oracle.c), "
@@ -663,14 +671,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
-            "config": {"workload": workload_text(args.members, args.pass_steps, args.n_freq)
-                                   + f" ({cell_steps/1e9:.2f} Gcell-updates/step/GPU), probes recorded every step",
-                       "members_per_gpu": args.members, "time_steps_per_step": args.pass_steps,
-                       "k_block": k_block, "arithmetic": ("fp32 on chip (PF_F_FP32; not a parity mode)" if args.fp32 else
+            "config": workload_config(args, "fp32 on chip (PF_F_FP32; not a parity mode)" if args.fp32 else
                                       "fma-contracted" if args.fma else "exact (bit-identical to reference order)"),
-                       "l2_policy": f"state {cfg_state_mb:.0f} MB per GPU > 126 MB L2, restored from a random template every step",
-                       "parallelism": f"members sharded over {world} GPU(s), no collectives",
-                       "batch_setup_s": setup_s},
+            "run": {"cell_updates_per_step_per_gpu": cell_steps, "k_block": k_block,
+                    "l2_policy": f"state {cfg_state_mb:.0f} MB per GPU > 126 MB L2, restored from a random template every step",
+                    "parallelism": f"members sharded over {world} GPU(s), no collectives", "batch_setup_s": setup_s},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
                     "ms_per_step": e2e_ms / args.steps, "probe_checksum": probe_checksum,
                     "how": "sweep.BatchPipeline: steps alternate between two batch pools; H2D of the next step's inputs and D2H of "

@@ -713,13 +713,18 @@ def reflection_sweep(freqs, domainSize, lowLimTim, highLimTim, *, amps=1.0, peri
     import time
     from . import sweep_setup
     nat.require_cuda()
+    if threads == 0 and world_size > 1:
+        import os
+        threads = max(1, (os.cpu_count() or 1) // world_size)      # one process per GPU on one host: share its cores
     t_start = time.perf_counter()
     freqs = np.ascontiguousarray(freqs, dtype=np.float64)
-    tables = sweep_setup.lorentz_sweep_tables(freqs, amps, domainSize, lowLimTim, highLimTim, periods=periods, tfsf=tfsf,
+    mine = np.arange(rank, len(freqs), world_size)
+    amps_mine = np.broadcast_to(np.asarray(amps, dtype=np.float64), freqs.shape)[mine]
+    # (only this rank's members are set up: the host chain is per member, nothing is shared between ranks)
+    tables = sweep_setup.lorentz_sweep_tables(freqs[mine], amps_mine, domainSize, lowLimTim, highLimTim, periods=periods, tfsf=tfsf,
                                               nsteps=nsteps, fma=fma, fp32=fp32)
     t_setup = time.perf_counter() - t_start
-    mine = np.arange(rank, len(freqs), world_size)
-    analytical = _analytical_reflection(freqs[mine], tables[1].wp[mine])     # medium as Controller leaves it
-    R, cell_steps, t_build, _ = _run_reflection_tables(tables, mine, chunk=chunk, k_block=k_block, threads=threads)
+    analytical = _analytical_reflection(freqs[mine], tables[1].wp)     # medium as Controller leaves it
+    R, cell_steps, t_build, _ = _run_reflection_tables(tables, np.arange(len(mine)), chunk=chunk, k_block=k_block, threads=threads)
     return dict(index=mine, freq=freqs[mine], measured=R, analytical=analytical, cell_steps=cell_steps,
                 timing=dict(setup_s=t_setup, build_inputs_s=t_build, total_s=time.perf_counter() - t_start))
