@@ -565,6 +565,8 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
     unsigned long long *pub = (unsigned long long *)(s + pl.off_counts);
     const long long n_pieces = (long long)p->L * S;
     PF_CUDA(cudaMemsetAsync(pub, 0, sizeof(unsigned long long) * (size_t)n_pieces, st));
+    const long long need = (n_pieces * 32 + PIC_THREADS - 1) / PIC_THREADS;
+#ifdef PF_PIC_SINGLE_PASS
     // persistent grid: every CTA resident (the kernel's warps wait for one another's publications)
     int dev = 0, sms = 0, per_sm = 0;
     PF_CUDA(cudaGetDevice(&dev));
@@ -572,10 +574,12 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
     if (deposit) PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pic_step1<true, 0>, PIC_THREADS, 0));
     else PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pic_step1<false, 0>, PIC_THREADS, 0));
     if (per_sm < 1) return set_err(PF_E_CUDA, "k_pic_step1 does not fit on an SM");
-    const long long need = (n_pieces * 32 + PIC_THREADS - 1) / PIC_THREADS;
     const unsigned blocks = (unsigned)std::min<long long>(need, (long long)sms * per_sm);
     if ((long long)blocks < need && (long long)blocks * (PIC_THREADS / 32) <= 4LL * S)
         return set_err(PF_E_UNSUPPORTED, "pf_pic_step_sorted: too few resident warps for %d pieces per cell", S);
+#else
+    const unsigned blocks = (unsigned)need;
+#endif
     double *part = (double *)(s + pl.off_part);
     // PF_PIC_SINGLE_PASS: one launch (pass 0).  Default: two launches of the same kernel (pass 1, pass 2) -- measured on a B200
     // at 2e7 particles the single launch is slower (1.28 ms against ~0.6 ms): its warps spend their time polling for the
@@ -591,8 +595,10 @@ static int pic_push_sorted(const PfPic *p, void *scratch, size_t scratch_bytes, 
         {
             ProfScope prof(st, pass == 1 ? "k_pic_step1<count>" : (deposit ? "k_pic_step1<place+deposit>" : "k_pic_step1<place>"));
 #define PF_PIC_LAUNCH(DEPV, PASSV) k_pic_step1<DEPV, PASSV><<<grid, PIC_THREADS, 0, st>>>(*p, pic_derived(p), start, new_start, pub, err, S, n_pieces, DEPV ? part : nullptr)
-            if (pass == 0) { if (deposit) PF_PIC_LAUNCH(true, 0); else PF_PIC_LAUNCH(false, 0); }
-            else if (pass == 1) PF_PIC_LAUNCH(false, 1);          // (the count pass does not deposit)
+#ifdef PF_PIC_SINGLE_PASS
+            if (pass == 0) { if (deposit) PF_PIC_LAUNCH(true, 0); else PF_PIC_LAUNCH(false, 0); } else
+#endif
+            if (pass == 1) PF_PIC_LAUNCH(false, 1);          // (the count pass does not deposit)
             else { if (deposit) PF_PIC_LAUNCH(true, 2); else PF_PIC_LAUNCH(false, 2); }
 #undef PF_PIC_LAUNCH
         }
