@@ -62,10 +62,17 @@ struct TileGrid {
 };
 enum { S_EX = 0, S_HY, S_PSIE, S_PSIH, S_DX, S_P, S_PP, S_COUNT };
 
+constexpr int TILE_MAX_WARPS = 32;
 struct TileDesc {
     int grid;
-    int base;  // local index of the tile's first cell (interior starts at base + halo)
+    int base;        // local index of the tile's first cell (interior starts at base + halo)
+    unsigned flags;  // TILE_F_*: written by k_tile_classify
+    int cls_c;       // cells per thread the classes below were computed for
+    // warp class of every warp of the tile (k_tile_classify): the per-tile prologue of k_tile reads one byte instead of
+    // re-deriving the region masks of its cells on every launch (the geometry of a tile never changes)
+    unsigned char cls[TILE_MAX_WARPS];
 };
+enum { TILE_F_SPECIAL = 1 };   // the tile holds a source cell or a probe
 
 // shared memory carve-up (doubles): 7 per-cell coefficient arrays + edge exchange + source tables
 template <int MODE, int C, class R>
@@ -187,6 +194,93 @@ struct CellMasks {
     size_t po0, po1;
 };
 
+// Masks of the C cells [lz0, lz0+C) of one thread: the index rules of the reference loops (update ranges, CPML ranges with
+// the exclusive-end quirk cell, slab, source cells) plus which cells this tile stores (its interior).
+template <int C>
+__device__ __forceinline__ void tile_cell_masks(const PfGrid &g, int tile_base, int lz0, int halo, CellMasks &M)
+{
+    const int L = g.L;
+    const int z0 = (int)g.z0, Lg = (int)g.Lg;
+    const int pw = g.pw, mf = g.mf, mr = g.mr;
+    const int flags = g.flags;
+    M.valid = M.updE = M.updH = M.pmlE = M.pmlH = M.slab = M.store = M.quirk = 0;
+    M.jsrc = M.jtfsf = M.pj0 = M.pj1 = -1;
+    M.po0 = M.po1 = 0;
+    const bool cpml_m = flags & PF_F_CPML_M, cpml_p = flags & PF_F_CPML_P;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        int lz = lz0 + j, gz = z0 + lz;
+        bool valid = lz >= 0 && lz < L;
+        bool updE = valid && lz >= 1 && gz >= 1 && gz <= Lg - 1;
+        bool updH = valid && lz <= L - 2 && gz >= 1 && gz <= Lg - 2;
+        bool inL = cpml_m && gz < pw, inR = cpml_p && gz >= Lg - pw;
+        bool slab = valid && lz >= 1 && gz >= mf && gz < mr;
+        bool interior = (lz - tile_base) >= halo && (lz - tile_base) < TILE_CELLS - halo;
+        M.valid |= (unsigned)valid << j;
+        M.updE |= (unsigned)updE << j;
+        M.updH |= (unsigned)updH << j;
+        M.pmlE |= (unsigned)(updE && (inL || inR)) << j;
+        M.pmlH |= (unsigned)(updH && (inL || inR)) << j;
+        M.slab |= (unsigned)slab << j;
+        M.store |= (unsigned)(valid && interior) << j;
+        M.quirk |= (unsigned)(gz == Lg - pw) << j;
+    }
+}
+
+// masks of a thread whose warp is entirely inside one region (warp classes 0..3): only the store mask is ever looked at
+template <int C>
+__device__ __forceinline__ void tile_plain_masks(int tid, int halo, int cls, CellMasks &M)
+{
+    constexpr unsigned ALL = (1u << C) - 1u;
+    M.valid = M.updE = M.updH = (cls == 5) ? 0u : ALL;
+    M.pmlE = M.pmlH = (cls & 2) && cls != 5 ? ALL : 0u;
+    M.slab = (cls & 1) && cls != 5 ? ALL : 0u;
+    M.quirk = 0;
+    M.store = 0;
+    M.jsrc = M.jtfsf = M.pj0 = M.pj1 = -1;
+    M.po0 = M.po1 = 0;
+#pragma unroll
+    for (int j = 0; j < C; ++j) M.store |= (unsigned)(tid * C + j >= halo && tid * C + j < TILE_CELLS - halo) << j;
+}
+
+// source cells and probes among the thread's cells (at most 2 probes per thread; guaranteed by the host layer);
+// returns true if the thread owns any
+template <int C>
+__device__ __forceinline__ bool tile_special_cells(const PfGrid &g, int lz0, CellMasks &M)
+{
+    const int z0 = (int)g.z0;
+    {
+        const int j = g.nzsrc - z0 - lz0;
+        if (j >= 0 && j < C && lz0 + j >= 0 && lz0 + j < g.L) M.jsrc = j;
+        if ((g.flags & PF_F_TFSF) && j - 1 >= 0 && j - 1 < C && lz0 + j - 1 >= 0 && lz0 + j - 1 < g.L) M.jtfsf = j - 1;
+    }
+    for (int p = 0; p < g.n_probes; ++p) {
+        int j = g.probe_idx[p] - z0 - lz0;
+        if (j >= 0 && j < C && ((M.store >> j) & 1)) {
+            if (M.pj0 < 0) { M.pj0 = j; M.po0 = (size_t)p * g.probe_stride; }
+            else { M.pj1 = j; M.po1 = (size_t)p * g.probe_stride; }
+        }
+    }
+    return M.jsrc >= 0 || M.jtfsf >= 0 || M.pj0 >= 0;
+}
+
+// warp class: 0 vacuum, 1 slab, 2 CPML, 3 slab+CPML, 4 mixed, 5 dead (warp-uniform result)
+// (a source cell inside a material-law cell would be overwritten anyway; it is sent to the
+//  mixed body only to keep the fast slab body free of the test)
+template <int C>
+__device__ __forceinline__ int tile_warp_class(const CellMasks &M)
+{
+    constexpr unsigned ALL = (1u << C) - 1u;
+    int cls = 4;
+    const bool plain = M.valid == ALL && M.updE == ALL && M.updH == ALL && M.quirk == 0;
+    const bool pmlAll = M.pmlE == ALL && M.pmlH == ALL, pmlNone = (M.pmlE | M.pmlH) == 0;
+    const bool slabAll = M.slab == ALL, slabNone = M.slab == 0;
+    if (plain && (pmlAll || pmlNone) && (slabAll || slabNone)) cls = (slabAll ? 1 : 0) + (pmlAll ? 2 : 0);
+    if (M.valid == 0) cls = 5;                    // cells beyond the end of the grid
+    const int cls0 = __shfl_sync(0xffffffffu, cls, 0);
+    return __all_sync(0xffffffffu, cls == cls0) ? cls0 : 4;
+}
+
 // -------------------------------------------------------------------------------------------------
 // One body for every warp class.  All field / material / CPML state of the thread's C cells lives in
 // registers for the whole launch.
@@ -197,6 +291,19 @@ struct CellMasks {
 //                 exactly 0 turns its term into an exact no-op (x + y*0 == x), so no per-cell branch
 //                 is needed; only the material law is selected per cell.
 // -------------------------------------------------------------------------------------------------
+// Where a warp keeps the CPML profiles b, c_e, c_m of its cells: mixed warps in their shared-memory slots, every uniform
+// class in registers.  -DPF_PML_COEF_SMEM=1 moves them to shared memory for the slab+CPML body too (7 state arrays, 3
+// profiles and the step constants are more than the 64-register budget holds comfortably): measured 546 against 597
+// Gcell-updates/s on the sweep, the loads land on the step's dependency chain (profiles/r2_tile_experiments.md).
+#ifndef PF_PML_COEF_SMEM
+#define PF_PML_COEF_SMEM 0
+#endif
+template <int MODE, int C, bool GEN, bool SLAB, bool PML, class R>
+__device__ __forceinline__ constexpr bool pml_coef_in_smem()
+{
+    return GEN || (PF_PML_COEF_SMEM && PML && SLAB && MODE != PF_FREE && C == 2 && std::is_same<R, double>::value);
+}
+
 // Everything a time step needs besides the per-cell register arrays.
 template <class R>
 struct StepConsts {
@@ -259,6 +366,7 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
     constexpr bool HAS_MAT = (GEN || SLAB) && MODE != PF_FREE;
     constexpr bool ALL_MAT = !GEN && SLAB && MODE != PF_FREE;
     constexpr bool HAS_PML = GEN || PML;
+    constexpr bool PS = pml_coef_in_smem<MODE, C, GEN, SLAB, PML, R>();
     // ===== E half-step: history shift + polarisation, ADE_ExUpdate, CPML_Psi_e, source,
     //                    ADE_DxUpdate, ADE_ExCreate | AcubicFinder + NonLinExUpdate =====
 #ifdef PF_WARP_XCHG
@@ -306,8 +414,8 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
             else e = A::mad(dHJ, GEN ? (R)S.cEu[j * NT + tid] : K.cEs, e);
         }
         if (HAS_PML) {
-            const R b = GEN ? (R)S.be[j * NT + tid] : rbe[j];
-            const R c = GEN ? (R)S.ce[j * NT + tid] : rce[j];
+            const R b = PS ? (R)S.be[j * NT + tid] : rbe[j];
+            const R c = PS ? (R)S.ce[j * NT + tid] : rce[j];
             const R psi = A::mad(b, pe[j], A::mul(c, dH));
             pe[j] = psi;
             if (!ALL_MAT) e = A::nmad(GEN ? (R)S.cb[j * NT + tid] : K.cEs, psi, e);
@@ -438,8 +546,8 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
         const R dE = A::sub((j == C - 1) ? exr : ex[(j + 1) % C], ex[j]);
         h = A::mad(dE, GEN ? (R)S.cHu[j * NT + tid] : K.cHs, h);
         if (HAS_PML) {
-            const R b = GEN ? (R)S.be[j * NT + tid] : rbe[j];
-            const R c = GEN ? (R)S.cm[j * NT + tid] : rcm[j];
+            const R b = PS ? (R)S.be[j * NT + tid] : rbe[j];
+            const R c = PS ? (R)S.cm[j * NT + tid] : rcm[j];
             const R psi = A::mad(b, ph[j], A::mul(c, dE));
             ph[j] = psi;
             h = A::mad(GEN ? (R)S.c2u[j * NT + tid] : K.c2s, psi, h);
@@ -480,7 +588,8 @@ __device__ __forceinline__ void tile_step(const TileShared<R> &S, const StepCons
 // -------------------------------------------------------------------------------------------------
 template <int MODE, bool POL, int C, class A, bool GEN, bool SLAB, bool PML, bool JX, class R = typename A::real>
 __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R> &S, const CellMasks &M, WarpLink W,
-                                          int tid, int lz0, int ks, int src, int nabs0)
+                                          int tid, int lz0, int ks, int src, int nabs0,
+                                          const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, int halo)
 {
     constexpr int NT = TILE_CELLS / C;
     constexpr bool F32 = std::is_same<R, float>::value;
@@ -522,7 +631,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
                 pe[j] = F32 ? (e_ ? inPe[lz] * sH : 0.0) : (e_ ? inPe[lz] : 0.0);
                 ph[j] = h_ ? inPh[lz] : 0.0;
                 const double b = (e_ || h_) ? g.beX[lz] : 0.0, c1 = e_ ? g.ceX[lz] : 0.0, c2 = h_ ? g.cmY[lz] : 0.0;
-                if (GEN) {
+                if (pml_coef_in_smem<MODE, C, GEN, SLAB, PML, R>()) {
                     S.be[j * NT + tid] = (R)b;
                     S.ce[j * NT + tid] = (R)c1;
                     S.cm[j * NT + tid] = (R)c2;
@@ -646,48 +755,64 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
     else time_loop(std::false_type{});
 
     // ---- store interior ---------------------------------------------------------------------------
+    // Uniform-class warps re-derive where their cells go (tile base, grid, store mask) from the block / thread index and the
+    // kernel's parameters instead of carrying those values through the time loop: the loop of the Lorentz slab body sits
+    // exactly at the 64-register budget of two 512-thread CTAs per SM, and four spilled words in it cost 8 % of the sweep.
+    const TileGrid *TGo = &TG;
+    int lz0o = lz0;
+    unsigned st = M.store;
+    if constexpr (!GEN) {
+        unsigned bid, tid2;
+        asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid));
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid2));
+        const TileDesc *tdp = tiles + bid;
+        TGo = grids + tdp->grid;
+        lz0o = tdp->base + (int)tid2 * C;
+        st = 0;
+#pragma unroll
+        for (int j = 0; j < C; ++j) st |= (unsigned)((int)tid2 * C + j >= halo && (int)tid2 * C + j < TILE_CELLS - halo) << j;
+    }
     const int dst = src ^ 1;
-    const unsigned st = M.store;
-    double *__restrict__ outEx = TG.buf[dst][S_EX];
-    double *__restrict__ outHy = TG.buf[dst][S_HY];
+    double *__restrict__ outEx = TGo->buf[dst][S_EX];
+    double *__restrict__ outHy = TGo->buf[dst][S_HY];
 #pragma unroll
     for (int j = 0; j < C; ++j)
-        if ((st >> j) & 1) { outEx[lz0 + j] = ex[j]; outHy[lz0 + j] = F32 ? hy[j] * uH : hy[j]; }
+        if ((st >> j) & 1) { outEx[lz0o + j] = ex[j]; outHy[lz0o + j] = F32 ? hy[j] * uH : hy[j]; }
     if (HAS_PML) {
-        double *__restrict__ outPe = TG.buf[dst][S_PSIE];
-        double *__restrict__ outPh = TG.buf[dst][S_PSIH];
+        double *__restrict__ outPe = TGo->buf[dst][S_PSIE];
+        double *__restrict__ outPh = TGo->buf[dst][S_PSIH];
         const unsigned se = GEN ? (st & M.pmlE) : st, sh = GEN ? (st & M.pmlH) : st;
 #pragma unroll
         for (int j = 0; j < C; ++j) {
-            if ((se >> j) & 1) outPe[lz0 + j] = F32 ? pe[j] * uH : pe[j];
-            if ((sh >> j) & 1) outPh[lz0 + j] = ph[j];
+            if ((se >> j) & 1) outPe[lz0o + j] = F32 ? pe[j] * uH : pe[j];
+            if ((sh >> j) & 1) outPh[lz0o + j] = ph[j];
         }
     }
     if (HAS_MAT) {
         const unsigned sm = GEN ? (st & mSlab) : st;
-        double *__restrict__ outDx = TG.buf[dst][S_DX];
+        double *__restrict__ outDx = TGo->buf[dst][S_DX];
 #pragma unroll
         for (int j = 0; j < C; ++j)
-            if ((sm >> j) & 1) outDx[lz0 + j] = F32 ? (LOR ? ((double)dx[j] + (double)pa[j]) * uD : dx[j] * uD) : dx[j];
+            if ((sm >> j) & 1) outDx[lz0o + j] = F32 ? (LOR ? ((double)dx[j] + (double)pa[j]) * uD : dx[j] * uD) : dx[j];
         if (LOR) {
-            double *__restrict__ outP = TG.buf[dst][S_P];
-            double *__restrict__ outPp = TG.buf[dst][S_PP];
+            double *__restrict__ outP = TGo->buf[dst][S_P];
+            double *__restrict__ outPp = TGo->buf[dst][S_PP];
 #pragma unroll
             for (int j = 0; j < C; ++j)
                 if ((sm >> j) & 1) {
                     if (F32) {
-                        outP[lz0 + j] = pa[j] * uD;
-                        outPp[lz0 + j] = ((double)pa[j] - (double)pb[j]) * uD;
+                        outP[lz0o + j] = pa[j] * uD;
+                        outPp[lz0o + j] = ((double)pa[j] - (double)pb[j]) * uD;
                     } else {
-                        outP[lz0 + j] = swapped ? pb[j] : pa[j];
-                        outPp[lz0 + j] = swapped ? pa[j] : pb[j];
+                        outP[lz0o + j] = swapped ? pb[j] : pa[j];
+                        outPp[lz0o + j] = swapped ? pa[j] : pb[j];
                     }
                 }
         }
-        if (CUB && g.Acubic) {
+        if (CUB && TGo->d.g.Acubic) {
 #pragma unroll
             for (int j = 0; j < C; ++j)
-                if ((sm >> j) & 1) g.Acubic[lz0 + j] = acub[j];
+                if ((sm >> j) & 1) TGo->d.g.Acubic[lz0o + j] = acub[j];
         }
     }
 }
@@ -737,53 +862,28 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     S.srcH.base = S.srcE.base + RB * TILE_KMAX;
     S.xw = (S.srcH.base + RB * TILE_KMAX + 15u) & ~15u;
 
-    const TileDesc td = tiles[blockIdx.x];
-    const TileGrid &TG = grids[td.grid];
+    const TileDesc *__restrict__ tdp = tiles + blockIdx.x;
+    const int tbase = tdp->base;
+    const unsigned tflags = tdp->flags;
+    const TileGrid &TG = grids[tdp->grid];
     const int ks = min(ksteps, TG.nsteps - n_done);
     if (ks <= 0) return;
 
     const PfGrid &g = TG.d.g;
     const int tid = threadIdx.x;
-    const int L = g.L;
-    const int z0 = (int)g.z0, Lg = (int)g.Lg;
-    const int pw = g.pw, mf = g.mf, mr = g.mr;
     const int flags = g.flags;
-    const int lz0 = td.base + tid * C;
+    const int lz0 = tbase + tid * C;
+#ifdef PF_WARP_XCHG
+    const int L = g.L;
+#endif
 
-    // ---- per-cell masks (bit j <-> cell lz0+j) -------------------------------------------
+    // ---- warp class (precomputed per tile) and per-cell masks (bit j <-> cell lz0+j) ------
+    const int cls_t = tdp->cls[tid >> 5];
     CellMasks M;
-    M.valid = M.updE = M.updH = M.pmlE = M.pmlH = M.slab = M.store = M.quirk = 0;
-    M.jsrc = M.jtfsf = M.pj0 = M.pj1 = -1;
-    M.po0 = M.po1 = 0;
-    const bool cpml_m = flags & PF_F_CPML_M, cpml_p = flags & PF_F_CPML_P;
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-        int lz = lz0 + j, gz = z0 + lz;
-        bool valid = lz >= 0 && lz < L;
-        bool updE = valid && lz >= 1 && gz >= 1 && gz <= Lg - 1;
-        bool updH = valid && lz <= L - 2 && gz >= 1 && gz <= Lg - 2;
-        bool inL = cpml_m && gz < pw, inR = cpml_p && gz >= Lg - pw;
-        bool slab = valid && lz >= 1 && gz >= mf && gz < mr;
-        bool interior = (lz - td.base) >= halo && (lz - td.base) < TILE_CELLS - halo;
-        M.valid |= (unsigned)valid << j;
-        M.updE |= (unsigned)updE << j;
-        M.updH |= (unsigned)updH << j;
-        M.pmlE |= (unsigned)(updE && (inL || inR)) << j;
-        M.pmlH |= (unsigned)(updH && (inL || inR)) << j;
-        M.slab |= (unsigned)slab << j;
-        M.store |= (unsigned)(valid && interior) << j;
-        M.quirk |= (unsigned)(gz == Lg - pw) << j;
-        if (valid && gz == g.nzsrc) M.jsrc = j;
-        if (valid && gz == g.nzsrc - 1 && (flags & PF_F_TFSF)) M.jtfsf = j;
-    }
-    // probes owned by this thread (at most 2; guaranteed by the host layer)
-    for (int p = 0; p < g.n_probes; ++p) {
-        int j = g.probe_idx[p] - z0 - lz0;
-        if (j >= 0 && j < C && ((M.store >> j) & 1)) {
-            if (M.pj0 < 0) { M.pj0 = j; M.po0 = (size_t)p * g.probe_stride; }
-            else { M.pj1 = j; M.po1 = (size_t)p * g.probe_stride; }
-        }
-    }
+    if (cls_t == 4) tile_cell_masks<C>(g, tbase, lz0, halo, M);
+    else tile_plain_masks<C>(tid, halo, cls_t, M);
+    if (tflags & TILE_F_SPECIAL) tile_special_cells<C>(g, lz0, M);
+    const int cls = tile_warp_class<C>(M);
     if (tid == 0) { S.edgeH[-1] = R(0); S.edgeE[NT] = R(0); }
     // source tables of this launch's steps (CTA-uniform load)
     const int nabs0 = n0 + n_done;
@@ -791,18 +891,6 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
         S.srcE[s] = (R)g.srcE[nabs0 + s];
         S.srcH[s] = (R)((flags & PF_F_TFSF) ? g.srcH[nabs0 + s] * (std::is_same<R, float>::value ? 1.0 / g.cH0 : 1.0) : 0.0);
     }
-
-    // ---- warp class: 0 vacuum, 1 slab, 2 CPML, 3 slab+CPML, 4 mixed, 5 dead ------------------
-    // (a source cell inside a material-law cell would be overwritten anyway; it is sent to the
-    //  mixed body only to keep the fast slab body free of the test)
-    int cls = 4;
-    const bool plain = M.valid == ALL && M.updE == ALL && M.updH == ALL && M.quirk == 0;
-    const bool pmlAll = M.pmlE == ALL && M.pmlH == ALL, pmlNone = (M.pmlE | M.pmlH) == 0;
-    const bool slabAll = M.slab == ALL, slabNone = M.slab == 0;
-    if (plain && (pmlAll || pmlNone) && (slabAll || slabNone)) cls = (slabAll ? 1 : 0) + (pmlAll ? 2 : 0);
-    if (M.valid == 0) cls = 5;                    // cells beyond the end of the grid
-    const int cls0 = __shfl_sync(0xffffffffu, cls, 0);
-    cls = __all_sync(0xffffffffu, cls == cls0) ? cls0 : 4;
 
     WarpLink W;
     W.pH = W.pE = W.fH = W.fE = 0u;
@@ -812,7 +900,7 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     {
         // a neighbour warp is live iff at least one of its cells lies inside the grid (same test as cls == 5 above)
         const int w = tid >> 5, lane = tid & 31;
-        const int wfirst = td.base + w * 32 * C;           // first cell of this warp
+        const int wfirst = tbase + w * 32 * C;          // first cell of this warp
         const bool live = cls != 5;
         const bool left = live && w > 0 && wfirst - 1 >= 0 && wfirst - 32 * C < L;
         const bool right = live && w < NT / 32 - 1 && wfirst + 32 * C < L && wfirst + 64 * C - 1 >= 0;
@@ -838,10 +926,10 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
 #endif
 
     switch (cls) {
-    case 0: tile_body<MODE, POL, C, A, false, false, false, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
-    case 1: tile_body<MODE, POL, C, A, false, true, false, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
-    case 2: tile_body<MODE, POL, C, A, false, false, true, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
-    case 3: tile_body<MODE, POL, C, A, false, true, true, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    case 0: tile_body<MODE, POL, C, A, false, false, false, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0, grids, tiles, halo); break;
+    case 1: tile_body<MODE, POL, C, A, false, true, false, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0, grids, tiles, halo); break;
+    case 2: tile_body<MODE, POL, C, A, false, false, true, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0, grids, tiles, halo); break;
+    case 3: tile_body<MODE, POL, C, A, false, true, true, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0, grids, tiles, halo); break;
     case 5:
         // nothing to compute: publish zero edges once, then only keep the CTA's barrier count
         S.edgeH[tid] = R(0);
@@ -849,8 +937,27 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
         cta_sync();
         for (int s = 0; s < ks; ++s) { cta_sync(); cta_sync(); }
         break;
-    default: tile_body<MODE, POL, C, A, true, true, true, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0); break;
+    default: tile_body<MODE, POL, C, A, true, true, true, JX>(TG, S, M, W, tid, lz0, ks, src, nabs0, grids, tiles, halo); break;
     }
+}
+
+// Writes the warp classes and flags of every tile (TileDesc::cls / flags): the same mask functions the kernels use, evaluated
+// once per tile table instead of once per launch.  Launched with the thread geometry of the kernel that will read them.
+template <int C>
+__global__ void __launch_bounds__(TILE_CELLS / C) k_tile_classify(const TileGrid *__restrict__ grids, TileDesc *__restrict__ tiles, int halo)
+{
+    TileDesc &td = tiles[blockIdx.x];
+    const PfGrid &g = grids[td.grid].d.g;
+    const int tid = threadIdx.x;
+    const int tbase = td.base;
+    const int lz0 = tbase + tid * C;
+    CellMasks M;
+    tile_cell_masks<C>(g, tbase, lz0, halo, M);
+    const bool special = tile_special_cells<C>(g, lz0, M);
+    const int cls = tile_warp_class<C>(M);
+    if ((tid & 31) == 0) td.cls[tid >> 5] = (unsigned char)cls;
+    const int any = __syncthreads_or(special);
+    if (tid == 0) { td.flags = any ? TILE_F_SPECIAL : 0u; td.cls_c = C; }
 }
 
 // Copy the interior of every tile from buffer `from` to buffer `to` -- only the cells a launch stores: Ex / Hy everywhere,
@@ -983,10 +1090,12 @@ static const char *tile_kernel_name()
     return name;
 }
 
+// cls_c: cells per thread the tile table's warp classes were computed for (k_tile_classify) -- must be this kernel's C
 template <int MODE, bool POL, int C, class A, bool JX = false>
 static int launch_tile_a(int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
-                         int n0, int ks, int halo, cudaStream_t st)
+                         int n0, int ks, int halo, cudaStream_t st, int cls_c)
 {
+    if (cls_c != C) return set_err(PF_E_ARG, "tile engine: the tile table was classified for %d cells per thread, the kernel has %d", cls_c, C);
     const size_t sm = TileSmem<MODE, C, typename A::real>::bytes;
     ProfScope prof(st, tile_kernel_name<MODE, POL, C, A>());
     static std::atomic<unsigned long long> attr_set{0};   // the attribute is per device; bit = device ordinal (idempotent, race-free)
@@ -1004,13 +1113,13 @@ static int launch_tile_a(int n_tiles, const TileGrid *dg, const TileDesc *dt, in
 
 template <int MODE, bool POL, int C>
 static int launch_tile(int arith, int n_tiles, const TileGrid *dg, const TileDesc *dt, int src, int n_done,
-                       int n0, int ks, int halo, cudaStream_t st)
+                       int n0, int ks, int halo, cudaStream_t st, int cls_c)
 {
-    if (arith == ARITH_FUSED) return launch_tile_a<MODE, POL, C, Fused>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    if (arith == ARITH_FUSED) return launch_tile_a<MODE, POL, C, Fused>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
     if constexpr (MODE == PF_NL || MODE == PF_LORENTZ_NL) {
-        if (arith == ARITH_NEWTON) return launch_tile_a<MODE, POL, C, ExactNewton>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        if (arith == ARITH_NEWTON) return launch_tile_a<MODE, POL, C, ExactNewton>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
     }
-    return launch_tile_a<MODE, POL, C, Exact>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    return launch_tile_a<MODE, POL, C, Exact>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
 }
 
 constexpr int TILE_C = PF_TILE_C;            // cells per thread, Lorentz and nonlinear modes
@@ -1030,41 +1139,68 @@ constexpr int TILE_C_FREE = PF_TILE_C_FREE;
 #ifndef PF_TILE_C_F32_FREE
 #define PF_TILE_C_F32_FREE 8
 #endif
-static int launch_tile_mode(int mode, int do_pol, int fma, bool wide, int n_tiles, const TileGrid *dg, const TileDesc *dt,
-                            int src, int n_done, int n0, int ks, int halo, cudaStream_t st)
+// cells per thread of the kernel launch_tile_mode picks (the tile table's warp classes depend on it)
+static int tile_c_for(int mode, int fma, bool wide)
 {
+    if (mode == PF_FREE) return fma == ARITH_FP32 ? PF_TILE_C_F32_FREE : TILE_C_FREE;
+    if (fma == ARITH_FP32) return PF_TILE_C_F32;
+    if (fma == ARITH_EXACT_JX) return TILE_C;
+    return (mode == PF_LORENTZ && wide) ? 2 * TILE_C : TILE_C;
+}
+
+static int tile_classify(int c, int n_tiles, const TileGrid *dg, TileDesc *dt, int halo, cudaStream_t st)
+{
+    ProfScope prof(st, "k_tile_classify");
+    switch (c) {
+    case 1: k_tile_classify<1><<<n_tiles, TILE_CELLS / 1, 0, st>>>(dg, dt, halo); break;
+    case 2: k_tile_classify<2><<<n_tiles, TILE_CELLS / 2, 0, st>>>(dg, dt, halo); break;
+    case 4: k_tile_classify<4><<<n_tiles, TILE_CELLS / 4, 0, st>>>(dg, dt, halo); break;
+    case 8: k_tile_classify<8><<<n_tiles, TILE_CELLS / 8, 0, st>>>(dg, dt, halo); break;
+    default: return set_err(PF_E_ARG, "tile engine: %d cells per thread", c);
+    }
+    PF_LAUNCH_CHECK("k_tile_classify");
+    return 0;
+}
+
+static int launch_tile_mode(int mode, int do_pol, int fma, bool wide, int n_tiles, const TileGrid *dg, const TileDesc *dt,
+                            int src, int n_done, int n0, int ks, int halo, cudaStream_t st, int cls_c)
+{
+#ifdef PF_EXPERIMENT   // compile-time experiments on one kernel (tools/sass_loops.py): instantiate the headline kernel only
+    return launch_tile_a<PF_LORENTZ, true, TILE_C, Exact>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
+#else
     if (fma == ARITH_EXACT_JX) {   // a current slot (PIC coupling) is present: exact arithmetic, one geometry per mode
-        if (mode == PF_FREE) return launch_tile_a<PF_FREE, false, TILE_C_FREE, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        if (mode == PF_FREE) return launch_tile_a<PF_FREE, false, TILE_C_FREE, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
         if (mode == PF_LORENTZ)
-            return do_pol ? launch_tile_a<PF_LORENTZ, true, TILE_C, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
-                          : launch_tile_a<PF_LORENTZ, false, TILE_C, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
-        if (mode == PF_NL) return launch_tile_a<PF_NL, false, TILE_C, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+            return do_pol ? launch_tile_a<PF_LORENTZ, true, TILE_C, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c)
+                          : launch_tile_a<PF_LORENTZ, false, TILE_C, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
+        if (mode == PF_NL) return launch_tile_a<PF_NL, false, TILE_C, Exact, true>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
         return set_err(PF_E_UNSUPPORTED, "tile engine: a current slot (Jx) is supported in modes FREE, LORENTZ and NL");
     }
     if (fma == ARITH_FP32) {   // PF_F_FP32: one geometry per mode
-        if (mode == PF_FREE) return launch_tile_a<PF_FREE, false, PF_TILE_C_F32_FREE, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        if (mode == PF_FREE) return launch_tile_a<PF_FREE, false, PF_TILE_C_F32_FREE, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
         if (mode == PF_LORENTZ)
-            return do_pol ? launch_tile_a<PF_LORENTZ, true, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
-                          : launch_tile_a<PF_LORENTZ, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
-        if (mode == PF_NL) return launch_tile_a<PF_NL, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+            return do_pol ? launch_tile_a<PF_LORENTZ, true, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c)
+                          : launch_tile_a<PF_LORENTZ, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
+        if (mode == PF_NL) return launch_tile_a<PF_NL, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
         if (mode == PF_LORENTZ_NL)
-            return do_pol ? launch_tile_a<PF_LORENTZ_NL, true, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
-                          : launch_tile_a<PF_LORENTZ_NL, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+            return do_pol ? launch_tile_a<PF_LORENTZ_NL, true, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c)
+                          : launch_tile_a<PF_LORENTZ_NL, false, PF_TILE_C_F32, Fast32>(n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
         return set_err(PF_E_ARG, "bad mode %d", mode);
     }
-    if (mode == PF_FREE) return launch_tile<PF_FREE, false, TILE_C_FREE>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    if (mode == PF_FREE) return launch_tile<PF_FREE, false, TILE_C_FREE>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
     if (mode == PF_LORENTZ) {
         if (wide)
-            return do_pol ? launch_tile<PF_LORENTZ, true, 2 * TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
-                          : launch_tile<PF_LORENTZ, false, 2 * TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
-        return do_pol ? launch_tile<PF_LORENTZ, true, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
-                      : launch_tile<PF_LORENTZ, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+            return do_pol ? launch_tile<PF_LORENTZ, true, 2 * TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c)
+                          : launch_tile<PF_LORENTZ, false, 2 * TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
+        return do_pol ? launch_tile<PF_LORENTZ, true, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c)
+                      : launch_tile<PF_LORENTZ, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
     }
-    if (mode == PF_NL) return launch_tile<PF_NL, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+    if (mode == PF_NL) return launch_tile<PF_NL, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
     if (mode == PF_LORENTZ_NL)
-        return do_pol ? launch_tile<PF_LORENTZ_NL, true, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st)
-                      : launch_tile<PF_LORENTZ_NL, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st);
+        return do_pol ? launch_tile<PF_LORENTZ_NL, true, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c)
+                      : launch_tile<PF_LORENTZ_NL, false, TILE_C>(fma, n_tiles, dg, dt, src, n_done, n0, ks, halo, st, cls_c);
     return set_err(PF_E_ARG, "bad mode %d", mode);
+#endif
 }
 
 // arithmetic class of a launch: PF_F_FP32 on any grid selects single precision, else PF_F_FMA contraction
@@ -1173,6 +1309,11 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
 
     const bool wide = mostly_interior(grids, n);
     const bool snaps = snap_out && snap_interval > 0 && n == 1;
+    const int cls_c = tile_c_for(mode, fma, wide);
+    {
+        int rc = tile_classify(cls_c, (int)ht.size(), dg, dt, halo, st);
+        if (rc) return rc;
+    }
     int n_done = 0, src = 0;
     while (n_done < max_steps) {
         int ks = std::min(k_block, max_steps - n_done);
@@ -1183,7 +1324,7 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
             if (nabs % snap_interval == 0 && nabs > 0) next_snap = nabs;   // step nabs itself is a snapshot step
             ks = std::min(ks, next_snap - nabs + 1);
         }
-        int rc = launch_tile_mode(mode, do_pol, fma, wide, (int)ht.size(), dg, dt, src, n_done, n0, ks, halo, st);
+        int rc = launch_tile_mode(mode, do_pol, fma, wide, (int)ht.size(), dg, dt, src, n_done, n0, ks, halo, st, cls_c);
         if (rc) return rc;
         n_done += ks;
         src ^= 1;
@@ -1249,8 +1390,9 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
     const size_t need = off_tiles + align_up(sizeof(TileDesc) * (size_t)n_tiles, 256);
     if (!scratch || scratch_bytes < need) return set_err(PF_E_SCRATCH, "pf_run_block needs %zu bytes of scratch, got %zu", need, scratch_bytes);
     const bool wide = mostly_interior(src, n);
+    const int cls_c = tile_c_for(mode, fma, wide);
     if (block_flags & PF_BLOCK_F_TABLES_VALID)
-        return launch_tile_mode(mode, do_pol, fma, wide, (int)n_tiles, dg, dt, (block_flags & PF_BLOCK_F_SWAPPED) ? 1 : 0, 0, n0, ks, halo, st);
+        return launch_tile_mode(mode, do_pol, fma, wide, (int)n_tiles, dg, dt, (block_flags & PF_BLOCK_F_SWAPPED) ? 1 : 0, 0, n0, ks, halo, st, cls_c);
     std::vector<TileGrid> hg(n);
     std::vector<TileDesc> ht;
     ht.reserve((size_t)n_tiles);
@@ -1271,7 +1413,11 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
     }
     PF_CUDA(cudaMemcpyAsync(dg, hg.data(), sizeof(TileGrid) * n, cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaMemcpyAsync(dt, ht.data(), sizeof(TileDesc) * ht.size(), cudaMemcpyHostToDevice, st));
-    return launch_tile_mode(mode, do_pol, fma, wide, (int)ht.size(), dg, dt, 0, 0, n0, ks, halo, st);
+    {
+        int rc = tile_classify(cls_c, (int)ht.size(), dg, dt, halo, st);
+        if (rc) return rc;
+    }
+    return launch_tile_mode(mode, do_pol, fma, wide, (int)ht.size(), dg, dt, 0, 0, n0, ks, halo, st, cls_c);
 }
 
 int ops_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, double *snap_out,
