@@ -136,6 +136,109 @@ def _pick_engine(P, arrs, Jx, probe_idx):
     return (nat.PF_ENGINE_TILE, canon) if ok else (nat.PF_ENGINE_OPS, None)
 
 
+class PassRun:
+    """One pass of the time loop in flight on the device: ``start`` uploads and enqueues every launch of the pass on a
+    CUDA stream and returns at once; ``finish`` waits, downloads and writes the results back into V / C_V.  The two passes
+    of IntegratorFreeSpace1D / IntegratorLinLor1D do not read each other's fields (each begins from zeroed fields), so
+    _two_pass starts the second while the first is still running: the host-side setup of pass 1 and both passes' kernels
+    -- a default grid is 7-15 tiles, far less than the machine -- overlap."""
+
+    def __init__(self, V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=False, n0=0, nsteps=None, stream=None,
+                 stage_tag="stage"):
+        torch = nat.require_cuda()
+        lib = nat.lib()
+        self.torch, self.V, self.C_V, self.P, self.mode = torch, V, C_V, P, mode
+        T = int(P.timeSteps)
+        nsteps = T - n0 if nsteps is None else int(nsteps)
+        self.n0, self.nsteps = n0, nsteps
+        L = len(V.Ex)
+        arrs = BaseFDTD11._host_arrays(V, C_V, V.tempVarPol)
+        Jx = V.Jx if np.any(V.Jx != 0.0) else None
+        engine, canon = _pick_engine(P, arrs, Jx, probe_idx)
+        scal = BaseFDTD11.grid_scalars(V, P, kerr_lorentz=(mode == "lorentz_nl"))
+        flags = BaseFDTD11.grid_flags(P, USE_FMA, USE_FP32, CUBIC == "newton")
+        if USE_FP32 and engine != nat.PF_ENGINE_TILE:
+            raise ValueError("USE_FP32 is a mode of the tile engine; this grid needs the general per-op engine")
+        if canon is not None:
+            scal.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
+            flags |= nat.PF_F_CANONICAL
+        self.engine = engine
+        self.launches0 = lib.pf_launch_count()
+        self.stream = torch.cuda.current_stream() if stream is None else stream
+        with torch.cuda.stream(self.stream):
+            g = dev.DeviceGrid(L=L, T=T, arrays=arrs, scalars=scal, srcE=np.asarray(Exs) / P.courantNo,
+                               srcH=np.asarray(Hys) / P.courantNo, probe_idx=list(probe_idx), flags=flags, Jx=Jx,
+                               stage_tag=stage_tag)
+            self.g = g
+            stream_ptr = nat.current_stream_ptr()
+            scratch = None
+            sbytes = lib.pf_run_scratch_bytes(g.ref(), 1, engine)
+            if sbytes:
+                scratch = torch.empty(sbytes, dtype=torch.uint8, device=g.device)
+            self.scratch = scratch
+            snap_t = None
+            rows = int(P.timeSteps / P.vidInterval)
+            if snapshots and rows > 0:
+                snap_t = torch.zeros((rows, L), dtype=torch.float64, device=g.device)
+            self.snap_t, self.rows = snap_t, rows
+            mode_id = dev.MODE_ID[mode]
+            self.pprev2 = None
+
+            def call(first, count):
+                nat.check(lib.pf_run_pass(g.ref(), mode_id, int(do_pol), first, count, engine,
+                                          snap_t.data_ptr() if snap_t is not None else None,
+                                          int(P.vidInterval) if snap_t is not None else 0, rows if snap_t is not None else 0,
+                                          scratch.data_ptr() if scratch is not None else None, sbytes, stream_ptr), "pf_run_pass")
+
+            if mode in ("lorentz", "lorentz_nl") and do_pol and nsteps >= 1:
+                # keep P^{N-2} as well so V.tempTempVarPol / V.tempVarPol end up as the reference leaves them
+                if nsteps > 1:
+                    call(n0, nsteps - 1)
+                self.pprev2 = g.tensor_view("Pprev").clone()
+                call(n0 + nsteps - 1, 1)
+            elif nsteps > 0:
+                call(n0, nsteps)
+        self.launches = lib.pf_launch_count() - self.launches0
+
+    def finish(self, write_state=True):
+        """Wait for the pass, return its probe traces [len(probe_idx), timeSteps]; with write_state the final fields go back
+        into V / C_V as the reference's loop leaves them (a pass whose fields the next prepare_pass zeroes can skip that)."""
+        torch, V, C_V, P, g, mode = self.torch, self.V, self.C_V, self.P, self.g, self.mode
+        with torch.cuda.stream(self.stream):
+            if not write_state:
+                traces = g.fetch_probes()
+                LAST_RUN_INFO.update(engine="tile" if self.engine == nat.PF_ENGINE_TILE else "ops", h2d_bytes=g.h2d_bytes,
+                                     d2h_bytes=g.d2h_bytes, launches=self.launches, cells=g.L, steps=self.nsteps)
+                return traces
+            out = g.fetch(["Ex", "Hy", "Dx", "P", "Pprev", "psiE", "psiH", "Acubic"])
+            V.Ex, V.Hy, V.Dx = out["Ex"], out["Hy"], out["Dx"]
+            C_V.psi_Ex, C_V.psi_Hy = out["psiE"], out["psiH"]
+            if mode in ("lorentz", "lorentz_nl"):
+                V.polarisationCurr = out["P"]
+                V.tempVarPol = out["Pprev"]
+                if self.pprev2 is not None:
+                    V.tempTempVarPol = self.pprev2.cpu().numpy()
+            if mode in ("nl", "lorentz_nl"):
+                V.Acubic = out["Acubic"]
+            snap_t, rows, n0, nsteps, L = self.snap_t, self.rows, self.n0, self.nsteps, g.L
+            if snap_t is not None:
+                n_abs = np.arange(rows) * int(P.vidInterval)
+                done = np.flatnonzero((n_abs > 0) & (n_abs >= n0) & (n_abs < n0 + nsteps))
+                if len(done):                               # a contiguous block of rows
+                    lo, hi = int(done[0]), int(done[-1]) + 1
+                    if "Ex_History" in V.__dict__ or not hasattr(V, "_build_ex_history") or getattr(V, "_rows", rows) != rows:
+                        stage = dev.pinned_buffer(rows * L, tag="history").view(rows, L)     # already materialised: update it now
+                        stage.copy_(snap_t, non_blocking=True)
+                        torch.cuda.current_stream().synchronize()
+                        V.Ex_History[lo:hi] = stage.numpy()[lo:hi]
+                    else:
+                        # leave the rows on the device; V.Ex_History downloads them when it is first read (vidMake / VideoMaker)
+                        V.__dict__.setdefault("_pending_history", []).append((snap_t, lo, hi))
+        LAST_RUN_INFO.update(engine="tile" if self.engine == nat.PF_ENGINE_TILE else "ops", h2d_bytes=g.h2d_bytes,
+                             d2h_bytes=g.d2h_bytes, launches=self.launches, cells=g.L, steps=nsteps)
+        return out["probe_out"]
+
+
 def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=False, n0=0, nsteps=None):
     """The reference's per-pass time loop, executed by libpyfdtd_b200 on the current CUDA device.
 
@@ -143,76 +246,7 @@ def run_time_loop(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=F
     absolute step ``n0``, downloads state + probe traces (one D2H) and writes them back into V / C_V.
     Returns the probe traces, shape [len(probe_idx), timeSteps].
     """
-    torch = nat.require_cuda()
-    lib = nat.lib()
-    T = int(P.timeSteps)
-    nsteps = T - n0 if nsteps is None else int(nsteps)
-    L = len(V.Ex)
-    arrs = BaseFDTD11._host_arrays(V, C_V, V.tempVarPol)
-    Jx = V.Jx if np.any(V.Jx != 0.0) else None
-    engine, canon = _pick_engine(P, arrs, Jx, probe_idx)
-    scal = BaseFDTD11.grid_scalars(V, P, kerr_lorentz=(mode == "lorentz_nl"))
-    flags = BaseFDTD11.grid_flags(P, USE_FMA, USE_FP32, CUBIC == "newton")
-    if USE_FP32 and engine != nat.PF_ENGINE_TILE:
-        raise ValueError("USE_FP32 is a mode of the tile engine; this grid needs the general per-op engine")
-    if canon is not None:
-        scal.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
-        flags |= nat.PF_F_CANONICAL
-    launches0 = lib.pf_launch_count()
-    g = dev.DeviceGrid(L=L, T=T, arrays=arrs, scalars=scal, srcE=np.asarray(Exs) / P.courantNo,
-                       srcH=np.asarray(Hys) / P.courantNo, probe_idx=list(probe_idx), flags=flags, Jx=Jx)
-    stream = nat.current_stream_ptr()
-    scratch = None
-    sbytes = lib.pf_run_scratch_bytes(g.ref(), 1, engine)
-    if sbytes:
-        scratch = torch.empty(sbytes, dtype=torch.uint8, device=g.device)
-    snap_t = None
-    rows = int(P.timeSteps / P.vidInterval)
-    if snapshots and rows > 0:
-        snap_t = torch.zeros((rows, L), dtype=torch.float64, device=g.device)
-    mode_id = dev.MODE_ID[mode]
-    pprev2 = None
-
-    def call(first, count):
-        nat.check(lib.pf_run_pass(g.ref(), mode_id, int(do_pol), first, count, engine,
-                                  snap_t.data_ptr() if snap_t is not None else None,
-                                  int(P.vidInterval) if snap_t is not None else 0, rows if snap_t is not None else 0,
-                                  scratch.data_ptr() if scratch is not None else None, sbytes, stream), "pf_run_pass")
-
-    if mode in ("lorentz", "lorentz_nl") and do_pol and nsteps >= 1:
-        # keep P^{N-2} as well so V.tempTempVarPol / V.tempVarPol end up as the reference leaves them
-        if nsteps > 1:
-            call(n0, nsteps - 1)
-        pprev2 = g.tensor_view("Pprev").clone()
-        call(n0 + nsteps - 1, 1)
-    elif nsteps > 0:
-        call(n0, nsteps)
-    out = g.fetch(["Ex", "Hy", "Dx", "P", "Pprev", "psiE", "psiH", "Acubic"])
-    V.Ex, V.Hy, V.Dx = out["Ex"], out["Hy"], out["Dx"]
-    C_V.psi_Ex, C_V.psi_Hy = out["psiE"], out["psiH"]
-    if mode in ("lorentz", "lorentz_nl"):
-        V.polarisationCurr = out["P"]
-        V.tempVarPol = out["Pprev"]
-        if pprev2 is not None:
-            V.tempTempVarPol = pprev2.cpu().numpy()
-    if mode in ("nl", "lorentz_nl"):
-        V.Acubic = out["Acubic"]
-    if snap_t is not None:
-        n_abs = np.arange(rows) * int(P.vidInterval)
-        done = np.flatnonzero((n_abs > 0) & (n_abs >= n0) & (n_abs < n0 + nsteps))
-        if len(done):                               # a contiguous block of rows
-            lo, hi = int(done[0]), int(done[-1]) + 1
-            if "Ex_History" in V.__dict__ or not hasattr(V, "_build_ex_history") or getattr(V, "_rows", rows) != rows:
-                stage = dev.pinned_buffer(rows * L, tag="history").view(rows, L)     # already materialised: update it now
-                stage.copy_(snap_t, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                V.Ex_History[lo:hi] = stage.numpy()[lo:hi]
-            else:
-                # leave the rows on the device; V.Ex_History downloads them when it is first read (vidMake / VideoMaker)
-                V.__dict__.setdefault("_pending_history", []).append((snap_t, lo, hi))
-    LAST_RUN_INFO.update(engine="tile" if engine == nat.PF_ENGINE_TILE else "ops", h2d_bytes=g.h2d_bytes,
-                         d2h_bytes=g.d2h_bytes, launches=lib.pf_launch_count() - launches0, cells=L, steps=nsteps)
-    return out["probe_out"]
+    return PassRun(V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=snapshots, n0=n0, nsteps=nsteps).finish()
 
 
 def prepare_pass(V, P, C_V, C_P, lorentz, nonlinear=False):
@@ -240,24 +274,42 @@ def prepare_pass(V, P, C_V, C_P, lorentz, nonlinear=False):
     return C_V, Exs, Hys
 
 
+_SIDE = {}
+
+
+def _side_stream(torch):
+    d = torch.cuda.current_device()
+    if d not in _SIDE:
+        _SIDE[d] = torch.cuda.Stream(device=d)
+    return _SIDE[d]
+
+
 def _two_pass(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf, lorentz):
     """Shared body of IntegratorFreeSpace1D / IntegratorLinLor1D: pass 0 = incident run (probe x1Loc),
     pass 1 = run with the medium's polarisation (probe x2Loc, history, attenuation probes)."""
+    torch = nat.require_cuda()
     n = np.arange(P.timeSteps)
     mode = ("lorentz_nl" if KERR_LORENTZ else "lorentz") if lorentz else "free"
-    for i in range(2):
-        C_V, Exs, Hys = prepare_pass(V, P, C_V, C_P, lorentz)
-        V.test = 0
-        if i == 0:
-            traces = run_time_loop(V, P, C_V, C_P, mode, False, Exs, Hys, [P.x1Loc])
-            V.x1ColBe = np.where(n <= probeReadFinishBe, traces[0], V.x1ColBe)
-        else:
-            atten = list(atten_probe_cells(V, P)) if P.atten else []
-            traces = run_time_loop(V, P, C_V, C_P, mode, lorentz, Exs, Hys, [P.x2Loc] + atten, snapshots=True)
-            window = n >= probeReadStartAf
-            V.x1ColAf = np.where(window, traces[0], V.x1ColAf)
-            for k in range(len(atten)):
-                V.x1Atten[k] = np.where(window, traces[1 + k], V.x1Atten[k])
+    # Pass 0 is enqueued on a side stream and left running: prepare_pass of pass 1 starts from zeroed fields and reads
+    # nothing pass 0 writes (its only output is the x1Loc trace), so the reference's order of host-side effects is kept
+    # while pass 1's setup and kernels overlap pass 0's.
+    side = _side_stream(torch)
+    side.wait_stream(torch.cuda.current_stream())
+    C_V, Exs, Hys = prepare_pass(V, P, C_V, C_P, lorentz)
+    V.test = 0
+    run0 = PassRun(V, P, C_V, C_P, mode, False, Exs, Hys, [P.x1Loc], stream=side, stage_tag="stage0")
+    C_V, Exs, Hys = prepare_pass(V, P, C_V, C_P, lorentz)
+    V.test = 0
+    atten = list(atten_probe_cells(V, P)) if P.atten else []
+    run1 = PassRun(V, P, C_V, C_P, mode, lorentz, Exs, Hys, [P.x2Loc] + atten, snapshots=True)
+    traces = run0.finish(write_state=False)
+    V.x1ColBe = np.where(n <= probeReadFinishBe, traces[0], V.x1ColBe)
+    traces = run1.finish()
+    LAST_RUN_INFO["launches"] = run0.launches + run1.launches
+    window = n >= probeReadStartAf
+    V.x1ColAf = np.where(window, traces[0], V.x1ColAf)
+    for k in range(len(atten)):
+        V.x1Atten[k] = np.where(window, traces[1 + k], V.x1Atten[k])
     return V.Ex, V.Hy, Exs, Hys, C_V.psi_Ex, C_V.psi_Hy, V.x1ColBe, V.x1ColAf
 
 

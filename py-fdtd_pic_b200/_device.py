@@ -85,7 +85,7 @@ class DeviceGrid:
     """Device-resident copy of one grid + its PfGrid descriptor."""
 
     def __init__(self, *, L, T, arrays, scalars, srcE, srcH, probe_idx, flags, Jx=None, z0=0, Lg=None,
-                 need=None, device=None):
+                 need=None, device=None, stage_tag="stage"):
         torch = nat.require_cuda()
         self.torch = torch
         self.L, self.T = int(L), int(T)
@@ -110,7 +110,7 @@ class DeviceGrid:
         cur += max(n_probe, 1) * Tp
         self.n_doubles = cur
         self.Tp = Tp
-        self.host = pinned_buffer(cur)
+        self.host = pinned_buffer(cur, tag=stage_tag)   # grids alive at the same time need their own staging buffers
         hv = self.host.numpy()
         hv[:] = 0.0
         for n in names:
@@ -161,6 +161,17 @@ class DeviceGrid:
             po = hv[self.off["probe_out"]: self.off["probe_out"] + max(n_p, 1) * self.Tp]
             out["probe_out"] = po.reshape(max(n_p, 1), self.Tp)[:n_p, : self.T].copy()
         return out
+
+    def fetch_probes(self):
+        """D2H of the probe traces only -> [n_probes, T]."""
+        torch = self.torch
+        n_p = max(self.g.n_probes, 1)
+        lo = self.off["probe_out"]
+        self.host[lo: lo + n_p * self.Tp].copy_(self.pool[lo: lo + n_p * self.Tp], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes += n_p * self.Tp * 8
+        po = self.host.numpy()[lo: lo + n_p * self.Tp]
+        return po.reshape(n_p, self.Tp)[: self.g.n_probes, : self.T].copy()
 
     def tensor_view(self, name):
         return self.pool[self.off[name]: self.off[name] + self.L]
