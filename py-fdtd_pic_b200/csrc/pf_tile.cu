@@ -841,7 +841,6 @@ k_tile(const TileGrid *__restrict__ grids, const TileDesc *__restrict__ tiles, i
     using R = typename A::real;
     constexpr unsigned RB = (unsigned)sizeof(R);
     constexpr int NT = TILE_CELLS / C;
-    constexpr unsigned ALL = (1u << C) - 1u;
     TileShared<R> S;
     unsigned sbase = (unsigned)__cvta_generic_to_shared(pf_smem);
     // keep the window address in an ordinary (per-thread) register: as a uniform value it is
