@@ -175,7 +175,7 @@ __device__ __forceinline__ void pub_store(unsigned long long *p, unsigned long l
 // then adds the partial sums of every node in a fixed order.  Deterministic (no atomics), but a different summation tree
 // from pf_pic_deposit's -- oracle/pic_oracle.py: deposit_fused().
 #ifndef PF_PIC_COUNT_MINBLOCKS
-#define PF_PIC_COUNT_MINBLOCKS 1
+#define PF_PIC_COUNT_MINBLOCKS 5   // 48 registers, 40 warps per SM: 0.558 against 0.582 ms per 2e7-particle step with 64 registers / 32 warps (no spills; 6 spills, 0.555)
 #endif
 #ifndef PF_PIC_PLACE_MINBLOCKS
 #define PF_PIC_PLACE_MINBLOCKS 4   // round 1: 62 instead of 78 registers for the depositing placement, 0.589 vs 0.616 ms per 2e7-particle step
