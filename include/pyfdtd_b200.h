@@ -264,8 +264,10 @@ size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine);
 enum {
     PF_BLOCK_F_TABLES_VALID = 1, /* promise by the caller: `scratch` still holds the tile tables the previous
                                     pf_run_block call on it wrote (nothing else has written to that memory since)
-                                    and they were built from these same two descriptor arrays -- the library then
-                                    skips the host-side rebuild and the H2D copy of the tables.  The library keeps
+                                    and they were built from these same two descriptor arrays with the same `mode`
+                                    and `halo` (the tables hold the tiling and the warp classes of every tile, which
+                                    depend on both) -- the library then skips the host-side rebuild, the H2D copy of
+                                    the tables and their classification kernel.  The library keeps
                                     NO record of earlier calls: without this flag the tables are always rebuilt.  */
     PF_BLOCK_F_SWAPPED = 2       /* with TABLES_VALID: src / dst are exchanged relative to the call that built the
                                     tables (the steady state of a ping-pong run alternates this bit)               */
