@@ -269,8 +269,13 @@ enum {
                                     depend on both) -- the library then skips the host-side rebuild, the H2D copy of
                                     the tables and their classification kernel.  The library keeps
                                     NO record of earlier calls: without this flag the tables are always rebuilt.  */
-    PF_BLOCK_F_SWAPPED = 2       /* with TABLES_VALID: src / dst are exchanged relative to the call that built the
+    PF_BLOCK_F_SWAPPED = 2,      /* with TABLES_VALID: src / dst are exchanged relative to the call that built the
                                     tables (the steady state of a ping-pong run alternates this bit)               */
+    PF_BLOCK_F_EDGE_TILES = 4,   /* advance only the tiles that read ghost cells (the first / last tiles of a piece
+                                    that has a neighbour on that side: z0 > 0, z0 + L < Lg) ...                     */
+    PF_BLOCK_F_INNER_TILES = 8   /* ... or only the others.  A block is complete after both calls (any order, same
+                                    arguments otherwise); the inner tiles read no ghost cell, so they can run while
+                                    the ghost exchange of the block is still in flight.  Neither flag: all tiles.   */
 };
 int pf_run_block(const PfGrid *src, const PfGrid *dst, int n_grids, int mode, int do_pol, int n0, int ksteps, int halo,
                  int block_flags, void *scratch, size_t scratch_bytes, void *stream);

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("PYFDTD_B200_LIB") or os.path.join(HERE, "libpyfdtd_b2
 PF_FREE, PF_LORENTZ, PF_NL, PF_LORENTZ_NL = 0, 1, 2, 3
 PF_ENGINE_OPS, PF_ENGINE_TILE = 0, 1
 PF_PIC_F_OFFSETS_VALID = 1
-PF_BLOCK_F_TABLES_VALID, PF_BLOCK_F_SWAPPED = 1, 2
+PF_BLOCK_F_TABLES_VALID, PF_BLOCK_F_SWAPPED, PF_BLOCK_F_EDGE_TILES, PF_BLOCK_F_INNER_TILES = 1, 2, 4, 8
 PF_ABI_VERSION = 2
 PF_F_TFSF, PF_F_CPML_M, PF_F_CPML_P, PF_F_CANONICAL, PF_F_FMA, PF_F_FP32, PF_F_NEWTON = 1, 2, 4, 8, 16, 32, 64
 

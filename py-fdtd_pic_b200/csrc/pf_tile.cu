@@ -1356,6 +1356,28 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
     return PF_OK;
 }
 
+// A tile of a piece of a decomposed grid is an EDGE tile if it reads ghost cells: cells [0, halo) of a piece that has a left
+// neighbour (z0 > 0), cells [L - halo, L) of one that has a right neighbour (z0 + L < Lg).  pf_run_block keeps the edge tiles
+// in front of the table so that a caller can advance the inner tiles while the ghost exchange is still in flight.
+static inline bool tile_is_edge(const PfGrid &g, int base, int halo)
+{
+    const bool left = g.z0 > 0 && base < halo;
+    const bool right = g.z0 + g.L < g.Lg && (long long)base + TILE_CELLS > (long long)g.L - halo;
+    return left || right;
+}
+// number of edge tiles of one piece (only its first and last few tiles can be: halo <= TILE_KMAX, W >= 3/4 TILE_CELLS)
+static int tile_count_edge(const PfGrid &g, int halo)
+{
+    const int W = TILE_CELLS - 2 * halo;
+    const int ntile = (g.L + W - 1) / W;
+    int c = 0;
+    for (int i = 0; i < ntile; ++i) {
+        if (i == 4 && ntile > 8) i = ntile - 4;
+        c += tile_is_edge(g, i * W - halo, halo) ? 1 : 0;
+    }
+    return c;
+}
+
 // One launch: advance n grids by `ks` steps (absolute steps n0 .. n0+ks-1) reading the arrays of
 // src[m] and writing the arrays of dst[m] (the caller owns both buffers and alternates them).
 // halo >= ks is the overlap the tiles are cut with.  scratch holds only the tile tables: they carry both
@@ -1390,11 +1412,21 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
     if (!scratch || scratch_bytes < need) return set_err(PF_E_SCRATCH, "pf_run_block needs %zu bytes of scratch, got %zu", need, scratch_bytes);
     const bool wide = mostly_interior(src, n);
     const int cls_c = tile_c_for(mode, fma, wide);
-    if (block_flags & PF_BLOCK_F_TABLES_VALID)
-        return launch_tile_mode(mode, do_pol, fma, wide, (int)n_tiles, dg, dt, (block_flags & PF_BLOCK_F_SWAPPED) ? 1 : 0, 0, n0, ks, halo, st, cls_c);
+    // the part of the table this call launches: [edge tiles | inner tiles]
+    if ((block_flags & PF_BLOCK_F_EDGE_TILES) && (block_flags & PF_BLOCK_F_INNER_TILES))
+        return set_err(PF_E_ARG, "pf_run_block: PF_BLOCK_F_EDGE_TILES and PF_BLOCK_F_INNER_TILES exclude each other (neither = all tiles)");
+    long long n_edge = 0;
+    for (int m = 0; m < n; ++m) n_edge += tile_count_edge(src[m], halo);
+    const long long part_off = (block_flags & PF_BLOCK_F_INNER_TILES) ? n_edge : 0;
+    const long long part_n = (block_flags & PF_BLOCK_F_EDGE_TILES) ? n_edge : ((block_flags & PF_BLOCK_F_INNER_TILES) ? n_tiles - n_edge : n_tiles);
+    if (block_flags & PF_BLOCK_F_TABLES_VALID) {
+        if (part_n == 0) return PF_OK;
+        return launch_tile_mode(mode, do_pol, fma, wide, (int)part_n, dg, dt + part_off, (block_flags & PF_BLOCK_F_SWAPPED) ? 1 : 0, 0, n0, ks, halo, st, cls_c);
+    }
     std::vector<TileGrid> hg(n);
-    std::vector<TileDesc> ht;
+    std::vector<TileDesc> ht, inner;
     ht.reserve((size_t)n_tiles);
+    inner.reserve((size_t)n_tiles);
     for (int m = 0; m < n; ++m) {
         TileGrid &t = hg[m];
         t.d = make_grid_dev(src[m]);
@@ -1408,15 +1440,18 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
         t.nsteps = 1 << 30;   // the step count of a block launch is the kernel's ksteps argument
         t.pad = 0;
         int ntile = (src[m].L + W - 1) / W;
-        for (int i = 0; i < ntile; ++i) ht.push_back(TileDesc{m, i * W - halo});
+        for (int i = 0; i < ntile; ++i) (tile_is_edge(src[m], i * W - halo, halo) ? ht : inner).push_back(TileDesc{m, i * W - halo});
     }
+    if ((long long)ht.size() != n_edge) return set_err(PF_E_ARG, "pf_run_block: internal: edge tile count %zu != %lld", ht.size(), n_edge);
+    ht.insert(ht.end(), inner.begin(), inner.end());
     PF_CUDA(cudaMemcpyAsync(dg, hg.data(), sizeof(TileGrid) * n, cudaMemcpyHostToDevice, st));
     PF_CUDA(cudaMemcpyAsync(dt, ht.data(), sizeof(TileDesc) * ht.size(), cudaMemcpyHostToDevice, st));
     {
         int rc = tile_classify(cls_c, (int)ht.size(), dg, dt, halo, st);
         if (rc) return rc;
     }
-    return launch_tile_mode(mode, do_pol, fma, wide, (int)ht.size(), dg, dt, 0, 0, n0, ks, halo, st, cls_c);
+    if (part_n == 0) return PF_OK;
+    return launch_tile_mode(mode, do_pol, fma, wide, (int)part_n, dg, dt + part_off, 0, 0, n0, ks, halo, st, cls_c);
 }
 
 int ops_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, double *snap_out,

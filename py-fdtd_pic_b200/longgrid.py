@@ -118,10 +118,9 @@ def exchange_schedule(pieces, rank):
     return sched
 
 
-def run_exchange(sched, pieces, pack, unpack, dist=None, make_buffer=None):
-    """Execute one ghost exchange.  ``pack(piece, side) -> tensor`` returns the k owned cells next to
-    that edge of every state array; ``unpack(piece, side, tensor)`` writes a neighbour's packed cells
-    into the ghost cells at that edge.  Remote messages are posted as one batch of isend/irecv."""
+def start_exchange(sched, pieces, pack, unpack, dist=None, make_buffer=None):
+    """First half of a ghost exchange: same-rank boundaries are copied at once, remote messages are packed and posted
+    as one batch of isend/irecv.  Returns the handle ``finish_exchange`` completes (requests + receive buffers)."""
     ops, recvs = [], []
     for kind, i, side, j in sched:
         if kind == "local":
@@ -134,11 +133,24 @@ def run_exchange(sched, pieces, pack, unpack, dist=None, make_buffer=None):
             buf = make_buffer(i, side)
             recvs.append((i, side, buf))
             ops.append(dist.P2POp(dist.irecv, buf, pieces[j]["rank"]))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    return reqs, recvs
+
+
+def finish_exchange(handle, unpack):
+    """Second half: wait for the posted messages, write the received cells into the ghost cells."""
+    reqs, recvs = handle
+    for req in reqs:
+        req.wait()
     for i, side, buf in recvs:
         unpack(i, side, buf)
+
+
+def run_exchange(sched, pieces, pack, unpack, dist=None, make_buffer=None):
+    """Execute one ghost exchange.  ``pack(piece, side) -> tensor`` returns the k owned cells next to
+    that edge of every state array; ``unpack(piece, side, tensor)`` writes a neighbour's packed cells
+    into the ghost cells at that edge.  Remote messages are posted as one batch of isend/irecv."""
+    finish_exchange(start_exchange(sched, pieces, pack, unpack, dist=dist, make_buffer=make_buffer), unpack)
 
 
 # ------------------------------------------------------------------------------------------------ device side
@@ -238,6 +250,8 @@ class LongGrid:
         self.n_done = 0
         self._tables_built = False    # the tile tables in self.scratch were written by this object's last pf_run_block
         self.time_exchange = False    # True: every ghost exchange is bracketed by CUDA events (exchange_ms())
+        self.overlap = True           # remote exchanges overlap the inner tiles of the block (run())
+        self.force_split = False      # tests: split every block into inner / edge launches even without remote neighbours
         self._xch_events = []
         self.halo_bufs = {}
         self.cells_owned = sum(p["hi"] - p["lo"] for p in self.mine)
@@ -274,39 +288,58 @@ class LongGrid:
 
     # -- time stepping -------------------------------------------------------------------------
     def run(self, nsteps, do_pol=True):
+        """Advance the grid ``nsteps`` steps, k at a time.  With remote neighbours (world_size > 1, ``overlap`` on) a block is
+        two launches: the inner tiles, which read no ghost cell, run while the messages of the exchange are in flight; the
+        edge tiles follow once the ghost cells are written.  Same tiles, same arithmetic: the result does not depend on it."""
         lib = nat.lib()
+        torch = self.torch
         if self.n_done + nsteps > self.T:
             raise ValueError(f"LongGrid.run: steps {self.n_done}..{self.n_done + nsteps - 1} run past the source tables (T = {self.T})")
-        done = 0
-        while done < nsteps:
-            ks = min(self.k, nsteps - done)
-            if len(self.pieces) > 1:
-                if self.time_exchange:
-                    ev = (self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True))
-                    ev[0].record()
-                    self.exchange()
-                    ev[1].record()
-                    self._xch_events.append(ev)
-                else:
-                    self.exchange()
+        import torch.distributed as dist
+        remote = self.world > 1 and any(kind != "local" for kind, *_ in self.sched)
+        split = (remote and self.overlap) or self.force_split
+
+        def block(ks, part):
             # the tables hold buffer set 0 as `src`; this object owns the scratch, so after the first call they stay valid
-            bflags = 0
+            bflags = part
             if self._tables_built:
-                bflags = nat.PF_BLOCK_F_TABLES_VALID | (nat.PF_BLOCK_F_SWAPPED if self.cur != self._tables_src else 0)
+                bflags |= nat.PF_BLOCK_F_TABLES_VALID | (nat.PF_BLOCK_F_SWAPPED if self.cur != self._tables_src else 0)
             nat.check(lib.pf_run_block(self.grids[self.cur], self.grids[self.cur ^ 1], len(self.mine), self.mode_id,
                                        int(do_pol), self.n_done, ks, self.k, bflags, self.scratch.data_ptr(), self.scratch_bytes,
                                        nat.current_stream_ptr()), "pf_run_block")
             if not self._tables_built:
                 self._tables_built, self._tables_src = True, self.cur
+
+        done = 0
+        while done < nsteps:
+            ks = min(self.k, nsteps - done)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if (self.time_exchange and len(self.pieces) > 1) else None
+            if len(self.pieces) > 1:
+                if ev:
+                    ev[0].record()
+                handle = start_exchange(self.sched, self.pieces, self._pack, self._unpack, dist=dist if self.world > 1 else None,
+                                        make_buffer=lambda i, side: self._buffer("recv", i, side))
+                if ev:
+                    ev[1].record()
+                if split:
+                    block(ks, nat.PF_BLOCK_F_INNER_TILES)
+                if ev:
+                    ev[2].record()
+                finish_exchange(handle, self._unpack)
+                if ev:
+                    ev[3].record()
+                    self._xch_events.append(ev)
+            block(ks, nat.PF_BLOCK_F_EDGE_TILES if split else 0)
             self.cur ^= 1
             self.n_done += ks
             done += ks
 
     def exchange_ms(self):
-        """Summed device time [ms] of the ghost exchanges timed since time_exchange was switched on (pack kernels,
-        point-to-point messages, unpack kernels); clears the list."""
+        """Summed device time [ms] the ghost exchanges kept the compute stream busy or waiting since time_exchange was
+        switched on: pack kernels + posting, and -- after the inner tiles, when the block is split -- the rest of the wait
+        for the messages + unpack kernels; clears the list."""
         self.torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in self._xch_events)
+        ms = sum(e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in self._xch_events)
         self._xch_events = []
         return float(ms)
 

@@ -30,10 +30,14 @@ def oracle_long(info, Lg, T, nsteps, mode="lorentz"):
     return pa
 
 
-@pytest.mark.parametrize("k,max_piece", [(64, 9000), (17, 7000), (64, 1 << 27)])
-def test_decomposed_long_grid_is_bit_identical_to_oracle(lg, k, max_piece):
+@pytest.mark.parametrize("k,max_piece,split", [(64, 9000, False), (17, 7000, False), (64, 1 << 27, False),
+                                               (64, 9000, True), (17, 1500, True), (25, 7000, True)])
+def test_decomposed_long_grid_is_bit_identical_to_oracle(lg, k, max_piece, split):
+    """split: every block as two launches, inner tiles (PF_BLOCK_F_INNER_TILES) then edge tiles (PF_BLOCK_F_EDGE_TILES) --
+    the form LongGrid.run uses to overlap a remote ghost exchange; 1500-cell pieces consist of edge tiles only."""
     Lg, T, nsteps = 40_000, 512, 300
     grid, info = lg.lorentz_long_grid(Lg, T=T, k=k, max_piece=max_piece)
+    grid.force_split = split
     assert Lg > 25000, "beyond the reference's grid-size guard"
     if max_piece < Lg:
         assert len(grid.pieces) >= 4

@@ -248,7 +248,8 @@ def test_pic_oracle_fused_summation_tree_agrees_with_the_plain_one():
 def test_python_constants_match_header_enums(tmp_path):
     """Modes, engines and flags of _native.py are the header's enum values (compiled from the header itself)."""
     names = ["PF_FREE", "PF_LORENTZ", "PF_NL", "PF_LORENTZ_NL", "PF_ENGINE_OPS", "PF_ENGINE_TILE", "PF_F_TFSF",
-             "PF_F_CPML_M", "PF_F_CPML_P", "PF_F_CANONICAL", "PF_F_FMA", "PF_F_FP32", "PF_F_NEWTON"]
+             "PF_F_CPML_M", "PF_F_CPML_P", "PF_F_CANONICAL", "PF_F_FMA", "PF_F_FP32", "PF_F_NEWTON",
+             "PF_BLOCK_F_TABLES_VALID", "PF_BLOCK_F_SWAPPED", "PF_BLOCK_F_EDGE_TILES", "PF_BLOCK_F_INNER_TILES"]
     src = tmp_path / "en.c"
     src.write_text('#include <stdio.h>\n#include "pyfdtd_b200.h"\nint main(){printf("' + " ".join(["%d"] * len(names)) +
                    '\\n", ' + ", ".join(names) + ");return 0;}\n")
