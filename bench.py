@@ -508,11 +508,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    import pyfdtd_b200  # noqa: F401
+    from pyfdtd_b200 import _native as nat, sweep
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    import pyfdtd_b200  # noqa: F401
-    from pyfdtd_b200 import _native as nat, sweep
     lib = nat.lib()
     t_setup0 = time.perf_counter()
     batch, table = lorentz_sweep_batch(args.members, args.pass_steps, args.n_freq, fma=args.fma, fp32=args.fp32)

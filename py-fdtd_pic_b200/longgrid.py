@@ -101,6 +101,16 @@ def plan_pieces(Lg, pw, world_size, k, max_piece=1 << 27, mf=None, mr=None, slab
     return pieces
 
 
+def nccl_options_for_overlap():
+    """Process-group options under which LongGrid.run's overlap works: NCCL's streams at high priority, so that the
+    point-to-point kernels of a ghost exchange are dispatched ahead of the thousands of pending CTAs of the inner-tile
+    launch instead of behind them.  Use: ``dist.init_process_group("nccl", pg_options=nccl_options_for_overlap(), ...)``."""
+    import torch.distributed as dist
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return opts
+
+
 def exchange_schedule(pieces, rank):
     """Messages of one ghost exchange for ``rank``: a list of (kind, piece, side, peer_piece) with kind in
     {"local", "send", "recv"}; side 0/1 = left/right edge of ``piece``.  Deterministic global order."""
@@ -250,7 +260,7 @@ class LongGrid:
         self.n_done = 0
         self._tables_built = False    # the tile tables in self.scratch were written by this object's last pf_run_block
         self.time_exchange = False    # True: every ghost exchange is bracketed by CUDA events (exchange_ms())
-        self.overlap = True           # remote exchanges overlap the inner tiles of the block (run())
+        self.overlap = False          # True: remote exchanges overlap the inner tiles of the block (run()); measured no gain
         self.force_split = False      # tests: split every block into inner / edge launches even without remote neighbours
         self._xch_events = []
         self.halo_bufs = {}
@@ -288,9 +298,12 @@ class LongGrid:
 
     # -- time stepping -------------------------------------------------------------------------
     def run(self, nsteps, do_pol=True):
-        """Advance the grid ``nsteps`` steps, k at a time.  With remote neighbours (world_size > 1, ``overlap`` on) a block is
-        two launches: the inner tiles, which read no ghost cell, run while the messages of the exchange are in flight; the
-        edge tiles follow once the ghost cells are written.  Same tiles, same arithmetic: the result does not depend on it."""
+        """Advance the grid ``nsteps`` steps, k at a time.  With remote neighbours and ``overlap`` switched on a block is two
+        launches: the inner tiles, which read no ghost cell, run while the messages of the exchange are in flight; the edge
+        tiles follow once the ghost cells are written.  Same tiles, same arithmetic: the result does not depend on it
+        (tests/test_gpu_longgrid.py, tests/test_gpu_multirank.py).  Off by default: on 2 B200s the exchange is ~0.1 ms of a
+        7.5 ms block and the extra launch for the edge tiles (a 64-step kernel is >= 30 us however few tiles it has) costs what
+        the hidden messages save -- 1673-1676 against 1680-1684 Gcell-updates/s, vacuum 3470-3489 against 3491-3508."""
         lib = nat.lib()
         torch = self.torch
         if self.n_done + nsteps > self.T:

@@ -17,19 +17,21 @@ def _n_gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def _torchrun(n, script, *args, port=29533):
+def _torchrun(n, script, *args, port=29533, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, script), *args]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, **(env or {})))
 
 
-@pytest.mark.parametrize("mode", ["lorentz", "lorentz_nl", "free"])
-def test_decomposed_long_grid_is_bit_identical_to_one_gpu(mode):
+@pytest.mark.parametrize("mode,overlap", [("lorentz", "0"), ("lorentz_nl", "0"), ("free", "0"), ("lorentz", "1")])
+def test_decomposed_long_grid_is_bit_identical_to_one_gpu(mode, overlap):
+    """overlap = 1: LongGrid.overlap, every block as inner tiles (while the NCCL messages are in flight) + edge tiles."""
     n = _n_gpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 4 if n >= 4 else 2
-    r = _torchrun(world, "tools/longgrid_multigpu_check.py", "--cells", "300000", "--steps", "256", "--mode", mode)
+    r = _torchrun(world, "tools/longgrid_multigpu_check.py", "--cells", "300000", "--steps", "256", "--mode", mode,
+                  env={"PF_LONGGRID_OVERLAP": overlap})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "== single GPU: True" in r.stdout and "ok=True" in r.stdout and "False" not in r.stdout
 

@@ -27,10 +27,11 @@ a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                            pg_options=longgrid.nccl_options_for_overlap() if os.environ.get("PF_NCCL_HIGH_PRIO", "0") != "0" else None)
 POL = a.mode in ("lorentz", "lorentz_nl")
 grid, info = longgrid.lorentz_long_grid(a.cells, T=a.steps, k=a.k, rank=rank, world_size=world, mode=a.mode)
-grid.overlap = os.environ.get("PF_LONGGRID_OVERLAP", "1") != "0"   # A/B: ghost exchange serial with / overlapped by the inner tiles
+grid.overlap = os.environ.get("PF_LONGGRID_OVERLAP", "0") != "0"   # A/B: ghost exchange serial with / overlapped by the inner tiles
 if a.no_check:
     # throughput runs start from a synthetic non-zero state (as bench.py's extras do): from zero most cells are
     # quiescent, which costs the Lorentz arithmetic the same but lets the cubic law skip its root (|d| <= 1e-8)
