@@ -826,11 +826,15 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
 #ifndef PF_TILE_MINBLOCKS_FREE
 #define PF_TILE_MINBLOCKS_FREE 4   // 128 instead of 164 registers, 4 CTAs of 128 threads per SM: 1670 vs 1645 Gcell-updates/s (5e7 cells)
 #endif
+#ifndef PF_TILE_MINBLOCKS_CUBIC
+#define PF_TILE_MINBLOCKS_CUBIC PF_TILE_MINBLOCKS   // 1 CTA/SM (128 registers, no spills): closed form 122 vs 148, Newton 186 vs 214 Gcell-updates/s
+#endif
 template <int MODE, class A>
 constexpr int tile_minblocks()
 {
     return std::is_same<typename A::real, float>::value ? PF_TILE_MINBLOCKS_F32
-           : (A::newton ? PF_TILE_MINBLOCKS_NEWTON : (MODE == PF_FREE ? PF_TILE_MINBLOCKS_FREE : PF_TILE_MINBLOCKS));
+           : (A::newton ? PF_TILE_MINBLOCKS_NEWTON
+              : (MODE == PF_FREE ? PF_TILE_MINBLOCKS_FREE : ((MODE == PF_NL || MODE == PF_LORENTZ_NL) ? PF_TILE_MINBLOCKS_CUBIC : PF_TILE_MINBLOCKS)));
 }
 
 template <int MODE, bool POL, int C, class A, bool JX = false>
