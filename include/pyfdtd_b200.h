@@ -240,7 +240,9 @@ int pf_drude_j_run(const PfDrudeJ *d, int i0, int nsteps, void *stream);
  * `for counts in range(P.timeSteps)` loop of Solver_Engine.Integrator{FreeSpace,LinLor,NL}1D
  * (Solver_Engine.py:167 / 294 / 236).  do_pol = 1 runs the polarisation update (pass i==1 of the
  * Lorentz integrator).  snap_out (may be NULL): Ex is copied to row n/snap_interval after step
- * n whenever n>0 and n % snap_interval == 0 and row < snap_rows (Solver_Engine.vidMake :57-68).
+ * n whenever n>0 and n % snap_interval == 0 and row < snap_rows (Solver_Engine.vidMake :57-68);
+ * ENGINE_TILE writes the rows from inside its kernel in modes PF_FREE / PF_LORENTZ and ends a launch at
+ * every snapshot step in the cubic modes.
  * scratch: pf_run_scratch_bytes(g,1,engine) bytes of device memory (may be NULL for ENGINE_OPS). */
 int pf_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, int engine,
                 double *snap_out, int snap_interval, int snap_rows,

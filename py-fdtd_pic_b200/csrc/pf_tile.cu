@@ -58,6 +58,9 @@ struct TileGrid {
     GridDev d;
     double *buf[2][7];   // ping-pong state: [which][Ex,Hy,psiE,psiH,Dx,P,Pprev]
     int nsteps;          // total steps this grid runs in the current pf_run_* call
+    int snap_interval;   // > 0 (linear modes, single grid): the kernel itself writes Ex of the grid into snap_out[row] after every
+    double *snap_out;    //      absolute step n > 0 with n % snap_interval == 0, row = n / snap_interval < snap_rows (vidMake)
+    int snap_rows;
     int pad;
 };
 enum { S_EX = 0, S_HY, S_PSIE, S_PSIH, S_DX, S_P, S_PP, S_COUNT };
@@ -693,8 +696,33 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
     const CubicConsts *kc = &TG.d.k;
     const int pj0 = M.pj0, pj1 = M.pj1;
     const bool wProbe = __any_sync(0xffffffffu, pj0 >= 0);
+    // snapshot rows (vidMake), linear modes: every warp of a launch that holds a snapshot step runs the loop copy with the
+    // per-step tests.  (The cubic modes have one loop copy only and keep ending a launch at each snapshot step instead: the
+    // test costs their 150-instruction material law 13 %.)
+    int snapS = -1;              // launch-relative step whose result is the next snapshot row
+    bool wSnap = false;
+    if constexpr (!CUB) {
+        const int snapI = TG.snap_interval;
+        if (snapI > 0) {
+            snapS = (snapI - nabs0 % snapI) % snapI;
+            if (nabs0 + snapS == 0) snapS += snapI;
+            wSnap = snapS < ks;
+        }
+    }
 
     auto probes = [&](int s) {   // Solver_Engine.probeSim: Ex after the step
+        if constexpr (!CUB) {
+            if (wSnap && s == snapS) {
+                const int row = (nabs0 + s) / TG.snap_interval;
+                if (row < TG.snap_rows) {
+                    double *__restrict__ out = TG.snap_out + (size_t)row * g.L;
+#pragma unroll
+                    for (int j = 0; j < C; ++j)
+                        if ((M.store >> j) & 1) out[lz0 + j] = ex[j];
+                }
+                snapS += TG.snap_interval;
+            }
+        }
         if (wProbe && pj0 >= 0) {
             R v = R(0);
 #pragma unroll
@@ -751,7 +779,7 @@ __device__ __forceinline__ void tile_body(const TileGrid &TG, const TileShared<R
         }
     };
     // (the cubic material law dwarfs those tests and is large: one copy of its loop only)
-    if (CUB || K.wSrc || wProbe) time_loop(std::true_type{});
+    if (CUB || K.wSrc || wProbe || wSnap) time_loop(std::true_type{});
     else time_loop(std::false_type{});
 
     // ---- store interior ---------------------------------------------------------------------------
@@ -1257,7 +1285,17 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
              cudaStream_t st)
 {
     if (n <= 0) return PF_OK;
-    if (k_block <= 0) k_block = TILE_KDEF;
+    if (k_block <= 0) {
+        // default: TILE_KDEF; but a batch whose tiles all fit the machine at once (a single run: 12-15 tiles) is bound by step
+        // latency and by the ~9 us a launch costs whatever it holds, not by the halo's redundant cells: longest blocks then
+        k_block = TILE_KDEF;
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) {
+            long long nt = 0;
+            for (int m = 0; m < n; ++m) nt += (grids[m].L + (TILE_CELLS - 2 * TILE_KMAX) - 1) / (TILE_CELLS - 2 * TILE_KMAX);
+            if (nt <= sms) k_block = TILE_KMAX;
+        }
+    }
     if (k_block > TILE_KMAX) k_block = TILE_KMAX;
     for (int m = 0; m < n; ++m) {
         int rc = tile_supported(grids[m], mode);
@@ -1298,10 +1336,23 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
             }
         }
         t.nsteps = nsteps[m];
+        t.snap_interval = 0;
+        t.snap_out = nullptr;
+        t.snap_rows = 0;
         t.pad = 0;
         max_steps = std::max(max_steps, nsteps[m]);
         int ntile = (g.L + W - 1) / W;
         for (int i = 0; i < ntile; ++i) ht.push_back(TileDesc{m, i * W - halo});
+    }
+    // snapshot rows (n == 1 only).  Linear modes: written by the kernel at the step they belong to, so the run is cut into the
+    // same k-step launches as one without; cubic modes: a launch ends at every snapshot step and the row is copied out.
+    const bool snaps_any = snap_out && snap_interval > 0 && n == 1;
+    const bool snaps_in_kernel = snaps_any && (mode == PF_FREE || mode == PF_LORENTZ);
+    const bool snaps = snaps_any && !snaps_in_kernel;
+    if (snaps_in_kernel) {
+        hg[0].snap_out = snap_out;
+        hg[0].snap_interval = snap_interval;
+        hg[0].snap_rows = snap_rows;
     }
     TileGrid *dg = (TileGrid *)(sbase + plan.off_grids);
     TileDesc *dt = (TileDesc *)(sbase + plan.off_tiles);
@@ -1311,7 +1362,6 @@ int tile_run(const PfGrid *grids, int n, int mode, int do_pol, int n0, const int
     // reads only those; the copy-back below moves exactly those cells, so the scratch buffer needs no seeding.
 
     const bool wide = mostly_interior(grids, n);
-    const bool snaps = snap_out && snap_interval > 0 && n == 1;
     const int cls_c = tile_c_for(mode, fma, wide);
     {
         int rc = tile_classify(cls_c, (int)ht.size(), dg, dt, halo, st);
@@ -1442,6 +1492,9 @@ int tile_block(const PfGrid *src, const PfGrid *dst, int n, int mode, int do_pol
             t.buf[1][a] = a1[a];
         }
         t.nsteps = 1 << 30;   // the step count of a block launch is the kernel's ksteps argument
+        t.snap_interval = 0;
+        t.snap_out = nullptr;
+        t.snap_rows = 0;
         t.pad = 0;
         int ntile = (src[m].L + W - 1) / W;
         for (int i = 0; i < ntile; ++i) (tile_is_edge(src[m], i * W - halo, halo) ? ht : inner).push_back(TileDesc{m, i * W - halo});

@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for v in prev default prev default; do
+  if [ $v = default ]; then unset PYFDTD_B200_LIB; else export PYFDTD_B200_LIB=$PWD/py-fdtd_pic_b200/variants/lib_$v.so; fi
+  echo "== $v"
+  timeout 300 python tools/single_run_profile.py 2>&1 | grep -E "Controller seconds|k_tile:" | cut -c1-220
+  timeout 300 python tools/single_run_profile.py free 2>&1 | grep -E "Controller seconds|k_tile:" | cut -c1-220
+  timeout 300 python tools/lorentz_profile.py exact 1024 256 2>&1 | tail -1
+done
