@@ -63,11 +63,12 @@ def SmoothTurnOn(V, P, tempfreq=0):
     """BaseFDTD11.py:104-120 -- sine that is switched off after P.Periods periods."""
     frq = tempfreq if tempfreq != 0 else P.freq_in
     ppw = P.c0 / (frq * P.dz)
-    n = np.arange(P.timeSteps)
-    on = n * P.delT < P.period * P.Periods
+    n = np.arange(P.timeSteps + 1)
+    on = n[:-1] * P.delT < P.period * P.Periods
     w = 2.0 * np.pi / ppw
-    Exs = np.where(on, np.sin(w * (P.courantNo * n)), 0.0)
-    Hys = np.where(on, np.sin(w * (P.courantNo * (n + 1))), 0.0)
+    s = np.sin(w * (P.courantNo * n))          # Hys[n] is the sine of step n + 1: one evaluation serves both tables
+    Exs = np.where(on, s[:-1], 0.0)
+    Hys = np.where(on, s[1:], 0.0)
     return Exs, Hys
 
 
@@ -171,7 +172,7 @@ def CPML_ScalingCalc(V, P, C_V, C_P):
 
 def _cpml_cells(P, L):
     pw = int(P.pmlWidth)
-    return list(range(pw)) + list(range(L - pw, L))
+    return np.concatenate([np.arange(0, pw), np.arange(L - pw, L)]).astype(np.int64)
 
 
 def _recursive_conv_coefs(P, sigma, kappa, alpha, cells, per_dz):

@@ -144,7 +144,7 @@ class PassRun:
     -- a default grid is 7-15 tiles, far less than the machine -- overlap."""
 
     def __init__(self, V, P, C_V, C_P, mode, do_pol, Exs, Hys, probe_idx, snapshots=False, n0=0, nsteps=None, stream=None,
-                 stage_tag="stage"):
+                 stage_tag="stage", defer=False):
         torch = nat.require_cuda()
         lib = nat.lib()
         self.torch, self.V, self.C_V, self.P, self.mode = torch, V, C_V, P, mode
@@ -163,7 +163,6 @@ class PassRun:
             scal.update(cE0=canon[0], cE1=canon[1], cH0=canon[2], cH1=canon[3], c2_pml=canon[4])
             flags |= nat.PF_F_CANONICAL
         self.engine = engine
-        self.launches0 = lib.pf_launch_count()
         self.stream = torch.cuda.current_stream() if stream is None else stream
         with torch.cuda.stream(self.stream):
             g = dev.DeviceGrid(L=L, T=T, arrays=arrs, scalars=scal, srcE=np.asarray(Exs) / P.courantNo,
@@ -190,15 +189,31 @@ class PassRun:
                                           int(P.vidInterval) if snap_t is not None else 0, rows if snap_t is not None else 0,
                                           scratch.data_ptr() if scratch is not None else None, sbytes, stream_ptr), "pf_run_pass")
 
-            if mode in ("lorentz", "lorentz_nl") and do_pol and nsteps >= 1:
-                # keep P^{N-2} as well so V.tempTempVarPol / V.tempVarPol end up as the reference leaves them
-                if nsteps > 1:
-                    call(n0, nsteps - 1)
-                self.pprev2 = g.tensor_view("Pprev").clone()
-                call(n0 + nsteps - 1, 1)
-            elif nsteps > 0:
-                call(n0, nsteps)
-        self.launches = lib.pf_launch_count() - self.launches0
+            def enqueue():
+                if mode in ("lorentz", "lorentz_nl") and do_pol and nsteps >= 1:
+                    # keep P^{N-2} as well so V.tempTempVarPol / V.tempVarPol end up as the reference leaves them
+                    if nsteps > 1:
+                        call(n0, nsteps - 1)
+                    self.pprev2 = g.tensor_view("Pprev").clone()
+                    call(n0 + nsteps - 1, 1)
+                elif nsteps > 0:
+                    call(n0, nsteps)
+            self._enqueue = enqueue
+        self.launches = 0
+        if not defer:
+            self.launch()
+
+    def launch(self):
+        """Enqueue the pass's kernels on its stream (done by the constructor unless ``defer``: the state is captured and
+        uploaded at construction, so the host arrays may change before this is called)."""
+        if self._enqueue is None:
+            return
+        lib = nat.lib()
+        n_before = lib.pf_launch_count()
+        with self.torch.cuda.stream(self.stream):
+            self._enqueue()
+        self._enqueue = None
+        self.launches = lib.pf_launch_count() - n_before
 
     def finish(self, write_state=True):
         """Wait for the pass, return its probe traces [len(probe_idx), timeSteps]; with write_state the final fields go back
@@ -297,11 +312,12 @@ def _two_pass(V, P, C_V, C_P, probeReadFinishBe, probeReadStartAf, lorentz):
     side.wait_stream(torch.cuda.current_stream())
     C_V, Exs, Hys = prepare_pass(V, P, C_V, C_P, lorentz)
     V.test = 0
-    run0 = PassRun(V, P, C_V, C_P, mode, False, Exs, Hys, [P.x1Loc], stream=side, stage_tag="stage0")
+    run0 = PassRun(V, P, C_V, C_P, mode, False, Exs, Hys, [P.x1Loc], stream=side, stage_tag="stage0", defer=True)
     C_V, Exs, Hys = prepare_pass(V, P, C_V, C_P, lorentz)
     V.test = 0
     atten = list(atten_probe_cells(V, P)) if P.atten else []
     run1 = PassRun(V, P, C_V, C_P, mode, lorentz, Exs, Hys, [P.x2Loc] + atten, snapshots=True)
+    run0.launch()          # pass 1 (snapshots, more probes) is the longer one: its kernels are enqueued first
     traces = run0.finish(write_state=False)
     V.x1ColBe = np.where(n <= probeReadFinishBe, traces[0], V.x1ColBe)
     traces = run1.finish()
