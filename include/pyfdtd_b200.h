@@ -251,7 +251,10 @@ int pf_run_pass(const PfGrid *g, int mode, int do_pol, int n0, int nsteps, int e
 /* The same pass over n_grids independent grids (the members of a LoopedSim sweep,
  * MasterController.py:543-563), fused: every launch advances every member by k steps.
  * Members may differ in every field of PfGrid; nsteps[m] gives each member's step count
- * (members that finish early idle).  k_block = steps per launch (0 = library default).          */
+ * (members that finish early idle).  k_block = steps per launch; 0 = library default: 64, or 128 (the
+ * maximum, pf_tile_config) when all tiles of the batch are resident at once (fewer tiles than SMs: such a
+ * run is bound by step latency and launch count, not by the halo's redundant cells).  The results do not
+ * depend on k_block.                                                                                */
 int pf_run_batch(const PfGrid *grids, int n_grids, int mode, int do_pol, int n0, const int *nsteps,
                  int k_block, void *scratch, size_t scratch_bytes, void *stream);
 size_t pf_run_scratch_bytes(const PfGrid *grids, int n_grids, int engine);
